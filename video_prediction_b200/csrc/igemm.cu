@@ -1,0 +1,533 @@
+// Tensor-core implicit-GEMM convolution engine for B200 (sm_100a).
+//
+//   D[pixels, Cout] = sum_taps  A_tap[pixels, Cin] * W_tap[Cin, Cout]          (fwd / dgrad)
+//   dW_tap[Cout, Cin] = sum_pixels dY[pixels, Cout]^T * X_tap[pixels, Cin]     (wgrad)
+//
+// Operands are fp32 in HBM/shared memory and are consumed by tcgen05.mma kind::tf32 with fp32
+// accumulation in TMEM.  Activation tiles are fetched with 5-D TMA boxes straight from the NDHWC
+// tensor: a box of bw x bh x bd x bn output positions is one 128-row (64-row for wgrad) operand
+// tile whose rows are 32 channels = 128 bytes, written by TMA with the 128-byte swizzle the UMMA
+// descriptor expects.  A filter tap is a coordinate shift of the box; TMA zero-fills out-of-bounds
+// rows/channels, which *is* the convolution's zero padding.  Strided convolutions read one of
+// s_d*s_h*s_w "parity" sub-lattices of the input (one tensor map each); transposed convolutions
+// (upsample_conv2d forward, dgrad of strided convs) are split into output phases.
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA
+// issuer, warps 2..5 = epilogue (TMEM -> registers -> bias/activation -> global).
+#include <cstdio>
+#include <cstring>
+#include <algorithm>
+#include <vector>
+
+#include "common.h"
+#include "ptx.cuh"
+
+namespace vp {
+
+constexpr int kMaxTaps = 128;
+constexpr int kMaxMaps = 8;
+constexpr int kStagesFwd = 4;
+constexpr int kStagesWg = 3;
+constexpr int kWgPix = 64;  // pixels (GEMM-K) per wgrad pipeline stage
+
+struct Tap {
+  int8_t map, cd, ch, cw;
+  int32_t wslot;
+};
+
+struct alignas(64) IgemmArgs {
+  CUtensorMap amap[kMaxMaps];  // shifted operand, one map per stride parity
+  CUtensorMap bmap;            // fwd: packed weights (2-D);  wgrad: the un-shifted operand (5-D)
+  int32_t tiles_w, tiles_h, tiles_d, tiles_n;
+  int32_t bw, bh, bd, bn;
+  int32_t kc, n_pad, bn_tile, tmem_cols;
+  int32_t num_phases, splits;
+  int32_t phase_begin[9];
+  int8_t phase_ooff[8][4];
+  int32_t os_d, os_h, os_w;
+  float* out;
+  long long so_n, so_d, so_h, so_w;
+  int32_t out_n, out_d, out_h, out_w, out_c;
+  const float* bias;
+  int32_t act;
+  float alpha;
+  // wgrad only
+  int32_t rows_from_shifted, m_tiles, n_tiles, kpad;
+  Tap taps[kMaxTaps];
+};
+
+__device__ __forceinline__ float apply_act(float v, int act, float alpha) {
+  switch (act) {
+    case VP_ACT_RELU: return fmaxf(v, 0.f);
+    case VP_ACT_LRELU: return fmaxf(alpha * v, v);
+    case VP_ACT_SIGMOID: return 1.f / (1.f + __expf(-v));
+    case VP_ACT_TANH: return tanhf(v);
+    default: return v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// forward / dgrad kernel: one CTA = one (128-pixel tile, BN-column tile, phase, k-split)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(192, 1) igemm_fwd_kernel(const __grid_constant__ IgemmArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ uint64_t full_bar[kStagesFwd], empty_bar[kStagesFwd], tmem_full_bar;
+  __shared__ uint32_t tmem_base_smem;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t stage_bytes = 16384u + static_cast<uint32_t>(a.bn_tile) * 128u;
+
+  // ---- tile decode
+  int mt = blockIdx.x;
+  const int tw = mt % a.tiles_w; mt /= a.tiles_w;
+  const int th = mt % a.tiles_h; mt /= a.tiles_h;
+  const int td = mt % a.tiles_d;
+  const int tn = mt / a.tiles_d;
+  const int x0 = tw * a.bw, y0 = th * a.bh, d0 = td * a.bd, s0 = tn * a.bn;
+  const int n0 = blockIdx.y * a.bn_tile;
+  const int phase = blockIdx.z / a.splits, split = blockIdx.z % a.splits;
+  const int tb = a.phase_begin[phase], te = a.phase_begin[phase + 1];
+  const int total = (te - tb) * a.kc;
+  const int it0 = static_cast<int>(static_cast<long long>(total) * split / a.splits);
+  const int it1 = static_cast<int>(static_cast<long long>(total) * (split + 1) / a.splits);
+  if (it1 <= it0) return;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kStagesFwd; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    mbar_init(&tmem_full_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(&tmem_base_smem, a.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int it = it0; it < it1; ++it) {
+        const int li = it - it0, s = li % kStagesFwd, ph = (li / kStagesFwd) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        const Tap tp = a.taps[tb + it / a.kc];
+        const int kci = it % a.kc;
+        uint8_t* As = smem + s * stage_bytes;
+        uint8_t* Bs = As + 16384;
+        mbar_expect_tx(&full_bar[s], stage_bytes);
+        tma_load_5d(As, &a.amap[tp.map], &full_bar[s], kci * 32, x0 + tp.cw, y0 + tp.ch, d0 + tp.cd, s0);
+        tma_load_2d(Bs, &a.bmap, &full_bar[s], kci * 32, tp.wslot * a.n_pad + n0);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_tf32(128, a.bn_tile, 0, 0);
+      for (int it = it0; it < it1; ++it) {
+        const int li = it - it0, s = li % kStagesFwd, ph = (li / kStagesFwd) & 1;
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(smem + s * stage_bytes);
+        const uint32_t b_addr = a_addr + 16384;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint64_t ad = make_smem_desc(a_addr + k * 32, 16, 1024, 0);
+          const uint64_t bd = make_smem_desc(b_addr + k * 32, 16, 1024, 0);
+          umma_tf32(tmem_base, ad, bd, idesc, (li > 0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit(&empty_bar[s]);
+      }
+      umma_commit(&tmem_full_bar);
+    }
+    __syncwarp();
+  } else {
+    // ---- epilogue: warp w owns TMEM lanes 32*(w%4)..+31, thread <-> one output pixel
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    int r = row;
+    const int lw = r % a.bw; r /= a.bw;
+    const int lh = r % a.bh; r /= a.bh;
+    const int ld = r % a.bd;
+    const int ln = r / a.bd;
+    const int ow = (x0 + lw) * a.os_w + a.phase_ooff[phase][2];
+    const int oh = (y0 + lh) * a.os_h + a.phase_ooff[phase][1];
+    const int od = (d0 + ld) * a.os_d + a.phase_ooff[phase][0];
+    const int on = s0 + ln;
+    const bool rvalid = (ow < a.out_w) && (oh < a.out_h) && (od < a.out_d) && (on < a.out_n);
+    float* orow = a.out + on * a.so_n + od * a.so_d + oh * a.so_h + ow * a.so_w;
+    const bool add_bias = (a.bias != nullptr) && (split == 0);
+    mbar_wait(&tmem_full_bar, 0);
+    tc_fence_after();
+    for (int c0 = 0; c0 < a.bn_tile; c0 += 16) {
+      float v[16];
+      __syncwarp();
+      tmem_ld16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c0, v);
+      const int col0 = n0 + c0;
+      if (rvalid && col0 < a.out_c) {
+        if (add_bias) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) if (col0 + j < a.out_c) v[j] += __ldg(a.bias + col0 + j);
+        }
+        if (a.splits > 1) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) if (col0 + j < a.out_c) atomicAdd(orow + col0 + j, v[j]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = apply_act(v[j], a.act, a.alpha);
+          if (col0 + 16 <= a.out_c) {
+            float4* o4 = reinterpret_cast<float4*>(orow + col0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) o4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) if (col0 + j < a.out_c) orow[col0 + j] = v[j];
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, a.tmem_cols);
+}
+
+// ------------------------------------------------------------------------------------------------
+// wgrad kernel: one CTA = (128 dy-channels x up-to-128 x-channels, one tap, a range of pixel boxes)
+// Both operands are MN-major (channel-contiguous) 64-pixel boxes; GEMM-K = pixels.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(192, 1) igemm_wgrad_kernel(const __grid_constant__ IgemmArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ uint64_t full_bar[kStagesWg], empty_bar[kStagesWg], tmem_full_bar;
+  __shared__ uint32_t tmem_base_smem;
+  constexpr uint32_t kSub = kWgPix * 128;  // bytes of one 32-channel sub-tile
+  constexpr uint32_t kStage = 8 * kSub;    // 4 A sub-tiles + up to 4 B sub-tiles
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int mtile = blockIdx.x % a.m_tiles, ntile = blockIdx.x / a.m_tiles;
+  const int m0 = mtile * 128;                     // dy channel (row) origin
+  const int c0 = ntile * 128;                     // x channel (col) origin
+  const int nb = min(4, a.kc - ntile * 4);        // 32-channel boxes of x in this tile
+  const Tap tp = a.taps[blockIdx.y];
+  const int total = a.tiles_w * a.tiles_h * a.tiles_d * a.tiles_n;
+  const int it0 = static_cast<int>(static_cast<long long>(total) * blockIdx.z / a.splits);
+  const int it1 = static_cast<int>(static_cast<long long>(total) * (blockIdx.z + 1) / a.splits);
+  if (it1 <= it0) return;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kStagesWg; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    mbar_init(&tmem_full_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(&tmem_base_smem, 128);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int it = it0; it < it1; ++it) {
+        const int li = it - it0, s = li % kStagesWg, ph = (li / kStagesWg) & 1;
+        int mt = it;
+        const int tw = mt % a.tiles_w; mt /= a.tiles_w;
+        const int th = mt % a.tiles_h; mt /= a.tiles_h;
+        const int td = mt % a.tiles_d;
+        const int tn = mt / a.tiles_d;
+        const int x0 = tw * a.bw, y0 = th * a.bh, d0 = td * a.bd, s0 = tn * a.bn;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        uint8_t* As = smem + s * kStage;
+        uint8_t* Bs = As + 4 * kSub;
+        mbar_expect_tx(&full_bar[s], (4 + nb) * kSub);
+        // rows (A) come from dy, cols (B) from x; exactly one of them is the tap-shifted operand
+        for (int i = 0; i < 4; ++i) {
+          if (a.rows_from_shifted)
+            tma_load_5d(As + i * kSub, &a.amap[tp.map], &full_bar[s], m0 + 32 * i, x0 + tp.cw, y0 + tp.ch,
+                        d0 + tp.cd, s0);
+          else
+            tma_load_5d(As + i * kSub, &a.bmap, &full_bar[s], m0 + 32 * i, x0, y0, d0, s0);
+        }
+        for (int j = 0; j < nb; ++j) {
+          if (a.rows_from_shifted)
+            tma_load_5d(Bs + j * kSub, &a.bmap, &full_bar[s], c0 + 32 * j, x0, y0, d0, s0);
+          else
+            tma_load_5d(Bs + j * kSub, &a.amap[tp.map], &full_bar[s], c0 + 32 * j, x0 + tp.cw, y0 + tp.ch,
+                        d0 + tp.cd, s0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_tf32(128, 32 * nb, 1, 1);
+      for (int it = it0; it < it1; ++it) {
+        const int li = it - it0, s = li % kStagesWg, ph = (li / kStagesWg) & 1;
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(smem + s * kStage);
+        const uint32_t b_addr = a_addr + 4 * kSub;
+#pragma unroll
+        for (int k = 0; k < kWgPix / 8; ++k) {
+          const uint64_t ad = make_smem_desc(a_addr + k * 1024, kSub, 1024, 0);
+          const uint64_t bd = make_smem_desc(b_addr + k * 1024, kSub, 1024, 0);
+          umma_tf32(tmem_base, ad, bd, idesc, (li > 0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit(&empty_bar[s]);
+      }
+      umma_commit(&tmem_full_bar);
+    }
+    __syncwarp();
+  } else {
+    const int q = warp & 3;
+    const int row = m0 + q * 32 + lane;
+    const bool rvalid = row < a.n_pad;
+    float* orow = a.out + (static_cast<long long>(tp.wslot) * a.n_pad + row) * a.kpad + c0;
+    mbar_wait(&tmem_full_bar, 0);
+    tc_fence_after();
+    for (int cc = 0; cc < 32 * nb; cc += 16) {
+      float v[16];
+      __syncwarp();
+      tmem_ld16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + cc, v);
+      if (rvalid) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) atomicAdd(orow + cc + j, v[j]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 128);
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      return nullptr;
+    fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+static int floor_pow2(int v) { int p = 1; while (p * 2 <= v) p *= 2; return p; }
+static int ceil_div(int a, int b) { return (a + b - 1) / b; }
+static int pos_mod(int a, int b) { int r = a % b; return r < 0 ? r + b : r; }
+static int floor_div(int a, int b) { return (a - pos_mod(a, b)) / b; }
+
+// 5-D map over the (sd,sh,sw)-strided sub-lattice with parity (qd,qh,qw) of an NDHWC view.
+static int make_act_map(CUtensorMap* m, const vp_tensor* t, int qd, int qh, int qw, int sd, int sh, int sw,
+                        const int box[4] /*w,h,d,n*/) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return set_error("cuTensorMapEncodeTiled entry point not found");
+  const long long cs = t->cstride;
+  float* base = t->ptr + ((static_cast<long long>(qd) * t->h + qh) * t->w + qw) * cs;
+  cuuint64_t dims[5] = {static_cast<cuuint64_t>(t->c), static_cast<cuuint64_t>(std::max(1, ceil_div(t->w - qw, sw))),
+                        static_cast<cuuint64_t>(std::max(1, ceil_div(t->h - qh, sh))),
+                        static_cast<cuuint64_t>(std::max(1, ceil_div(t->d - qd, sd))), static_cast<cuuint64_t>(t->n)};
+  cuuint64_t strides[4] = {static_cast<cuuint64_t>(cs * sw * 4), static_cast<cuuint64_t>(cs * t->w * sh * 4),
+                           static_cast<cuuint64_t>(cs * t->w * t->h * sd * 4),
+                           static_cast<cuuint64_t>(cs * t->w * t->h * t->d * 4)};
+  cuuint32_t boxd[5] = {32, static_cast<cuuint32_t>(box[0]), static_cast<cuuint32_t>(box[1]),
+                        static_cast<cuuint32_t>(box[2]), static_cast<cuuint32_t>(box[3])};
+  cuuint32_t es[5] = {1, 1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, base, dims, strides, boxd, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_error("cuTensorMapEncodeTiled(activation) failed with %d", static_cast<int>(r));
+  return 0;
+}
+
+static int check_tensor(const vp_tensor* t, const char* what) {
+  if (!t || !t->ptr) return set_error("%s: null tensor", what);
+  if ((reinterpret_cast<uintptr_t>(t->ptr) & 15) || (t->cstride & 3))
+    return set_error("%s: pointer must be 16B aligned and cstride a multiple of 4", what);
+  if (t->n < 1 || t->d < 1 || t->h < 1 || t->w < 1 || t->c < 1 || t->c > t->cstride)
+    return set_error("%s: bad dims", what);
+  return 0;
+}
+
+// Fills taps / phases / maps for the tap-shifted tensor `sh_t`; the iteration lattice has dims `lat`.
+static int build_geometry(IgemmArgs& A, const vp_conv_geom* g, const vp_tensor* sh_t, int rows_per_tile,
+                          const int lat_in[4] /*w,h,d,n*/) {
+  int lat[4] = {lat_in[0], lat_in[1], lat_in[2], lat_in[3]};
+  int ntaps = 0;
+  const int K = g->kd * g->kh * g->kw;
+  if (K > kMaxTaps) return set_error("too many filter taps (%d)", K);
+  if (!g->transposed) {
+    if (g->sd * g->sh * g->sw > kMaxMaps) return set_error("stride product too large");
+    A.num_phases = 1;
+    A.phase_begin[0] = 0;
+    A.os_d = A.os_h = A.os_w = 1;
+    std::memset(A.phase_ooff, 0, sizeof(A.phase_ooff));
+    for (int rd = 0; rd < g->kd; ++rd)
+      for (int rh = 0; rh < g->kh; ++rh)
+        for (int rw = 0; rw < g->kw; ++rw) {
+          Tap& t = A.taps[ntaps++];
+          const int qd = pos_mod(rd - g->pd, g->sd), qh = pos_mod(rh - g->ph, g->sh), qw = pos_mod(rw - g->pw, g->sw);
+          t.map = static_cast<int8_t>((qd * g->sh + qh) * g->sw + qw);
+          t.cd = static_cast<int8_t>(floor_div(rd - g->pd, g->sd));
+          t.ch = static_cast<int8_t>(floor_div(rh - g->ph, g->sh));
+          t.cw = static_cast<int8_t>(floor_div(rw - g->pw, g->sw));
+          t.wslot = (rd * g->kh + rh) * g->kw + rw;
+        }
+    A.phase_begin[1] = ntaps;
+  } else {
+    const int P = g->sd * g->sh * g->sw;
+    if (P > 8) return set_error("stride product too large");
+    A.num_phases = P;
+    A.os_d = g->sd; A.os_h = g->sh; A.os_w = g->sw;
+    int p = 0;
+    for (int fd = 0; fd < g->sd; ++fd)
+      for (int fh = 0; fh < g->sh; ++fh)
+        for (int fw = 0; fw < g->sw; ++fw, ++p) {
+          A.phase_begin[p] = ntaps;
+          A.phase_ooff[p][0] = static_cast<int8_t>(fd);
+          A.phase_ooff[p][1] = static_cast<int8_t>(fh);
+          A.phase_ooff[p][2] = static_cast<int8_t>(fw);
+          A.phase_ooff[p][3] = 0;
+          const int r0d = pos_mod(fd + g->pd, g->sd), r0h = pos_mod(fh + g->ph, g->sh), r0w = pos_mod(fw + g->pw, g->sw);
+          for (int rd = r0d; rd < g->kd; rd += g->sd)
+            for (int rh = r0h; rh < g->kh; rh += g->sh)
+              for (int rw = r0w; rw < g->kw; rw += g->sw) {
+                if (ntaps >= kMaxTaps) return set_error("too many taps");
+                Tap& t = A.taps[ntaps++];
+                t.map = 0;
+                t.cd = static_cast<int8_t>((fd + g->pd - rd) / g->sd);   // exact: (f+p-r) is a multiple of s
+                t.ch = static_cast<int8_t>((fh + g->ph - rh) / g->sh);
+                t.cw = static_cast<int8_t>((fw + g->pw - rw) / g->sw);
+                t.wslot = (rd * g->kh + rh) * g->kw + rw;
+              }
+        }
+    A.phase_begin[P] = ntaps;
+    lat[0] = ceil_div(lat[0], g->sw); lat[1] = ceil_div(lat[1], g->sh); lat[2] = ceil_div(lat[2], g->sd);
+  }
+  // box shape: product == rows_per_tile, powers of two, w fastest
+  int rem = rows_per_tile;
+  A.bw = std::min(floor_pow2(lat[0]), rem); rem /= A.bw;
+  A.bh = std::min(floor_pow2(lat[1]), rem); rem /= A.bh;
+  A.bd = std::min(floor_pow2(lat[2]), rem); rem /= A.bd;
+  A.bn = rem;
+  A.tiles_w = ceil_div(lat[0], A.bw); A.tiles_h = ceil_div(lat[1], A.bh);
+  A.tiles_d = ceil_div(lat[2], A.bd); A.tiles_n = ceil_div(lat[3], A.bn);
+  const int box[4] = {A.bw, A.bh, A.bd, A.bn};
+  if (!g->transposed) {
+    for (int qd = 0; qd < g->sd; ++qd)
+      for (int qh = 0; qh < g->sh; ++qh)
+        for (int qw = 0; qw < g->sw; ++qw) {
+          int rc = make_act_map(&A.amap[(qd * g->sh + qh) * g->sw + qw], sh_t, qd, qh, qw, g->sd, g->sh, g->sw, box);
+          if (rc) return rc;
+        }
+  } else {
+    int rc = make_act_map(&A.amap[0], sh_t, 0, 0, 0, 1, 1, 1, box);
+    if (rc) return rc;
+  }
+  return 0;
+}
+
+static int next_pow2_cols(int n) { int c = 32; while (c < n) c *= 2; return c; }
+
+}  // namespace vp
+
+using namespace vp;
+
+extern "C" int vp_conv_igemm(const vp_tensor* in, const vp_conv_geom* g, const float* wpacked, int n_pad, int kc,
+                             const vp_tensor* out, const float* bias, int act, float alpha, int split_k,
+                             vp_stream_t stream) {
+  if (check_tensor(in, "vp_conv_igemm(in)") || check_tensor(out, "vp_conv_igemm(out)")) return -1;
+  if (!g || !wpacked) return set_error("vp_conv_igemm: null argument");
+  if (n_pad % 16 || n_pad < 16) return set_error("vp_conv_igemm: n_pad must be a positive multiple of 16");
+  if (kc < 1 || kc * 32 < in->c) return set_error("vp_conv_igemm: kc*32 must cover in->c");
+  if (out->c > n_pad) return set_error("vp_conv_igemm: out->c exceeds n_pad");
+  if (in->n != out->n) return set_error("vp_conv_igemm: batch mismatch");
+  if (split_k < 1) split_k = 1;
+  if (split_k > 1 && act != VP_ACT_NONE) return set_error("vp_conv_igemm: split_k needs act NONE");
+  static IgemmArgs A;  // large POD; host-side scratch (calls are serialized by the Python GIL / caller)
+  std::memset(&A, 0, sizeof(A));
+  const int lat[4] = {out->w, out->h, out->d, out->n};
+  if (build_geometry(A, g, in, 128, lat)) return -1;
+  A.kc = kc; A.n_pad = n_pad;
+  A.bn_tile = n_pad <= 256 ? n_pad : (n_pad % 256 == 0 ? 256 : (n_pad % 128 == 0 ? 128 : 0));
+  if (n_pad >= 256 && n_pad % 128 == 0) A.bn_tile = 128;  // more CTAs for the small-M ConvLSTM GEMMs
+  if (A.bn_tile == 0) return set_error("vp_conv_igemm: unsupported n_pad %d", n_pad);
+  A.tmem_cols = next_pow2_cols(A.bn_tile);
+  int min_iters = 1 << 30;
+  for (int p = 0; p < A.num_phases; ++p) min_iters = std::min(min_iters, (A.phase_begin[p + 1] - A.phase_begin[p]) * kc);
+  if (min_iters < 1) return set_error("vp_conv_igemm: a phase has no taps");
+  A.splits = std::min(split_k, min_iters);
+  A.out = out->ptr;
+  A.so_w = out->cstride; A.so_h = A.so_w * out->w; A.so_d = A.so_h * out->h; A.so_n = A.so_d * out->d;
+  A.out_n = out->n; A.out_d = out->d; A.out_h = out->h; A.out_w = out->w; A.out_c = out->c;
+  A.bias = bias; A.act = act; A.alpha = alpha;
+  // weights: 2-D [slots*n_pad rows][kc*32]
+  {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return set_error("cuTensorMapEncodeTiled entry point not found");
+    const int slots = g->kd * g->kh * g->kw;
+    cuuint64_t dims[2] = {static_cast<cuuint64_t>(kc) * 32, static_cast<cuuint64_t>(slots) * n_pad};
+    cuuint64_t strides[1] = {static_cast<cuuint64_t>(kc) * 128};
+    cuuint32_t box[2] = {32, static_cast<cuuint32_t>(A.bn_tile)};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = enc(&A.bmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(wpacked), dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_error("cuTensorMapEncodeTiled(weights) failed with %d", static_cast<int>(r));
+  }
+  const size_t smem = static_cast<size_t>(kStagesFwd) * (16384 + A.bn_tile * 128) + 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(igemm_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
+      return set_error("cudaFuncSetAttribute(igemm_fwd_kernel) failed: %s", cudaGetErrorString(cudaGetLastError()));
+    attr_set = true;
+  }
+  dim3 grid(A.tiles_w * A.tiles_h * A.tiles_d * A.tiles_n, n_pad / A.bn_tile, A.num_phases * A.splits);
+  igemm_fwd_kernel<<<grid, 192, smem, static_cast<cudaStream_t>(stream)>>>(A);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error("igemm_fwd_kernel launch failed: %s", cudaGetErrorString(e));
+  return 0;
+}
+
+extern "C" int vp_conv_wgrad(const vp_tensor* x, const vp_tensor* dy, const vp_conv_geom* g, float* dwpacked,
+                             int n_pad, int kc, int split_k, vp_stream_t stream) {
+  if (check_tensor(x, "vp_conv_wgrad(x)") || check_tensor(dy, "vp_conv_wgrad(dy)")) return -1;
+  if (!g || !dwpacked) return set_error("vp_conv_wgrad: null argument");
+  if (n_pad % 16 || dy->c > n_pad || kc * 32 < x->c) return set_error("vp_conv_wgrad: bad n_pad / kc");
+  static IgemmArgs A;
+  std::memset(&A, 0, sizeof(A));
+  // conv:  dW[r] += sum_o dy[o]^T x[s*o+r-p]   (x shifted, lattice = dy)
+  // tconv: dW[r] += sum_o dy[s*o+r-p]^T x[o]   (dy shifted, lattice = x); as a gather this is a
+  //        plain (non-transposed) strided access pattern, so build the geometry with transposed=0.
+  vp_conv_geom gg = *g;
+  gg.transposed = 0;
+  const vp_tensor* shifted = g->transposed ? dy : x;
+  const vp_tensor* plain = g->transposed ? x : dy;
+  const int lat[4] = {plain->w, plain->h, plain->d, plain->n};
+  if (build_geometry(A, &gg, shifted, kWgPix, lat)) return -1;
+  const int box[4] = {A.bw, A.bh, A.bd, A.bn};
+  if (make_act_map(&A.bmap, plain, 0, 0, 0, 1, 1, 1, box)) return -1;
+  A.rows_from_shifted = g->transposed ? 1 : 0;
+  A.kc = kc; A.n_pad = n_pad; A.kpad = kc * 32;
+  A.m_tiles = ceil_div(n_pad, 128);
+  A.n_tiles = ceil_div(kc, 4);
+  const int total = A.tiles_w * A.tiles_h * A.tiles_d * A.tiles_n;
+  A.splits = std::max(1, std::min(split_k, total));
+  A.out = dwpacked;
+  const int ntaps = A.phase_begin[1];
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(igemm_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
+      return set_error("cudaFuncSetAttribute(igemm_wgrad_kernel) failed");
+    attr_set = true;
+  }
+  const size_t smem = static_cast<size_t>(kStagesWg) * 8 * kWgPix * 128 + 1024;
+  dim3 grid(A.m_tiles * A.n_tiles, ntaps, A.splits);
+  igemm_wgrad_kernel<<<grid, 192, smem, static_cast<cudaStream_t>(stream)>>>(A);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error("igemm_wgrad_kernel launch failed: %s", cudaGetErrorString(e));
+  return 0;
+}
