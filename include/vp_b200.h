@@ -85,6 +85,59 @@ int vp_pack_weights(const float* w, int kd, int kh, int kw, int ci_ref, int co, 
 int vp_unpack_wgrad(const float* dwpacked, int kd, int kh, int kw, int ci_ref, int co, int kind,
                     const int32_t* cmap, int ci_int, float* dw, int n_pad, int kc, vp_stream_t stream);
 
+
+/* ---- HBM-bound kernels --------------------------------------------------------------------------
+ * "positions" = product of the spatial dims of one sample; x[(n*positions + p)*cstride + ch]. */
+
+/* fused_instance_norm (+ activation), layers/normalization.py:34-196 + savp_model.py:463-464:
+ * y = act(gamma*(x-mean)*rsqrt(var_biased+eps)+beta), stats over `positions` per (sample, channel).
+ * stats (optional): [n][c][2] = (mean, rstd) kept for the backward pass. c % 4 == 0. */
+int vp_inorm_act(const float* x, int x_cstride, float* y, int y_cstride, int n, int positions, int c,
+                 const float* gamma, const float* beta, float eps, int act, float alpha, float* stats,
+                 vp_stream_t stream);
+
+/* BasicConv2DLSTMCell gate math, rnn_ops.py:148-165 (instance norm over the 4F concat, i/j/f/o
+ * split, forget bias, instance norm of new_c, h = tanh(c)*sigmoid(o)).  pre: conv output
+ * [n][positions][4*filters] dense; c_prev/c_new: [n][positions][filters] dense.  h is written to
+ * num_h_dst (1..3) channel slices h_dst[i] with channel strides h_cstride[i].
+ * stats1 [n][4F][2], stats2 [n][F][2] optional. positions <= 1024, filters % 4 == 0. */
+int vp_lstm_gates_fwd(const float* pre, int n, int positions, int filters, const float* c_prev,
+                      const float* gamma1, const float* beta1, const float* gamma2, const float* beta2,
+                      float forget_bias, float eps, float* c_new, float* const* h_dst, const int* h_cstride,
+                      int num_h_dst, float* stats1, float* stats2, vp_stream_t stream);
+
+/* ops.tile_concat (ops.py:968-1006): dst[n][p][0..c) = vec[n][0..c) for every position p. */
+int vp_broadcast_channels(const float* vec, int vec_stride, float* dst, int dst_cstride, int n, int positions,
+                          int c, vp_stream_t stream);
+/* channel-slice copy: dst[r][0..c) = src[r][0..c) for r < rows. */
+int vp_copy_channels(const float* src, int src_cstride, float* dst, int dst_cstride, long long rows, int c,
+                     vp_stream_t stream);
+/* tf.where(ground_truth[t], images, gen_image) (savp_model.py:406): out[i] = sel[i] ? a[i] : b[i], rows of per_row floats. */
+int vp_select_rows(const int32_t* sel, const float* a, const float* b, float* out, int n, long long per_row,
+                   vp_stream_t stream);
+/* global average pool (networks.py:30-31): y[n][c] = mean_p x[n][p][c]. */
+int vp_avgpool(const float* x, int x_cstride, float* y, int n, int positions, int c, vp_stream_t stream);
+/* ops.dense (ops.py:5-16): y[b][j] = sum_k x[b][k] w[k][j] / (*inv_scale) + bias[j].
+ * k_splits > 1 accumulates atomically into a zero-filled y. */
+int vp_dense_fwd(const float* x, int x_stride, const float* w, const float* bias, const float* inv_scale, float* y,
+                 int y_stride, int b, int k, int j, int k_splits, vp_stream_t stream);
+/* tf.nn.rnn_cell.LSTMCell elementwise part (savp_model.py:354-362); gates [b][4*units] (i,j,f,o). */
+int vp_lstm_cell_fwd(const float* gates, const float* c_prev, float* c_new, float* h_new, int b, int units,
+                     float forget_bias, vp_stream_t stream);
+/* savp_model.py:49,712: lss <- clip(lss,-10,10); z = mu + sqrt(exp(lss))*eps. */
+int vp_sample_z(const float* mu, float* log_sigma_sq, const float* eps, float* z, int total, vp_stream_t stream);
+/* savp_model.py:551-559: +identity kernel, relu(.-1e-12)+1e-12, normalise over the kh*kw taps.
+ * raw/out: [b][kh*kw][nk]. */
+int vp_cdna_kernel_norm(const float* raw, float* out, int b, int kh, int kw, int nk, vp_stream_t stream);
+/* apply_cdna_kernels (savp_model.py:893-923) + the two background layers (:581-584): image and
+ * first_image are [n][h][w][4] (colour channels padded to 4); writes nk+2 float4 slots per pixel at
+ * layers[(n*h*w+p)*layers_cstride + 4*l]. */
+int vp_cdna_apply(const float* image, const float* first_image, const float* kernels, float* layers,
+                  int layers_cstride, int n, int h, int w, int kh, int kw, int nk, vp_stream_t stream);
+/* masks = softmax(logits) (savp_model.py:634); gen_image = sum_l layer_l * mask_l (:645-646). */
+int vp_composite(const float* logits, int logits_cstride, const float* layers, int layers_cstride, float* masks,
+                 int masks_cstride, float* gen_image, long long positions, int num_layers, vp_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

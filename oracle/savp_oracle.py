@@ -177,7 +177,7 @@ def upsampled_kernel(kernel):
     """ops.py:698-704: FULL cross-correlation of the 4x4 bilinear kernel with the conv kernel.
     Returns kernel_up [6,6,Cout,Cin] (conv2d_transpose filter layout)."""
     kh, kw, ci, co = kernel.shape
-    b2 = torch.tensor(bilinear_kernel_2x(), dtype=kernel.dtype)
+    b2 = torch.tensor(bilinear_kernel_2x(), dtype=kernel.dtype, device=kernel.device)
     kt = kernel.permute(0, 1, 3, 2).reshape(kh, kw, 1, co * ci)       # kernel_reshaped
     up = conv2d_tf(b2[None, :, :, None], kt, padding='FULL')           # [1,6,6,co*ci]
     return up.reshape(up.shape[1], up.shape[2], co, ci)
@@ -452,7 +452,7 @@ def savp_cell_step(V, hp, scope, t, inp, first_image, states, ground_truth_t, ta
     dk = V.get(scope + '/cdna_kernels/dense/kernel', (flat.shape[1], kh * kw * nk))
     db = V.get(scope + '/cdna_kernels/dense/bias', (kh * kw * nk,), 'zeros')
     kernels = dense(flat, dk, db).reshape(B, kh, kw, nk)
-    kernels = kernels + torch.tensor(identity_kernel((kh, kw)), dtype=kernels.dtype)[None, :, :, None]
+    kernels = kernels + torch.tensor(identity_kernel((kh, kw)), dtype=kernels.dtype, device=kernels.device)[None, :, :, None]
     kernels = torch.relu(kernels - RELU_SHIFT) + RELU_SHIFT                  # :558
     kernels = kernels / kernels.sum(dim=(1, 2), keepdim=True)                # :559
 

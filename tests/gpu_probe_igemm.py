@@ -217,7 +217,10 @@ def main():
         print('VERDICT %s %s' % (name, 'PASS' if rel < 2e-3 else 'FAIL'))
         return
     results = {}
-    for name in CASES:
+    cases = CASES
+    if '--only' in sys.argv:
+        cases = sys.argv[sys.argv.index('--only') + 1].split(',')
+    for name in cases:
         t0 = time.time()
         try:
             r = subprocess.run([sys.executable, os.path.abspath(__file__), '--case', name], capture_output=True,

@@ -265,8 +265,10 @@ __global__ void __launch_bounds__(192, 1) igemm_wgrad_kernel(const __grid_consta
         const uint32_t b_addr = a_addr + 4 * kSub;
 #pragma unroll
         for (int k = 0; k < kWgPix / 8; ++k) {
-          const uint64_t ad = make_smem_desc(a_addr + k * 1024, kSub, 1024, 0);
-          const uint64_t bd = make_smem_desc(b_addr + k * 1024, kSub, 1024, 0);
+          // MN-major tf32: 32-channel x 4-pixel atoms (512 B) with the 32-byte-granular 128B swizzle;
+          // LBO = stride between 32-channel groups, SBO = stride between 4-pixel groups.
+          const uint64_t ad = make_smem_desc(a_addr + k * 1024, kSub, 512, 0, 1);
+          const uint64_t bd = make_smem_desc(b_addr + k * 1024, kSub, 512, 0, 1);
           umma_tf32(tmem_base, ad, bd, idesc, (li > 0 || k > 0) ? 1u : 0u);
         }
         umma_commit(&empty_bar[s]);
@@ -323,7 +325,7 @@ static int floor_div(int a, int b) { return (a - pos_mod(a, b)) / b; }
 
 // 5-D map over the (sd,sh,sw)-strided sub-lattice with parity (qd,qh,qw) of an NDHWC view.
 static int make_act_map(CUtensorMap* m, const vp_tensor* t, int qd, int qh, int qw, int sd, int sh, int sw,
-                        const int box[4] /*w,h,d,n*/) {
+                        const int box[4] /*w,h,d,n*/, bool mn_major = false) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return set_error("cuTensorMapEncodeTiled entry point not found");
   const long long cs = t->cstride;
@@ -338,7 +340,8 @@ static int make_act_map(CUtensorMap* m, const vp_tensor* t, int qd, int qh, int 
                         static_cast<cuuint32_t>(box[2]), static_cast<cuuint32_t>(box[3])};
   cuuint32_t es[5] = {1, 1, 1, 1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, base, dims, strides, boxd, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return set_error("cuTensorMapEncodeTiled(activation) failed with %d", static_cast<int>(r));
   return 0;
 }
@@ -354,7 +357,7 @@ static int check_tensor(const vp_tensor* t, const char* what) {
 
 // Fills taps / phases / maps for the tap-shifted tensor `sh_t`; the iteration lattice has dims `lat`.
 static int build_geometry(IgemmArgs& A, const vp_conv_geom* g, const vp_tensor* sh_t, int rows_per_tile,
-                          const int lat_in[4] /*w,h,d,n*/) {
+                          const int lat_in[4] /*w,h,d,n*/, bool mn_major = false) {
   int lat[4] = {lat_in[0], lat_in[1], lat_in[2], lat_in[3]};
   int ntaps = 0;
   const int K = g->kd * g->kh * g->kw;
@@ -420,11 +423,11 @@ static int build_geometry(IgemmArgs& A, const vp_conv_geom* g, const vp_tensor* 
     for (int qd = 0; qd < g->sd; ++qd)
       for (int qh = 0; qh < g->sh; ++qh)
         for (int qw = 0; qw < g->sw; ++qw) {
-          int rc = make_act_map(&A.amap[(qd * g->sh + qh) * g->sw + qw], sh_t, qd, qh, qw, g->sd, g->sh, g->sw, box);
+          int rc = make_act_map(&A.amap[(qd * g->sh + qh) * g->sw + qw], sh_t, qd, qh, qw, g->sd, g->sh, g->sw, box, mn_major);
           if (rc) return rc;
         }
   } else {
-    int rc = make_act_map(&A.amap[0], sh_t, 0, 0, 0, 1, 1, 1, box);
+    int rc = make_act_map(&A.amap[0], sh_t, 0, 0, 0, 1, 1, 1, box, mn_major);
     if (rc) return rc;
   }
   return 0;
@@ -481,7 +484,7 @@ extern "C" int vp_conv_igemm(const vp_tensor* in, const vp_conv_geom* g, const f
   const size_t smem = static_cast<size_t>(kStagesFwd) * (16384 + A.bn_tile * 128) + 1024;
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(igemm_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
+    if (cudaFuncSetAttribute(igemm_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kStagesFwd * (16384 + 256 * 128) + 1024) != cudaSuccess)
       return set_error("cudaFuncSetAttribute(igemm_fwd_kernel) failed: %s", cudaGetErrorString(cudaGetLastError()));
     attr_set = true;
   }
@@ -507,9 +510,9 @@ extern "C" int vp_conv_wgrad(const vp_tensor* x, const vp_tensor* dy, const vp_c
   const vp_tensor* shifted = g->transposed ? dy : x;
   const vp_tensor* plain = g->transposed ? x : dy;
   const int lat[4] = {plain->w, plain->h, plain->d, plain->n};
-  if (build_geometry(A, &gg, shifted, kWgPix, lat)) return -1;
+  if (build_geometry(A, &gg, shifted, kWgPix, lat, true)) return -1;
   const int box[4] = {A.bw, A.bh, A.bd, A.bn};
-  if (make_act_map(&A.bmap, plain, 0, 0, 0, 1, 1, 1, box)) return -1;
+  if (make_act_map(&A.bmap, plain, 0, 0, 0, 1, 1, 1, box, true)) return -1;
   A.rows_from_shifted = g->transposed ? 1 : 0;
   A.kc = kc; A.n_pad = n_pad; A.kpad = kc * 32;
   A.m_tiles = ceil_div(n_pad, 128);
@@ -520,8 +523,8 @@ extern "C" int vp_conv_wgrad(const vp_tensor* x, const vp_tensor* dy, const vp_c
   const int ntaps = A.phase_begin[1];
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(igemm_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
-      return set_error("cudaFuncSetAttribute(igemm_wgrad_kernel) failed");
+    if (cudaFuncSetAttribute(igemm_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kStagesWg * 8 * kWgPix * 128 + 1024) != cudaSuccess)
+      return set_error("cudaFuncSetAttribute(igemm_wgrad_kernel) failed: %s", cudaGetErrorString(cudaGetLastError()));
     attr_set = true;
   }
   const size_t smem = static_cast<size_t>(kStagesWg) * 8 * kWgPix * 128 + 1024;

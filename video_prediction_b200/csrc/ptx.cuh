@@ -116,15 +116,17 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
 //  bits [0,14)  start address >> 4      bits [16,30) leading byte offset >> 4
 //  bits [32,46) stride byte offset >> 4 bits [46,48) version = 1
 //  bits [49,52) base offset             bits [61,64) layout: 0 none, 2 = 128B swizzle
+//  layout_type: 2 = SWIZZLE_128B (16-byte atoms; K-major operands), 1 = SWIZZLE_128B_BASE32B (32-byte atoms;
+//  the only layout for MN-major 32-bit (tf32) operands; TMA twin: CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes,
-                                                   uint32_t base_offset) {
+                                                   uint32_t base_offset, uint32_t layout_type = 2) {
   uint64_t d = 0;
   d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
   d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
   d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32;
   d |= static_cast<uint64_t>(1) << 46;
   d |= static_cast<uint64_t>(base_offset & 7) << 49;
-  d |= static_cast<uint64_t>(2) << 61;  // SWIZZLE_128B
+  d |= static_cast<uint64_t>(layout_type & 7) << 61;
   return d;
 }
 // Instruction descriptor for kind::tf32 with fp32 accumulate.

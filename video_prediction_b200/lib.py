@@ -118,3 +118,68 @@ def unpack_wgrad(dwpacked, k, ci_ref, co, kind, dw, n_pad, kc, ci_int=None, cmap
     ci_int = ci_ref if ci_int is None else ci_int
     check(lib().vp_unpack_wgrad(ptr(dwpacked), k[0], k[1], k[2], ci_ref, co, kind, ptr(cmap), ci_int, ptr(dw),
                                 n_pad, kc, stream_ptr()))
+
+
+# ---------------------------------------------------------------------------------- HBM-bound kernels
+def _f(v):
+    return C.c_float(v)
+
+
+def inorm_act(x_addr, x_cs, y_addr, y_cs, n, positions, c, gamma, beta, act=ACT_NONE, alpha=0.0, stats=None, eps=1e-6):
+    check(lib().vp_inorm_act(C.c_void_p(x_addr), x_cs, C.c_void_p(y_addr), y_cs, n, positions, c, ptr(gamma), ptr(beta), _f(eps), act, _f(alpha),
+                             ptr(stats), stream_ptr()))
+
+
+def lstm_gates_fwd(pre, n, positions, filters, c_prev, g1, b1, g2, b2, c_new, h_dsts, stats1=None, stats2=None,
+                   forget_bias=1.0, eps=1e-6):
+    """h_dsts: list of (address:int, cstride:int)."""
+    k = len(h_dsts)
+    pa = (C.c_void_p * k)(*[C.c_void_p(a) for a, _ in h_dsts])
+    sa = (C.c_int * k)(*[s for _, s in h_dsts])
+    check(lib().vp_lstm_gates_fwd(ptr(pre), n, positions, filters, ptr(c_prev), ptr(g1), ptr(b1), ptr(g2), ptr(b2),
+                                  _f(forget_bias), _f(eps), ptr(c_new), pa, sa, k, ptr(stats1), ptr(stats2),
+                                  stream_ptr()))
+
+
+def broadcast_channels(vec, vec_stride, dst_addr, dst_cs, n, positions, c):
+    check(lib().vp_broadcast_channels(ptr(vec), vec_stride, C.c_void_p(dst_addr), dst_cs, n, positions, c, stream_ptr()))
+
+
+def copy_channels(src_addr, src_cs, dst_addr, dst_cs, rows, c):
+    check(lib().vp_copy_channels(C.c_void_p(src_addr), src_cs, C.c_void_p(dst_addr), dst_cs, C.c_longlong(rows), c,
+                                 stream_ptr()))
+
+
+def select_rows(sel, a, b, out, n, per_row):
+    check(lib().vp_select_rows(ptr(sel), ptr(a), ptr(b), ptr(out), n, C.c_longlong(per_row), stream_ptr()))
+
+
+def avgpool(x, x_cs, y, n, positions, c):
+    check(lib().vp_avgpool(ptr(x), x_cs, ptr(y), n, positions, c, stream_ptr()))
+
+
+def dense_fwd(x, x_stride, w, bias, y, y_stride, b, k, j, k_splits=1, inv_scale=None):
+    check(lib().vp_dense_fwd(ptr(x), x_stride, ptr(w), ptr(bias), ptr(inv_scale), ptr(y), y_stride, b, k, j, k_splits,
+                             stream_ptr()))
+
+
+def lstm_cell_fwd(gates, c_prev, c_new, h_new, b, units, forget_bias=1.0):
+    check(lib().vp_lstm_cell_fwd(ptr(gates), ptr(c_prev), ptr(c_new), ptr(h_new), b, units, _f(forget_bias), stream_ptr()))
+
+
+def sample_z(mu, lss, eps, z, total):
+    check(lib().vp_sample_z(ptr(mu), ptr(lss), ptr(eps), ptr(z), total, stream_ptr()))
+
+
+def cdna_kernel_norm(raw, out, b, kh, kw, nk):
+    check(lib().vp_cdna_kernel_norm(ptr(raw), ptr(out), b, kh, kw, nk, stream_ptr()))
+
+
+def cdna_apply(image, first, kernels, layers_addr, layers_cs, n, h, w, kh, kw, nk):
+    check(lib().vp_cdna_apply(ptr(image), ptr(first), ptr(kernels), C.c_void_p(layers_addr), layers_cs, n, h, w, kh, kw, nk,
+                              stream_ptr()))
+
+
+def composite(logits, logits_cs, layers_addr, layers_cs, masks, masks_cs, gen, positions, num_layers):
+    check(lib().vp_composite(ptr(logits), logits_cs, C.c_void_p(layers_addr), layers_cs, ptr(masks), masks_cs, ptr(gen),
+                             C.c_longlong(positions), num_layers, stream_ptr()))

@@ -1,0 +1,710 @@
+"""SAVP model on B200: host-side orchestration of the sm_100a kernels in libvp_b200.so.
+
+Mirrors `SAVPVideoPredictionModel` of the reference (video_prediction/models/savp_model.py:771-855):
+same constructor, same default hparams (:779-822), same deprecated-key handling (:824-846), same
+`build_graph(inputs)` entry and `outputs['gen_images']` (batch-major [B,T-1,H,W,C]).
+
+What differs is everything below that surface: there is no TF graph.  `build_graph` lays the whole
+unroll out in HBM as time-stacked channels-last buffers ([T-1, NB, H, W, C']) whose channel layout
+*is* the concatenation each convolution reads (image | first image | z), (features | z | h_prev),
+(features | skip | z): producers write straight into their consumers' slices, `tile_concat` is a
+broadcast store, and the posterior and prior unrolls (savp_model.py:730-732, shared weights) run as
+one batch NB = 2B.  All FLOP-carrying ops are tcgen05 implicit GEMMs (csrc/igemm.cu); the rest are
+HBM-bound kernels (csrc/elementwise.cu).  PyTorch only owns memory and streams.
+"""
+from __future__ import annotations
+
+import itertools
+from collections import OrderedDict
+
+import numpy as np
+import torch
+
+from .. import lib as L
+from .base_model import VideoPredictionModel
+
+RELU_SHIFT = 1e-12
+
+
+def _ceil4(v):
+    return (v + 3) // 4 * 4
+
+
+class ConcatSpec(object):
+    """Channel layout of a concat buffer: segments (name, valid, alloc); offsets are multiples of 4.
+    `cmap[i]` = index in the reference's concatenated tensor feeding internal channel i, or -1."""
+
+    def __init__(self, segs):
+        self.segs = []
+        off, ref = 0, 0
+        cmap = []
+        for name, valid in segs:
+            alloc = _ceil4(valid)
+            self.segs.append((name, off, valid, alloc))
+            cmap += list(range(ref, ref + valid)) + [-1] * (alloc - valid)
+            off += alloc
+            ref += valid
+        self.cstride = off
+        self.ref_channels = ref
+        self.cmap = cmap
+
+    def off(self, name):
+        for n, o, v, a in self.segs:
+            if n == name:
+                return o
+        raise KeyError(name)
+
+    def valid(self, name):
+        for n, o, v, a in self.segs:
+            if n == name:
+                return v
+        raise KeyError(name)
+
+
+class ConvLayer(object):
+    """One convolution of the path: reference-layout parameters + packed tensor-core weights."""
+
+    def __init__(self, model, wname, bname, k, kind, stride, pad, transposed, spec, co):
+        self.model, self.wname, self.bname = model, wname, bname
+        self.k, self.kind, self.stride, self.pad, self.transposed = k, kind, stride, pad, transposed
+        self.spec, self.co = spec, co
+        self.ci_ref, self.ci_int = spec.ref_channels, spec.cstride
+        if kind == L.WKIND_POOLED:
+            self.ke = (1, k[1] + 1, k[2] + 1)
+        elif kind == L.WKIND_UPSAMPLED:
+            self.ke = (1, k[1] + 3, k[2] + 3)
+        else:
+            self.ke = k
+        self.geom = L.geom(self.ke, stride, pad, transposed)
+        self.cmap = torch.tensor(spec.cmap, dtype=torch.int32, device=model.device)
+        self.wp = None
+        self.n_pad = self.kc = None
+
+    def pack(self):
+        w = self.model.params[self.wname]
+        self.wp, self.n_pad, self.kc = L.pack_weights(w, self.k, self.ci_ref, self.co, self.kind, L.WLAYOUT_FWD,
+                                                      ci_int=self.ci_int, cmap=self.cmap, out=self.wp)
+
+    def fwd(self, x, out, out_off=0, out_c=None, act=L.ACT_NONE, alpha=0.0, split_k=1):
+        """x: stacked buffer [.., h, w, cstride] (4-D or 5-D torch tensor, leading dims folded into n)."""
+        xv = L.tensor_view(x.view((-1,) + tuple(x.shape[-3:])), self.ci_int)
+        ov = L.tensor_view(out.view((-1,) + tuple(out.shape[-3:])), self.co if out_c is None else out_c, out_off)
+        bias = self.model.params[self.bname] if self.bname else None
+        L.conv_igemm(xv, self.geom, self.wp, self.n_pad, self.kc, ov, bias, act, alpha, split_k)
+
+
+class SAVPVideoPredictionModel(VideoPredictionModel):
+    def __init__(self, *args, **kwargs):
+        super(SAVPVideoPredictionModel, self).__init__(*args, **kwargs)
+        self.deterministic = not self.hparams.nz
+        self.device = None
+        self.params = None
+        self.built = False
+
+    # ------------------------------------------------------------------ hparams (savp_model.py:779-846)
+    def get_default_hparams_dict(self):
+        default_hparams = super(SAVPVideoPredictionModel, self).get_default_hparams_dict()
+        hparams = dict(
+            l1_weight=1.0, l2_weight=0.0, n_layers=3, ndf=32, norm_layer='instance', use_same_discriminator=False,
+            ngf=32, downsample_layer='conv_pool2d', upsample_layer='upsample_conv2d', activation_layer='relu',
+            transformation='cdna', kernel_size=(5, 5), dilation_rate=(1, 1), where_add='all', use_tile_concat=True,
+            learn_initial_state=False, rnn='lstm', conv_rnn='lstm', conv_rnn_norm_layer='instance',
+            num_transformed_images=4, last_frames=1, prev_image_background=True, first_image_background=True,
+            last_image_background=False, last_context_image_background=False, context_images_background=False,
+            generate_scratch_image=True, dependent_mask=True, schedule_sampling='inverse_sigmoid',
+            schedule_sampling_k=900.0, schedule_sampling_steps=(0, 100000), use_e_rnn=False, learn_prior=False, nz=8,
+            num_samples=8, nef=64, use_rnn_z=True, ablation_conv_rnn_norm=False, ablation_rnn=False,
+        )
+        return dict(itertools.chain(default_hparams.items(), hparams.items()))
+
+    def parse_hparams(self, hparams_dict, hparams):
+        deprecated = ['num_gpus', 'e_net', 'd_conditional', 'd_downsample_layer', 'd_net', 'd_use_gt_inputs',
+                      'acvideo_gan_weight', 'acvideo_vae_gan_weight', 'image_gan_weight', 'image_vae_gan_weight',
+                      'tuple_gan_weight', 'tuple_vae_gan_weight', 'gan_weight', 'vae_gan_weight', 'video_gan_weight',
+                      'video_vae_gan_weight']
+        hparams_dict = dict(hparams_dict or {})
+        for key in deprecated:
+            hparams_dict.pop(key, None)
+        return super(SAVPVideoPredictionModel, self).parse_hparams(hparams_dict, hparams)
+
+    def _check_supported(self):
+        hp = self.hparams
+        if hp.where_add not in ('input', 'all', 'middle'):
+            raise ValueError('Invalid where_add %s' % hp.where_add)  # savp_model.py:176-177
+        unsupported = []
+        for key, want in (('where_add', 'all'), ('use_tile_concat', True), ('transformation', 'cdna'),
+                          ('conv_rnn', 'lstm'), ('rnn', 'lstm'), ('conv_rnn_norm_layer', 'instance'),
+                          ('norm_layer', 'instance'), ('downsample_layer', 'conv_pool2d'),
+                          ('upsample_layer', 'upsample_conv2d'), ('activation_layer', 'relu'), ('last_frames', 1),
+                          ('prev_image_background', True), ('first_image_background', True),
+                          ('last_image_background', False), ('last_context_image_background', False),
+                          ('context_images_background', False), ('generate_scratch_image', True),
+                          ('dependent_mask', True), ('use_e_rnn', False), ('learn_prior', False),
+                          ('learn_initial_state', False), ('ablation_conv_rnn_norm', False), ('ablation_rnn', False),
+                          ('use_rnn_z', True)):
+            if getattr(hp, key) != want:
+                unsupported.append('%s=%r' % (key, getattr(hp, key)))
+        if unsupported:
+            raise NotImplementedError('hparams outside the B200 hot path (SURVEY.md 8f): ' + ', '.join(unsupported))
+
+    # ------------------------------------------------------------------ structure (savp_model.py:182-232)
+    @staticmethod
+    def layer_specs(ngf, height, width):
+        s = min(height, width)
+        g = ngf
+        if s >= 256:
+            enc = [(g, False), (g * 2, False), (g * 4, True), (g * 8, True), (g * 8, True)]
+            dec = [(g * 8, True), (g * 4, True), (g * 2, False), (g, False), (g, False)]
+        elif s >= 128:
+            enc = [(g, False), (g * 2, True), (g * 4, True), (g * 8, True)]
+            dec = [(g * 8, True), (g * 4, True), (g * 2, False), (g, False)]
+        elif s >= 64:
+            enc = [(g, True), (g * 2, True), (g * 4, True)]
+            dec = [(g * 2, True), (g, True), (g, False)]
+        elif s >= 32:
+            enc = [(g, True), (g * 2, True)]
+            dec = [(g, True), (g, False)]
+        else:
+            raise NotImplementedError
+        return enc, dec
+
+    def _generator_param_specs(self):
+        """name -> (shape, init) with the reference's variable scopes (generator/...)."""
+        hp = self.hparams
+        H, W, C, A = self.H, self.W, self.C, self.A
+        specs = OrderedDict()
+        Zc = self.Zc
+        enc, dec = self.enc_specs, self.dec_specs
+        if hp.nz:
+            sc = 'generator/encoder'
+            cin = 2 * C + A
+            for i in range(hp.n_layers):
+                oc = hp.nef * min(2 ** i, 4)
+                specs['%s/layer_%d/conv2d/kernel' % (sc, i + 1)] = ((4, 4, cin, oc), 'kernel')
+                specs['%s/layer_%d/conv2d/bias' % (sc, i + 1)] = ((oc,), 'zeros')
+                if i > 0:
+                    specs['%s/layer_%d/InstanceNorm/gamma' % (sc, i + 1)] = ((oc,), 'ones')
+                    specs['%s/layer_%d/InstanceNorm/beta' % (sc, i + 1)] = ((oc,), 'zeros')
+                cin = oc
+            for nm in ('z_mu', 'z_log_sigma_sq'):
+                specs['%s/%s/dense/kernel' % (sc, nm)] = ((cin, hp.nz), 'kernel')
+                specs['%s/%s/dense/bias' % (sc, nm)] = ((hp.nz,), 'zeros')
+        sc = 'generator/rnn/savp_cell'
+        if hp.nz:
+            specs[sc + '/lstm_z/basic_lstm_cell/kernel'] = ((2 * hp.nz, 4 * hp.nz), 'kernel')
+            specs[sc + '/lstm_z/basic_lstm_cell/bias'] = ((4 * hp.nz,), 'zeros')
+
+        def norm(name, c):
+            specs[name + '/gamma'] = ((c,), 'ones')
+            specs[name + '/beta'] = ((c,), 'zeros')
+
+        def lstm(i, cin, oc):
+            b = '%s/lstm_h%d/basic_conv2dlstm_cell' % (sc, i)
+            specs[b + '/kernel'] = ((5, 5, cin + Zc + oc, 4 * oc), 'kernel')
+            norm(b + '/input_transform_forget_output', 4 * oc)
+            norm(b + '/state', oc)
+        outs = []
+        cin = 2 * C
+        for i, (oc, use) in enumerate(enc):
+            ks = 5 if i == 0 else 3
+            specs['%s/h%d/conv_pool2d/kernel' % (sc, i)] = ((ks, ks, cin + Zc, oc), 'kernel')
+            specs['%s/h%d/conv_pool2d/bias' % (sc, i)] = ((oc,), 'zeros')
+            norm('%s/h%d/InstanceNorm' % (sc, i), oc)
+            if use:
+                lstm(i, oc, oc)
+            outs.append(oc)
+            cin = oc
+        n_enc = len(enc)
+        for i, (oc, use) in enumerate(dec):
+            li = n_enc + i
+            cin = outs[-1] if i == 0 else outs[-1] + outs[n_enc - i - 1]
+            specs['%s/h%d/upsample_conv2d/kernel' % (sc, li)] = ((3, 3, cin + Zc, oc), 'kernel')
+            specs['%s/h%d/upsample_conv2d/bias' % (sc, li)] = ((oc,), 'zeros')
+            norm('%s/h%d/InstanceNorm' % (sc, li), oc)
+            if use:
+                lstm(li, oc, oc)
+            outs.append(oc)
+        nl = n_enc + len(dec)
+        kh, kw = hp.kernel_size
+        nk = hp.last_frames * hp.num_transformed_images
+        sh = H // (2 ** n_enc)
+        sw = W // (2 ** n_enc)
+        specs[sc + '/cdna_kernels/dense/kernel'] = ((sh * sw * outs[n_enc - 1], kh * kw * nk), 'kernel')
+        specs[sc + '/cdna_kernels/dense/bias'] = ((kh * kw * nk,), 'zeros')
+        top = outs[-1]
+        for nm in ('h%d_scratch' % nl, 'h%d_masks' % nl):
+            specs['%s/%s/conv2d/kernel' % (sc, nm)] = ((3, 3, top, hp.ngf), 'kernel')
+            specs['%s/%s/conv2d/bias' % (sc, nm)] = ((hp.ngf,), 'zeros')
+            norm('%s/%s/InstanceNorm' % (sc, nm), hp.ngf)
+        specs[sc + '/scratch_image/conv2d/kernel'] = ((3, 3, hp.ngf, C), 'kernel')
+        specs[sc + '/scratch_image/conv2d/bias'] = ((C,), 'zeros')
+        nlayers = nk + 3
+        specs[sc + '/masks/conv2d/kernel'] = ((3, 3, hp.ngf + nlayers * C, nlayers), 'kernel')
+        specs[sc + '/masks/conv2d/bias'] = ((nlayers,), 'zeros')
+        return specs
+
+    # ------------------------------------------------------------------ build
+    def build_graph(self, inputs):
+        """inputs: dict with 'images' [B,T,H,W,C] (torch / numpy, batch-major as in base_model.py:467)
+        and optionally 'actions' [B,T-1,A].  Allocates parameters (reference initialisers) unless
+        `set_params` was called, and all activation buffers."""
+        super(SAVPVideoPredictionModel, self).build_graph(inputs)
+        if not torch.cuda.is_available():
+            raise RuntimeError('video_prediction_b200 needs a CUDA device (sm_100a); there is no CPU fallback')
+        L.lib()  # fail loudly if the CUDA library is missing
+        self._check_supported()
+        hp = self.hparams
+        self.device = torch.device('cuda', torch.cuda.current_device())
+        imgs = inputs['images']
+        B, T, H, W, C = [int(s) for s in imgs.shape]
+        if T < hp.sequence_length:
+            raise ValueError('images have %d frames, sequence_length is %d' % (T, hp.sequence_length))
+        self.B, self.T, self.H, self.W, self.C = B, hp.sequence_length, H, W, C
+        self.A = int(inputs['actions'].shape[-1]) if 'actions' in inputs else 0
+        self.S = self.T - 1
+        self.Zc = self.A + (hp.nz if hp.nz else 0)
+        self.NB = 2 * B if hp.nz else B
+        self.enc_specs, self.dec_specs = self.layer_specs(hp.ngf, H, W)
+        total_stride = 2 ** len(self.enc_specs)
+        if (H % total_stride) or (W % total_stride):
+            raise ValueError('The image has dimension (%d, %d), but it should be divisible by the total stride, '
+                             'which is %d.' % (H, W, total_stride))
+        if C > 4:
+            raise NotImplementedError('at most 4 colour channels')
+        self.param_specs = self._generator_param_specs()
+        if self.params is None:
+            self.init_params(seed=0)
+        self._build_generator()
+        self.built = True
+        self.set_inputs(inputs)
+
+    def init_params(self, seed=0):
+        rng = np.random.default_rng(seed)
+        vals = OrderedDict()
+        for name, (shape, init) in self.param_specs.items():
+            if init == 'kernel':
+                x = rng.standard_normal(size=shape)
+                bad = np.abs(x) > 2.0
+                while bad.any():
+                    x[bad] = rng.standard_normal(size=int(bad.sum()))
+                    bad = np.abs(x) > 2.0
+                vals[name] = (x * 0.02).astype(np.float32)
+            elif init == 'ones':
+                vals[name] = np.ones(shape, np.float32)
+            else:
+                vals[name] = np.zeros(shape, np.float32)
+        self.set_params(vals)
+
+    def set_params(self, values):
+        """values: name -> array/tensor with the reference's variable names and shapes."""
+        dev = self.device or torch.device('cuda', torch.cuda.current_device())
+        self.device = dev
+        specs = getattr(self, 'param_specs', None)
+        if self.params is None:
+            self.params = OrderedDict()
+        for name, v in values.items():
+            t = torch.as_tensor(np.asarray(v.detach().cpu() if torch.is_tensor(v) else v), dtype=torch.float32)
+            if specs is not None and name in specs and tuple(t.shape) != tuple(specs[name][0]):
+                raise ValueError('shape mismatch for %s: %s vs %s' % (name, tuple(t.shape), specs[name][0]))
+            if name in self.params:
+                self.params[name].copy_(t)
+            else:
+                self.params[name] = t.to(dev).contiguous()
+        if self.built:
+            self._pack_all()
+
+    def get_params(self):
+        return OrderedDict((k, v.detach().cpu().numpy()) for k, v in self.params.items())
+
+    def _z(self, *shape):
+        return torch.zeros(*shape, device=self.device, dtype=torch.float32)
+
+    def _build_generator(self):
+        hp = self.hparams
+        S, NB, H, W, C, Zc = self.S, self.NB, self.H, self.W, self.C, self.Zc
+        sc = 'generator/rnn/savp_cell'
+        enc, dec = self.enc_specs, self.dec_specs
+        n_enc = len(enc)
+        self.convs = []
+        self.Bf = {}   # name -> stacked buffer
+        Bf = self.Bf
+        zseg = [('z', Zc)] if Zc else []
+        self.gl = []   # per generator layer dict
+        res = [(H >> (i + 1), W >> (i + 1)) for i in range(n_enc)]
+        for i in range(len(dec)):
+            res.append((res[n_enc - 1][0] << (i + 1), res[n_enc - 1][1] << (i + 1)))
+        outs = []
+        for li in range(n_enc + len(dec)):
+            is_enc = li < n_enc
+            oc, use = enc[li] if is_enc else dec[li - n_enc]
+            hh, ww = res[li]
+            ih, iw = (H, W) if li == 0 else res[li - 1]
+            d = dict(li=li, oc=oc, use=use, h=hh, w=ww, is_enc=is_enc)
+            if li == 0:
+                segs = [('image', C), ('first', C)] + zseg
+            elif is_enc or li == n_enc:
+                segs = [('x', outs[-1])] + zseg
+            else:
+                segs = [('x', outs[-1]), ('skip', outs[n_enc - (li - n_enc) - 1])] + zseg
+            d['in_spec'] = ConcatSpec(segs)
+            Bf['in%d' % li] = self._z(S, NB, ih, iw, d['in_spec'].cstride)
+            if is_enc:
+                ks = 5 if li == 0 else 3
+                pb = (ks + 1 - 2) // 2
+                d['conv'] = ConvLayer(self, '%s/h%d/conv_pool2d/kernel' % (sc, li), '%s/h%d/conv_pool2d/bias' % (sc, li),
+                                      (1, ks, ks), L.WKIND_POOLED, (1, 2, 2), (0, pb, pb), False, d['in_spec'], oc)
+            else:
+                d['conv'] = ConvLayer(self, '%s/h%d/upsample_conv2d/kernel' % (sc, li),
+                                      '%s/h%d/upsample_conv2d/bias' % (sc, li), (1, 3, 3), L.WKIND_UPSAMPLED, (1, 2, 2),
+                                      (0, 2, 2), True, d['in_spec'], oc)
+            self.convs.append(d['conv'])
+            Bf['pre%d' % li] = self._z(S, NB, hh, ww, oc)
+            Bf['nst%d' % li] = self._z(S, NB, oc, 2)
+            if use:
+                d['rin_spec'] = ConcatSpec([('x', oc)] + zseg + [('h', oc)])
+                Bf['rin%d' % li] = self._z(S + 1, NB, hh, ww, d['rin_spec'].cstride)
+                b = '%s/lstm_h%d/basic_conv2dlstm_cell' % (sc, li)
+                d['rconv'] = ConvLayer(self, b + '/kernel', None, (1, 5, 5), L.WKIND_PLAIN, (1, 1, 1), (0, 2, 2), False,
+                                       d['rin_spec'], 4 * oc)
+                d['rname'] = b
+                self.convs.append(d['rconv'])
+                Bf['gpre%d' % li] = self._z(S, NB, hh, ww, 4 * oc)
+                Bf['c%d' % li] = self._z(S + 1, NB, hh, ww, oc)      # c[t] = state entering step t
+                Bf['gst1_%d' % li] = self._z(S, NB, 4 * oc, 2)
+                Bf['gst2_%d' % li] = self._z(S, NB, oc, 2)
+            else:
+                Bf['out%d' % li] = self._z(S, NB, hh, ww, oc)
+            outs.append(oc)
+            self.gl.append(d)
+        nl = len(self.gl)
+        self.nl = nl
+        top = outs[-1]
+        kh, kw = hp.kernel_size
+        nk = hp.last_frames * hp.num_transformed_images
+        self.nk, self.kh, self.kw = nk, kh, kw
+        self.nlayers = nk + 3
+        sl = self.gl[n_enc - 1]
+        Bf['small'] = self._z(S, NB, sl['h'] * sl['w'] * sl['oc'])
+        Bf['kraw'] = self._z(S, NB, kh * kw * nk)
+        Bf['kern'] = self._z(S, NB, kh * kw * nk)
+        top_spec = ConcatSpec([('x', top)])
+        self.top_spec = top_spec
+        self.conv_scratch = ConvLayer(self, '%s/h%d_scratch/conv2d/kernel' % (sc, nl), '%s/h%d_scratch/conv2d/bias' % (sc, nl),
+                                      (1, 3, 3), L.WKIND_PLAIN, (1, 1, 1), (0, 1, 1), False, top_spec, hp.ngf)
+        self.conv_hmasks = ConvLayer(self, '%s/h%d_masks/conv2d/kernel' % (sc, nl), '%s/h%d_masks/conv2d/bias' % (sc, nl),
+                                     (1, 3, 3), L.WKIND_PLAIN, (1, 1, 1), (0, 1, 1), False, top_spec, hp.ngf)
+        hs_spec = ConcatSpec([('x', hp.ngf)])
+        self.conv_simg = ConvLayer(self, sc + '/scratch_image/conv2d/kernel', sc + '/scratch_image/conv2d/bias',
+                                   (1, 3, 3), L.WKIND_PLAIN, (1, 1, 1), (0, 1, 1), False, hs_spec, C)
+        self.mk_spec = ConcatSpec([('hm', hp.ngf)] + [('l%d' % l, C) for l in range(self.nlayers)])
+        self.conv_masks = ConvLayer(self, sc + '/masks/conv2d/kernel', sc + '/masks/conv2d/bias', (1, 3, 3), L.WKIND_PLAIN,
+                                    (1, 1, 1), (0, 1, 1), False, self.mk_spec, self.nlayers)
+        self.convs += [self.conv_scratch, self.conv_hmasks, self.conv_simg, self.conv_masks]
+        Bf['spre'] = self._z(S, NB, H, W, hp.ngf)
+        Bf['mpre'] = self._z(S, NB, H, W, hp.ngf)
+        Bf['sst'] = self._z(S, NB, hp.ngf, 2)
+        Bf['mst'] = self._z(S, NB, hp.ngf, 2)
+        Bf['hs'] = self._z(S, NB, H, W, hp.ngf)
+        Bf['mk'] = self._z(S, NB, H, W, self.mk_spec.cstride)
+        Bf['mlog'] = self._z(S, NB, H, W, 8)
+        Bf['masks'] = self._z(S, NB, H, W, 8)
+        Bf['gen'] = self._z(S, NB, H, W, 4)
+        Bf['img'] = self._z(S, NB, H, W, 4)
+        Bf['x'] = self._z(self.T, NB, H, W, 4)
+        Bf['sel'] = torch.ones(S, NB, device=self.device, dtype=torch.int32)
+        if Zc:
+            Bf['zvec'] = self._z(S, NB, _ceil4(Zc))
+        if hp.nz:
+            nz = hp.nz
+            Bf['zs'] = self._z(S, NB, nz)             # zs fed to the two unrolls (posterior | prior)
+            Bf['zcat'] = self._z(S, NB, 2 * nz)       # [z_t, h_{t-1}] of the dense LSTM on z
+            Bf['zgates'] = self._z(S, NB, 4 * nz)
+            Bf['zc'] = self._z(S + 1, NB, nz)
+            Bf['zh'] = self._z(S + 1, NB, nz)
+            self._build_posterior()
+        self._pack_all()
+
+    def _build_posterior(self):
+        hp = self.hparams
+        S, B, H, W, C, A = self.S, self.B, self.H, self.W, self.C, self.A
+        sc = 'generator/encoder'
+        Bf = self.Bf
+        segs = [('a', C), ('b', C)] + ([('act', A)] if A else [])
+        self.pair_spec = ConcatSpec(segs)
+        Bf['pairs'] = self._z(S * B, H, W, self.pair_spec.cstride)
+        self.enc_layers = []
+        spec = self.pair_spec
+        hh, ww = H, W
+        for i in range(hp.n_layers):
+            oc = hp.nef * min(2 ** i, 4)
+            hh, ww = hh // 2, ww // 2
+            conv = ConvLayer(self, '%s/layer_%d/conv2d/kernel' % (sc, i + 1), '%s/layer_%d/conv2d/bias' % (sc, i + 1),
+                             (1, 4, 4), L.WKIND_PLAIN, (1, 2, 2), (0, 1, 1), False, spec, oc)
+            self.convs.append(conv)
+            Bf['epre%d' % i] = self._z(S * B, hh, ww, oc)
+            if i > 0:
+                Bf['eact%d' % i] = self._z(S * B, hh, ww, oc)
+                Bf['est%d' % i] = self._z(S * B, oc, 2)
+            self.enc_layers.append(dict(conv=conv, oc=oc, h=hh, w=ww))
+            spec = ConcatSpec([('x', oc)])
+        Bf['epool'] = self._z(S * B, self.enc_layers[-1]['oc'])
+        Bf['zmu'] = self._z(S, B, hp.nz)
+        Bf['zlss'] = self._z(S, B, hp.nz)
+        Bf['zpost'] = self._z(S, B, hp.nz)
+        Bf['eps'] = self._z(S, B, hp.nz)
+        Bf['zprior'] = self._z(self.T - hp.context_frames, B, hp.nz)
+
+    def _pack_all(self):
+        for c in self.convs:
+            c.pack()
+
+    # ------------------------------------------------------------------ inputs
+    def set_inputs(self, inputs, noise=None, sampling=None):
+        """Stages a batch: images [B,T,H,W,C] -> time-major, colour-padded, duplicated for the two
+        unrolls.  noise: dict eps [T-1,B,nz], z_prior [T-context,B,nz] (time-major, as the oracle);
+        sampling: optional bool [T-1-context, B] scheduled-sampling mask (savp_model.py:309-334)."""
+        hp = self.hparams
+        Bf = self.Bf
+        dev = self.device
+        B, T, S, C = self.B, self.T, self.S, self.C
+        imgs = torch.as_tensor(inputs['images']).to(dev, torch.float32)[:, :T]
+        x = imgs.permute(1, 0, 2, 3, 4)
+        Bf['x'].zero_()
+        Bf['x'][:, :B, :, :, :C] = x
+        if self.NB > B:
+            Bf['x'][:, B:, :, :, :C] = x
+        if self.A:
+            act = torch.as_tensor(inputs['actions']).to(dev, torch.float32)[:, :S].permute(1, 0, 2)
+            self._actions = act.contiguous()
+            Bf['zvec'][:, :B, :self.A] = act
+            if self.NB > B:
+                Bf['zvec'][:, B:, :self.A] = act
+        sel = torch.ones(S, self.NB, dtype=torch.int32)
+        if sampling is not None:
+            sm = torch.as_tensor(sampling).to(torch.int32).reshape(S - hp.context_frames, B)
+            sel[hp.context_frames:, :B] = sm
+            if self.NB > B:
+                sel[hp.context_frames:, B:] = sm
+        else:
+            sel[hp.context_frames:] = 0
+        Bf['sel'].copy_(sel)
+        if hp.nz:
+            if noise is None:
+                g = torch.Generator(device='cpu').manual_seed(self.global_step + 1)
+                noise = dict(eps=torch.randn(S, B, hp.nz, generator=g),
+                             z_prior=torch.randn(T - hp.context_frames, B, hp.nz, generator=g))
+            Bf['eps'].copy_(torch.as_tensor(noise['eps']).to(dev, torch.float32))
+            Bf['zprior'].copy_(torch.as_tensor(noise['z_prior']).to(dev, torch.float32))
+
+    # ------------------------------------------------------------------ forward
+    def _posterior_forward(self):
+        hp = self.hparams
+        Bf = self.Bf
+        S, B, H, W, C, A = self.S, self.B, self.H, self.W, self.C, self.A
+        ps = self.pair_spec
+        rows = S * B * H * W
+        x = Bf['x']
+        # image pairs concat([x_t, x_{t+1}]) (savp_model.py:23) for the first B samples of each frame
+        for t in range(S):
+            dst = Bf['pairs'][t * B:(t + 1) * B]
+            L.copy_channels(x[t].data_ptr(), 4, dst.data_ptr() + 4 * ps.off('a'), ps.cstride, B * H * W, 4)
+            L.copy_channels(x[t + 1].data_ptr(), 4, dst.data_ptr() + 4 * ps.off('b'), ps.cstride, B * H * W, 4)
+        if A:
+            L.broadcast_channels(self._actions, A, Bf['pairs'].data_ptr() + 4 * ps.off('act'), ps.cstride, S * B, H * W, A)
+        cur = Bf['pairs']
+        for i, el in enumerate(self.enc_layers):
+            pre = Bf['epre%d' % i]
+            if i == 0:
+                el['conv'].fwd(cur, pre, act=L.ACT_LRELU, alpha=0.2)      # networks.py:17-20
+                cur = pre
+            else:
+                el['conv'].fwd(cur, pre)
+                nm = 'generator/encoder/layer_%d/InstanceNorm' % (i + 1)
+                L.inorm_act(pre.data_ptr(), el['oc'], Bf['eact%d' % i].data_ptr(), el['oc'], S * B, el['h'] * el['w'],
+                            el['oc'], self.params[nm + '/gamma'], self.params[nm + '/beta'], L.ACT_LRELU, 0.2,
+                            Bf['est%d' % i])
+                cur = Bf['eact%d' % i]
+        last = self.enc_layers[-1]
+        L.avgpool(cur, last['oc'], Bf['epool'], S * B, last['h'] * last['w'], last['oc'])
+        P = self.params
+        sc = 'generator/encoder'
+        L.dense_fwd(Bf['epool'], last['oc'], P[sc + '/z_mu/dense/kernel'], P[sc + '/z_mu/dense/bias'], Bf['zmu'], hp.nz,
+                    S * B, last['oc'], hp.nz)
+        L.dense_fwd(Bf['epool'], last['oc'], P[sc + '/z_log_sigma_sq/dense/kernel'], P[sc + '/z_log_sigma_sq/dense/bias'],
+                    Bf['zlss'], hp.nz, S * B, last['oc'], hp.nz)
+        L.sample_z(Bf['zmu'], Bf['zlss'], Bf['eps'], Bf['zpost'], S * B * hp.nz)
+        # zs for the two unrolls: posterior half, prior half = [z_post[:ctx-1], z_prior] (savp_model.py:724-725)
+        nz = hp.nz
+        L.copy_channels(Bf['zpost'].data_ptr(), nz, Bf['zs'].data_ptr(), 2 * B * nz // 2 * 0 + nz, 0, nz)  # no-op (rows=0)
+        zs = Bf['zs']
+        for t in range(S):
+            L.copy_channels(Bf['zpost'][t].data_ptr(), nz, zs[t, :B].data_ptr(), nz, B, nz)
+            src = Bf['zpost'][t] if t < hp.context_frames - 1 else Bf['zprior'][t - (hp.context_frames - 1)]
+            L.copy_channels(src.data_ptr(), nz, zs[t, B:].data_ptr(), nz, B, nz)
+
+    def _rnn_z_forward(self):
+        """Dense LSTM on z (savp_model.py:424-432): independent of the images, so the whole chain runs first
+        and every tile_concat of (actions, rnn_z) becomes one broadcast store per concat buffer."""
+        hp = self.hparams
+        Bf = self.Bf
+        S, NB, nz, A = self.S, self.NB, hp.nz, self.A
+        P = self.params
+        b = 'generator/rnn/savp_cell/lstm_z/basic_lstm_cell'
+        Zp = _ceil4(self.Zc)
+        Bf['zc'][0].zero_()
+        Bf['zh'][0].zero_()
+        for t in range(S):
+            L.copy_channels(Bf['zs'][t].data_ptr(), nz, Bf['zcat'][t].data_ptr(), 2 * nz, NB, nz)
+            L.copy_channels(Bf['zh'][t].data_ptr(), nz, Bf['zcat'][t].data_ptr() + 4 * nz, 2 * nz, NB, nz)
+            L.dense_fwd(Bf['zcat'][t], 2 * nz, P[b + '/kernel'], P[b + '/bias'], Bf['zgates'][t], 4 * nz, NB, 2 * nz, 4 * nz)
+            L.lstm_cell_fwd(Bf['zgates'][t], Bf['zc'][t], Bf['zc'][t + 1], Bf['zh'][t + 1], NB, nz)
+            L.copy_channels(Bf['zh'][t + 1].data_ptr(), nz, Bf['zvec'][t].data_ptr() + 4 * A, Zp, NB, nz)
+
+    def _broadcast_z(self):
+        if not self.Zc:
+            return
+        Bf = self.Bf
+        S, NB, Zc = self.S, self.NB, self.Zc
+        Zp = _ceil4(Zc)
+        for d in self.gl:
+            li = d['li']
+            buf = Bf['in%d' % li]
+            sp = d['in_spec']
+            L.broadcast_channels(Bf['zvec'], Zp, buf.data_ptr() + 4 * sp.off('z'), sp.cstride, S * NB,
+                                 buf.shape[2] * buf.shape[3], Zc)
+            if d['use']:
+                buf = Bf['rin%d' % li]
+                sp = d['rin_spec']
+                L.broadcast_channels(Bf['zvec'], Zp, buf.data_ptr() + 4 * sp.off('z'), sp.cstride, S * NB,
+                                     buf.shape[2] * buf.shape[3], Zc)
+
+    def _h_dests(self, li, t):
+        """Where the output of generator layer li at step t must land (its consumers' concat slices)."""
+        Bf = self.Bf
+        d = self.gl[li]
+        n_enc = len(self.enc_specs)
+        dests = []
+        if d['use'] and t + 1 <= self.S:
+            sp = d['rin_spec']
+            dests.append((Bf['rin%d' % li][t + 1].data_ptr() + 4 * sp.off('h'), sp.cstride))
+        if li + 1 < self.nl:
+            sp = self.gl[li + 1]['in_spec']
+            dests.append((Bf['in%d' % (li + 1)][t].data_ptr() + 4 * sp.off('x'), sp.cstride))
+        if li < n_enc - 1:       # skip connection: decoder layer n_enc + i reads layers[n_enc - i - 1]
+            i = n_enc - 1 - li
+            sp = self.gl[n_enc + i]['in_spec']
+            dests.append((Bf['in%d' % (n_enc + i)][t].data_ptr() + 4 * sp.off('skip'), sp.cstride))
+        if li == n_enc - 1:
+            dests.append((Bf['small'][t].data_ptr(), d['oc']))
+        return dests
+
+    def _gen_step(self, t):
+        hp = self.hparams
+        Bf, P = self.Bf, self.params
+        NB, H, W, C = self.NB, self.H, self.W, self.C
+        sc = 'generator/rnn/savp_cell'
+        HW = H * W
+        # image = where(ground_truth[t], x_t, gen_{t-1})  (savp_model.py:406)
+        if t == 0:
+            L.copy_channels(Bf['x'][0].data_ptr(), 4, Bf['img'][0].data_ptr(), 4, NB * HW, 4)
+        else:
+            L.select_rows(Bf['sel'][t], Bf['x'][t], Bf['gen'][t - 1], Bf['img'][t], NB, HW * 4)
+        sp = self.gl[0]['in_spec']
+        L.copy_channels(Bf['img'][t].data_ptr(), 4, Bf['in0'][t].data_ptr() + 4 * sp.off('image'), sp.cstride, NB * HW, 4)
+        L.copy_channels(Bf['x'][0].data_ptr(), 4, Bf['in0'][t].data_ptr() + 4 * sp.off('first'), sp.cstride, NB * HW, 4)
+        for d in self.gl:
+            li, oc, hh, ww = d['li'], d['oc'], d['h'], d['w']
+            pre = Bf['pre%d' % li][t]
+            d['conv'].fwd(Bf['in%d' % li][t], pre)
+            nm = '%s/h%d/InstanceNorm' % (sc, li)
+            if d['use']:
+                rsp = d['rin_spec']
+                rin = Bf['rin%d' % li][t]
+                L.inorm_act(pre.data_ptr(), oc, rin.data_ptr() + 4 * rsp.off('x'), rsp.cstride, NB, hh * ww, oc,
+                            P[nm + '/gamma'], P[nm + '/beta'], L.ACT_RELU, 0.0, Bf['nst%d' % li][t])
+                gpre = Bf['gpre%d' % li][t]
+                d['rconv'].fwd(rin, gpre)
+                b = d['rname']
+                L.lstm_gates_fwd(gpre, NB, hh * ww, oc, Bf['c%d' % li][t],
+                                 P[b + '/input_transform_forget_output/gamma'], P[b + '/input_transform_forget_output/beta'],
+                                 P[b + '/state/gamma'], P[b + '/state/beta'], Bf['c%d' % li][t + 1], self._h_dests(li, t),
+                                 Bf['gst1_%d' % li][t], Bf['gst2_%d' % li][t])
+            else:
+                dests = self._h_dests(li, t)
+                out = Bf['out%d' % li][t]
+                L.inorm_act(pre.data_ptr(), oc, out.data_ptr(), oc, NB, hh * ww, oc, P[nm + '/gamma'], P[nm + '/beta'],
+                            L.ACT_RELU, 0.0, Bf['nst%d' % li][t])
+                for addr, cs in dests:
+                    L.copy_channels(out.data_ptr(), oc, addr, cs, NB * hh * ww, oc)
+        # cdna kernels (savp_model.py:546-559)
+        nk, kh, kw = self.nk, self.kh, self.kw
+        small = Bf['small'][t]
+        K = small.shape[1]
+        Bf['kraw'][t].zero_()
+        L.dense_fwd(small, K, P[sc + '/cdna_kernels/dense/kernel'], P[sc + '/cdna_kernels/dense/bias'], Bf['kraw'][t],
+                    kh * kw * nk, NB, K, kh * kw * nk, k_splits=32)
+        L.cdna_kernel_norm(Bf['kraw'][t], Bf['kern'][t], NB, kh, kw, nk)
+        # heads
+        top = Bf['out%d' % (self.nl - 1)][t] if not self.gl[-1]['use'] else None
+        ngf = hp.ngf
+        nl = self.nl
+        self.conv_scratch.fwd(top, Bf['spre'][t])
+        self.conv_hmasks.fwd(top, Bf['mpre'][t])
+        nm = '%s/h%d_scratch/InstanceNorm' % (sc, nl)
+        L.inorm_act(Bf['spre'][t].data_ptr(), ngf, Bf['hs'][t].data_ptr(), ngf, NB, HW, ngf, P[nm + '/gamma'],
+                    P[nm + '/beta'], L.ACT_RELU, 0.0, Bf['sst'][t])
+        mk = Bf['mk'][t]
+        msp = self.mk_spec
+        nm = '%s/h%d_masks/InstanceNorm' % (sc, nl)
+        L.inorm_act(Bf['mpre'][t].data_ptr(), ngf, mk.data_ptr() + 4 * msp.off('hm'), msp.cstride, NB, HW, ngf,
+                    P[nm + '/gamma'], P[nm + '/beta'], L.ACT_RELU, 0.0, Bf['mst'][t])
+        # scratch image -> last layer slot (savp_model.py:570-572, 595-596)
+        self.conv_simg.fwd(Bf['hs'][t], mk, out_off=msp.off('l%d' % (self.nlayers - 1)), out_c=C, act=L.ACT_SIGMOID)
+        # transformed images: 4 CDNA + prev image + first image (savp_model.py:574-584)
+        L.cdna_apply(Bf['img'][t], Bf['x'][0], Bf['kern'][t], mk.data_ptr() + 4 * msp.off('l0'), msp.cstride, NB, H, W,
+                     kh, kw, nk)
+        # masks + compositing (savp_model.py:623-646)
+        self.conv_masks.fwd(mk, Bf['mlog'][t], out_c=self.nlayers)
+        L.composite(Bf['mlog'][t], 8, mk.data_ptr() + 4 * msp.off('l0'), msp.cstride, Bf['masks'][t], 8, Bf['gen'][t],
+                    NB * HW, self.nlayers)
+
+    def generator_forward(self):
+        hp = self.hparams
+        if hp.nz:
+            self._posterior_forward()
+            self._rnn_z_forward()
+        self._broadcast_z()
+        for d in self.gl:
+            if d['use']:
+                li = d['li']
+                self.Bf['c%d' % li][0].zero_()
+                sp = d['rin_spec']
+                # h state entering step 0 is zero (zero_state, savp_model.py:344-352)
+                z = self.Bf['rin%d' % li][0]
+                z[..., sp.off('h'):sp.off('h') + d['oc']] = 0
+        for t in range(self.S):
+            self._gen_step(t)
+        self._collect_outputs()
+
+    def _collect_outputs(self):
+        B, C = self.B, self.C
+        Bf = self.Bf
+        out = OrderedDict()
+        gen = Bf['gen'][..., :C]                       # [S, NB, H, W, C] time-major
+        nlay = self.nlayers
+        msp = self.mk_spec
+        tr = torch.stack([Bf['mk'][..., msp.off('l%d' % l):msp.off('l%d' % l) + C] for l in range(nlay)], dim=-1)
+        masks = Bf['masks'][..., :nlay].unsqueeze(-2)  # [S,NB,H,W,1,L]
+        if self.hparams.nz:
+            out['gen_images_enc'] = gen[:, :B].permute(1, 0, 2, 3, 4)
+            out['gen_images'] = gen[:, B:].permute(1, 0, 2, 3, 4)
+            out['transformed_images'] = tr[:, B:].permute(1, 0, 2, 3, 4, 5)
+            out['masks'] = masks[:, B:].permute(1, 0, 2, 3, 4, 5)
+            out['zs_mu_enc'] = Bf['zmu'].permute(1, 0, 2)
+            out['zs_log_sigma_sq_enc'] = Bf['zlss'].permute(1, 0, 2)
+        else:
+            out['gen_images'] = gen.permute(1, 0, 2, 3, 4)
+            out['transformed_images'] = tr.permute(1, 0, 2, 3, 4, 5)
+            out['masks'] = masks.permute(1, 0, 2, 3, 4, 5)
+        self.outputs = out
+        self.gen_images = out['gen_images']
