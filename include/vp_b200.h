@@ -58,9 +58,10 @@ int vp_version(void);
  * wpacked: [kd*kh*kw][n_pad][kc*32] floats (see vp_pack_weights); GEMM N = n_pad (multiple of 16),
  * GEMM K = kc 32-channel chunks of in->c per tap.  out->c columns are stored.
  * split_k > 1: partial sums are atomically added into `out` (caller zero-fills; act must be NONE;
- * bias is added by split 0). */
+ * bias is added by split 0).  accumulate != 0: out += result (act must be NONE). */
 int vp_conv_igemm(const vp_tensor* in, const vp_conv_geom* g, const float* wpacked, int n_pad, int kc,
-                  const vp_tensor* out, const float* bias, int act, float alpha, int split_k, vp_stream_t stream);
+                  const vp_tensor* out, const float* bias, int act, float alpha, int split_k, int accumulate,
+                  vp_stream_t stream);
 
 /* Weight gradient of the same convolution: dwpacked[tap][co][ci] += sum_o  dy.. * x..
  * (layout VP_WLAYOUT_FWD: rows = channels of dy (n_pad rows), cols = kc*32 channels of x).
@@ -137,6 +138,75 @@ int vp_cdna_apply(const float* image, const float* first_image, const float* ker
 /* masks = softmax(logits) (savp_model.py:634); gen_image = sum_l layer_l * mask_l (:645-646). */
 int vp_composite(const float* logits, int logits_cstride, const float* layers, int layers_cstride, float* masks,
                  int masks_cstride, float* gen_image, long long positions, int num_layers, vp_stream_t stream);
+
+
+/* ---- backward passes of the HBM-bound kernels ----------------------------------------------------
+ * Gradient inputs that have several consumers are passed as lists of (pointer, channel stride)
+ * "sources" which the kernel sums.  Parameter gradients (dgamma, dbeta, dw, db ...) are ACCUMULATED. */
+int vp_inorm_act_bwd(const float* x, int x_cstride, const float* const* dy, const int* dy_cstride, int num_dy,
+                     float* dx, int dx_cstride, int n, int positions, int c, const float* gamma, const float* beta,
+                     const float* stats, int act, float alpha, float* dgamma, float* dbeta, vp_stream_t stream);
+int vp_lstm_gates_bwd(const float* pre, int n, int positions, int filters, const float* c_prev, const float* gamma1,
+                      const float* beta1, const float* gamma2, const float* beta2, const float* stats1,
+                      const float* stats2, float forget_bias, const float* const* dh, const int* dh_cstride,
+                      int num_dh, const float* dc_next, float* dpre, float* dc_prev, float* dgamma1, float* dbeta1,
+                      float* dgamma2, float* dbeta2, vp_stream_t stream);
+int vp_composite_bwd(const float* dgen, const float* masks, int masks_cstride, const float* layers, int layers_cstride,
+                     float* dlogits, int dlogits_cstride, float* dlayers, int dlayers_cstride, long long positions,
+                     int num_layers, vp_stream_t stream);
+/* dT_k = d_a[..,4k] + d_b[..,4k]; dimage += (atomic) ; dkernels += (atomic) */
+int vp_cdna_apply_bwd(const float* image, const float* kernels, const float* d_a, int d_a_cstride, const float* d_b,
+                      int d_b_cstride, float* dimage, float* dkernels, int n, int h, int w, int kh, int kw, int nk,
+                      vp_stream_t stream);
+int vp_cdna_kernel_norm_bwd(const float* raw, const float* out, const float* dout, float* draw, int b, int kh, int kw,
+                            int nk, vp_stream_t stream);
+/* dx (optional; overwritten or accumulated), dw += , dbias += */
+int vp_dense_bwd(const float* x, int x_stride, const float* w, const float* inv_scale, const float* dy, int dy_stride,
+                 float* dx, int dx_stride, int dx_accumulate, float* dw, float* dbias, int b, int k, int j,
+                 vp_stream_t stream);
+int vp_lstm_cell_bwd(const float* gates, const float* c_prev, const float* c_new, const float* dh, const float* dc_next,
+                     float* dgates, float* dc_prev, int b, int units, float forget_bias, vp_stream_t stream);
+/* out[n*out_stride + c] += scale * sum_p x[n][p][c] */
+int vp_colsum(const float* x, int x_cstride, float* out, int out_stride, int n, long long positions, int c, float scale,
+              vp_stream_t stream);
+/* dst[r][c] = (accumulate ? dst[r][c] : 0) + scale*src[r][c]; rows whose row_mask[r / rows_per_mask] != 0 contribute 0 */
+int vp_axpy_channels(const float* src, int src_cstride, float* dst, int dst_cstride, long long rows, int c, float scale,
+                     const int32_t* row_mask, long long rows_per_mask, int accumulate, vp_stream_t stream);
+/* dx = (dy_a + dy_b) * act'(.) evaluated from the activation OUTPUT y */
+int vp_act_bwd(const float* y, int y_cstride, const float* dy_a, int dy_a_cstride, const float* dy_b, int dy_b_cstride,
+               float* dx, int dx_cstride, long long rows, int c, int act, float alpha, vp_stream_t stream);
+int vp_avgpool_bwd(const float* dy, float* dx, int dx_cstride, int n, int positions, int c, vp_stream_t stream);
+/* kl_scale = kl_weight / rows (rows = (T-1)*B); dz may be NULL */
+int vp_sample_z_bwd(const float* mu, const float* lss, const float* eps, const float* dz, float* dmu, float* dlss,
+                    int total, float kl_scale, vp_stream_t stream);
+
+/* ---- losses (losses.py:6-67): out[0] += value; optional gradient = grad_scale * d value / d pred -------- */
+int vp_pixel_loss(const float* pred, int pred_cstride, const float* target, int target_cstride, float* dpred,
+                  int dpred_cstride, long long rows, int c, int mode /*0 = L1, 1 = L2*/, long long mean_count,
+                  float grad_scale, float* out, vp_stream_t stream);
+int vp_lsgan_loss(const float* logits, float label, int n, float grad_scale, float* dlogits, float* out, vp_stream_t stream);
+int vp_kl_loss(const float* mu, const float* lss, int rows, int nz, float* out, vp_stream_t stream);
+/* cosine_distance(a, b) over rows of c channels; da += grad (gradient w.r.t. a only) */
+int vp_cosine_distance(const float* a, const float* b, float* da, long long rows, int c, float grad_scale, float* out,
+                       vp_stream_t stream);
+/* tf.train.AdamOptimizer (TF1 epsilon-hat form), step is 1-based; g is multiplied by grad_scale first */
+int vp_adam(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2, float eps,
+            int step, float grad_scale, vp_stream_t stream);
+
+/* ---- discriminator helpers ------------------------------------------------------------------------
+ * spectral_normed_weight (ops.py:1020-1049): w [rows][cols] (rows = prod(kernel dims)*cin), u [cols].
+ * fwd: v [rows] = l2n(W u), s [cols] = v W, u_new = l2n(s), scal[0..2] = (|Wu|, |s|, sigma).
+ * bwd: dw += d(W/sigma)/dW applied to g_wbar, differentiating through the power iteration;
+ *      gs [cols], gt [rows] are scratch; scal[3] is scratch. */
+int vp_spectral_norm_fwd(const float* w, const float* u, int rows, int cols, float* v, float* s, float* u_new,
+                         float* scal, vp_stream_t stream);
+int vp_spectral_norm_bwd(const float* w, const float* u, const float* g_wbar, int rows, int cols, const float* v,
+                         const float* s, float* scal, float* gs, float* gt, float* dw, vp_stream_t stream);
+/* savp_model.py:97-102: clip[b][j][p] = video[t_start[b]+j][batch_offset+b][p]; pixels = H*W (4 floats each) */
+int vp_gather_clip(const float* video, const int32_t* t_start, float* clip, int clips, int clip_len, long long pixels,
+                   int video_batch, int batch_offset, vp_stream_t stream);
+int vp_scatter_clip(const float* dclip, const int32_t* t_start, float* dvideo, int clips, int clip_len, long long pixels,
+                    int video_batch, int batch_offset, vp_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,188 @@
+// Discriminator-side helpers: spectral normalisation (ops.py:1020-1049, one power iteration,
+// differentiable through the iteration) and per-sample clip gather/scatter (savp_model.py:97-102).
+#include "common.h"
+#include "ptx.cuh"
+
+namespace vp {
+
+__device__ __forceinline__ float wsum2(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ float block_reduce(float v, float* scratch) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = wsum2(v);
+  __syncthreads();
+  if (lane == 0) scratch[warp] = v;
+  __syncthreads();
+  float t = (lane < nw) ? scratch[lane] : 0.f;
+  return wsum2(t);
+}
+
+// out[r] = sum_c W[r][c] * vec[c]     (one warp per row)
+__global__ void __launch_bounds__(256) sn_rowdot_kernel(const float* __restrict__ W, const float* __restrict__ vec,
+                                                        float* __restrict__ out, int R, int C) {
+  const int r = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (r >= R) return;
+  float s = 0.f;
+  for (int c = lane; c < C; c += 32) s += W[static_cast<long long>(r) * C + c] * vec[c];
+  s = wsum2(s);
+  if (lane == 0) out[r] = s;
+}
+// out[c] += sum_r vec[r] * W[r][c]   (rows split over blockIdx.y; out zero-filled by caller)
+__global__ void __launch_bounds__(256) sn_coldot_kernel(const float* __restrict__ W, const float* __restrict__ vec,
+                                                        float* __restrict__ out, int R, int C, int rows_per_block) {
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31), sub = threadIdx.x >> 5;
+  const int r0 = blockIdx.y * rows_per_block, r1 = min(R, r0 + rows_per_block);
+  float s = 0.f;
+  if (c < C)
+    for (int r = r0 + sub; r < r1; r += 8) s += vec[r] * W[static_cast<long long>(r) * C + c];
+  __shared__ float red[8][32];
+  red[sub][threadIdx.x & 31] = s;
+  __syncthreads();
+  if (sub == 0 && c < C) {
+    float t = 0.f;
+    for (int i = 0; i < 8; ++i) t += red[i][threadIdx.x & 31];
+    atomicAdd(out + c, t);
+  }
+}
+// v = t/(|t|+eps) in place; scal[0] = |t|
+__global__ void __launch_bounds__(1024) sn_normalize_kernel(float* __restrict__ t, int n, float* __restrict__ scal, int slot) {
+  __shared__ float scratch[32];
+  float s = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) s += t[i] * t[i];
+  const float nrm = sqrtf(block_reduce(s, scratch));
+  if (threadIdx.x == 0) scal[slot] = nrm;
+  const float inv = 1.f / (nrm + 1e-12f);
+  for (int i = threadIdx.x; i < n; i += blockDim.x) t[i] *= inv;
+}
+// s -> u' = s/(|s|+eps); sigma = s.u' ; scal[1] = |s|, scal[2] = sigma
+__global__ void __launch_bounds__(1024) sn_finish_kernel(const float* __restrict__ s, float* __restrict__ u_new, int n,
+                                                         float* __restrict__ scal) {
+  __shared__ float scratch[32];
+  float q = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) q += s[i] * s[i];
+  q = block_reduce(q, scratch);
+  const float nrm = sqrtf(q);
+  const float inv = 1.f / (nrm + 1e-12f);
+  for (int i = threadIdx.x; i < n; i += blockDim.x) u_new[i] = s[i] * inv;
+  if (threadIdx.x == 0) { scal[1] = nrm; scal[2] = q * inv; }
+}
+// scal[3] += <G, W>
+__global__ void __launch_bounds__(256) sn_dot_kernel(const float* __restrict__ G, const float* __restrict__ W, long long n,
+                                                     float* __restrict__ scal) {
+  __shared__ float scratch[32];
+  float s = 0.f;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x)
+    s += G[i] * W[i];
+  s = block_reduce(s, scratch);
+  if (threadIdx.x == 0) atomicAdd(scal + 3, s);
+}
+// gs[c] = a * s_hat[c] * gsigma, gsigma = -<G,W>/sigma^2, a = (|s|^2+2 eps |s|)/(|s|+eps)^2, s_hat = s/|s|
+__global__ void sn_bwd_gs_kernel(const float* __restrict__ s, float* __restrict__ gs, int n, const float* __restrict__ scal) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float ns = scal[1], sigma = scal[2], dot = scal[3];
+  const float gsig = -dot / (sigma * sigma);
+  const float a = (ns * ns + 2e-12f * ns) / ((ns + 1e-12f) * (ns + 1e-12f));
+  gs[i] = ns > 0.f ? a * (s[i] / ns) * gsig : 0.f;
+}
+// gt = gv/(n+eps) - t*(t.gv)/(n*(n+eps)^2), t = v*(n+eps);  in place on gv
+__global__ void __launch_bounds__(1024) sn_bwd_gt_kernel(const float* __restrict__ v, float* __restrict__ gv, int n,
+                                                         const float* __restrict__ scal) {
+  __shared__ float scratch[32];
+  const float nt = scal[0];
+  float d = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) d += v[i] * gv[i];
+  d = block_reduce(d, scratch);   // v.gv
+  const float ne = nt + 1e-12f;
+  // t.gv = ne * (v.gv);  t_i*(t.gv)/(n*ne^2) = v_i*ne*ne*(v.gv)/(n*ne^2) = v_i*(v.gv)/n
+  const float coef = nt > 0.f ? d / nt : 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) gv[i] = gv[i] / ne - v[i] * coef;
+}
+// dW[r][c] += G[r][c]/sigma + v[r]*gs[c] + gt[r]*u[c]
+__global__ void sn_bwd_final_kernel(const float* __restrict__ G, const float* __restrict__ v, const float* __restrict__ gs,
+                                    const float* __restrict__ gt, const float* __restrict__ u, float* __restrict__ dW,
+                                    long long n, int C, const float* __restrict__ scal) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int c = static_cast<int>(i % C);
+  const long long r = i / C;
+  dW[i] += G[i] / scal[2] + v[r] * gs[c] + gt[r] * u[c];
+}
+
+// clip[b][j][p] = video[t_start[b] + j][b][p]  (float4 pixels; video time-major [T][NBv][P], sample offset b_off)
+__global__ void gather_clip_kernel(const float4* __restrict__ video, const int32_t* __restrict__ t_start,
+                                   float4* __restrict__ clip, int Bc, int clip_len, long long P, int NBv, int b_off) {
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long total = static_cast<long long>(Bc) * clip_len * P;
+  if (idx >= total) return;
+  const long long p = idx % P;
+  const int j = static_cast<int>((idx / P) % clip_len);
+  const int b = static_cast<int>(idx / (P * clip_len));
+  clip[idx] = video[(static_cast<long long>(t_start[b] + j) * NBv + b_off + b) * P + p];
+}
+__global__ void scatter_clip_kernel(const float4* __restrict__ dclip, const int32_t* __restrict__ t_start,
+                                    float4* __restrict__ dvideo, int Bc, int clip_len, long long P, int NBv, int b_off) {
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long total = static_cast<long long>(Bc) * clip_len * P;
+  if (idx >= total) return;
+  const long long p = idx % P;
+  const int j = static_cast<int>((idx / P) % clip_len);
+  const int b = static_cast<int>(idx / (P * clip_len));
+  float4* o = dvideo + (static_cast<long long>(t_start[b] + j) * NBv + b_off + b) * P + p;
+  const float4 d = dclip[idx];
+  float4 c = *o;
+  c.x += d.x; c.y += d.y; c.z += d.z; c.w += d.w;
+  *o = c;
+}
+
+}  // namespace vp
+
+using namespace vp;
+
+extern "C" int vp_spectral_norm_fwd(const float* w, const float* u, int rows, int cols, float* v, float* s, float* u_new,
+                                    float* scal, vp_stream_t stream) {
+  cudaStream_t st = as_stream(stream);
+  sn_rowdot_kernel<<<(rows + 7) / 8, 256, 0, st>>>(w, u, v, rows, cols);            // t = W u
+  sn_normalize_kernel<<<1, 1024, 0, st>>>(v, rows, scal, 0);                          // v = l2n(t)
+  cudaMemsetAsync(s, 0, sizeof(float) * cols, st);
+  const int rpb = 512;
+  dim3 grid((cols + 31) / 32, (rows + rpb - 1) / rpb);
+  sn_coldot_kernel<<<grid, 256, 0, st>>>(w, v, s, rows, cols, rpb);                   // s = v W
+  sn_finish_kernel<<<1, 1024, 0, st>>>(s, u_new, cols, scal);                         // u' = l2n(s), sigma
+  return check_launch("spectral_norm_fwd");
+}
+
+extern "C" int vp_spectral_norm_bwd(const float* w, const float* u, const float* g_wbar, int rows, int cols, const float* v,
+                                    const float* s, float* scal, float* gs, float* gt, float* dw, vp_stream_t stream) {
+  cudaStream_t st = as_stream(stream);
+  const long long n = static_cast<long long>(rows) * cols;
+  cudaMemsetAsync(scal + 3, 0, sizeof(float), st);
+  sn_dot_kernel<<<static_cast<int>(std::min<long long>(592, (n + 255) / 256)), 256, 0, st>>>(g_wbar, w, n, scal);
+  sn_bwd_gs_kernel<<<(cols + 127) / 128, 128, 0, st>>>(s, gs, cols, scal);
+  sn_rowdot_kernel<<<(rows + 7) / 8, 256, 0, st>>>(w, gs, gt, rows, cols);            // gv = W gs
+  sn_bwd_gt_kernel<<<1, 1024, 0, st>>>(v, gt, rows, scal);
+  sn_bwd_final_kernel<<<grid_for(n, 256), 256, 0, st>>>(g_wbar, v, gs, gt, u, dw, n, cols, scal);
+  return check_launch("spectral_norm_bwd");
+}
+
+extern "C" int vp_gather_clip(const float* video, const int32_t* t_start, float* clip, int clips, int clip_len,
+                              long long pixels, int video_batch, int batch_offset, vp_stream_t stream) {
+  const long long total = static_cast<long long>(clips) * clip_len * pixels;
+  gather_clip_kernel<<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(reinterpret_cast<const float4*>(video), t_start,
+                                                                         reinterpret_cast<float4*>(clip), clips, clip_len, pixels,
+                                                                         video_batch, batch_offset);
+  return check_launch("gather_clip_kernel");
+}
+
+extern "C" int vp_scatter_clip(const float* dclip, const int32_t* t_start, float* dvideo, int clips, int clip_len,
+                               long long pixels, int video_batch, int batch_offset, vp_stream_t stream) {
+  const long long total = static_cast<long long>(clips) * clip_len * pixels;
+  scatter_clip_kernel<<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(reinterpret_cast<const float4*>(dclip), t_start,
+                                                                          reinterpret_cast<float4*>(dvideo), clips, clip_len, pixels,
+                                                                          video_batch, batch_offset);
+  return check_launch("scatter_clip_kernel");
+}

@@ -51,6 +51,7 @@ struct alignas(64) IgemmArgs {
   const float* bias;
   int32_t act;
   float alpha;
+  int32_t accumulate;
   // wgrad only
   int32_t rows_from_shifted, m_tiles, n_tiles, kpad;
   Tap taps[kMaxTaps];
@@ -175,10 +176,15 @@ __global__ void __launch_bounds__(192, 1) igemm_fwd_kernel(const __grid_constant
           if (col0 + 16 <= a.out_c) {
             float4* o4 = reinterpret_cast<float4*>(orow + col0);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) o4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            for (int j = 0; j < 4; ++j) {
+              float4 o = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+              if (a.accumulate) { const float4 e = o4[j]; o.x += e.x; o.y += e.y; o.z += e.z; o.w += e.w; }
+              o4[j] = o;
+            }
           } else {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) if (col0 + j < a.out_c) orow[col0 + j] = v[j];
+            for (int j = 0; j < 16; ++j)
+              if (col0 + j < a.out_c) orow[col0 + j] = a.accumulate ? orow[col0 + j] + v[j] : v[j];
           }
         }
       }
@@ -441,7 +447,7 @@ using namespace vp;
 
 extern "C" int vp_conv_igemm(const vp_tensor* in, const vp_conv_geom* g, const float* wpacked, int n_pad, int kc,
                              const vp_tensor* out, const float* bias, int act, float alpha, int split_k,
-                             vp_stream_t stream) {
+                             int accumulate, vp_stream_t stream) {
   if (check_tensor(in, "vp_conv_igemm(in)") || check_tensor(out, "vp_conv_igemm(out)")) return -1;
   if (!g || !wpacked) return set_error("vp_conv_igemm: null argument");
   if (n_pad % 16 || n_pad < 16) return set_error("vp_conv_igemm: n_pad must be a positive multiple of 16");
@@ -466,7 +472,8 @@ extern "C" int vp_conv_igemm(const vp_tensor* in, const vp_conv_geom* g, const f
   A.out = out->ptr;
   A.so_w = out->cstride; A.so_h = A.so_w * out->w; A.so_d = A.so_h * out->h; A.so_n = A.so_d * out->d;
   A.out_n = out->n; A.out_d = out->d; A.out_h = out->h; A.out_w = out->w; A.out_c = out->c;
-  A.bias = bias; A.act = act; A.alpha = alpha;
+  A.bias = bias; A.act = act; A.alpha = alpha; A.accumulate = accumulate;
+  if (accumulate && act != VP_ACT_NONE) return set_error("vp_conv_igemm: accumulate needs act NONE");
   // weights: 2-D [slots*n_pad rows][kc*32]
   {
     EncodeTiledFn enc = get_encode();

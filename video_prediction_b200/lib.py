@@ -77,9 +77,9 @@ def geom(k, s=(1, 1, 1), p=(0, 0, 0), transposed=False):
     return VpConvGeom(k[0], k[1], k[2], s[0], s[1], s[2], p[0], p[1], p[2], int(transposed))
 
 
-def conv_igemm(x_view, g, wpacked, n_pad, kc, out_view, bias=None, act=ACT_NONE, alpha=0.0, split_k=1):
+def conv_igemm(x_view, g, wpacked, n_pad, kc, out_view, bias=None, act=ACT_NONE, alpha=0.0, split_k=1, accumulate=0):
     check(lib().vp_conv_igemm(C.byref(x_view), C.byref(g), ptr(wpacked), n_pad, kc, C.byref(out_view), ptr(bias),
-                              act, C.c_float(alpha), split_k, stream_ptr()))
+                              act, C.c_float(alpha), split_k, int(accumulate), stream_ptr()))
 
 
 def conv_wgrad(x_view, dy_view, g, dwpacked, n_pad, kc, split_k=1):
@@ -183,3 +183,117 @@ def cdna_apply(image, first, kernels, layers_addr, layers_cs, n, h, w, kh, kw, n
 def composite(logits, logits_cs, layers_addr, layers_cs, masks, masks_cs, gen, positions, num_layers):
     check(lib().vp_composite(ptr(logits), logits_cs, C.c_void_p(layers_addr), layers_cs, ptr(masks), masks_cs, ptr(gen),
                              C.c_longlong(positions), num_layers, stream_ptr()))
+
+
+# ---------------------------------------------------------------------------------- backward / losses / optimizer
+def _srcs(srcs):
+    """srcs: list of (address:int, cstride:int) gradient sources to be summed."""
+    k = len(srcs)
+    return (C.c_void_p * k)(*[C.c_void_p(a) for a, _ in srcs]), (C.c_int * k)(*[s for _, s in srcs]), k
+
+
+def addr(a):
+    return C.c_void_p(a)
+
+
+def inorm_act_bwd(x_addr, x_cs, dy_srcs, dx_addr, dx_cs, n, positions, c, gamma, beta, stats, act, alpha, dgamma, dbeta):
+    pa, sa, k = _srcs(dy_srcs)
+    check(lib().vp_inorm_act_bwd(addr(x_addr), x_cs, pa, sa, k, addr(dx_addr), dx_cs, n, positions, c, ptr(gamma), ptr(beta),
+                                 ptr(stats), act, _f(alpha), ptr(dgamma), ptr(dbeta), stream_ptr()))
+
+
+def lstm_gates_bwd(pre, n, positions, filters, c_prev, g1, b1, g2, b2, stats1, stats2, dh_srcs, dc_next, dpre, dc_prev,
+                   dg1, db1, dg2, db2, forget_bias=1.0):
+    pa, sa, k = _srcs(dh_srcs)
+    check(lib().vp_lstm_gates_bwd(ptr(pre), n, positions, filters, ptr(c_prev), ptr(g1), ptr(b1), ptr(g2), ptr(b2), ptr(stats1),
+                                  ptr(stats2), _f(forget_bias), pa, sa, k, ptr(dc_next), ptr(dpre), ptr(dc_prev), ptr(dg1),
+                                  ptr(db1), ptr(dg2), ptr(db2), stream_ptr()))
+
+
+def composite_bwd(dgen, masks, masks_cs, layers_addr, layers_cs, dlogits, dlogits_cs, dlayers, dlayers_cs, positions, num_layers):
+    check(lib().vp_composite_bwd(ptr(dgen), ptr(masks), masks_cs, addr(layers_addr), layers_cs, ptr(dlogits), dlogits_cs,
+                                 ptr(dlayers), dlayers_cs, C.c_longlong(positions), num_layers, stream_ptr()))
+
+
+def cdna_apply_bwd(image, kernels, da_addr, da_cs, db_addr, db_cs, dimage, dkernels, n, h, w, kh, kw, nk):
+    check(lib().vp_cdna_apply_bwd(ptr(image), ptr(kernels), addr(da_addr), da_cs, addr(db_addr), db_cs, ptr(dimage), ptr(dkernels),
+                                  n, h, w, kh, kw, nk, stream_ptr()))
+
+
+def cdna_kernel_norm_bwd(raw, out, dout, draw, b, kh, kw, nk):
+    check(lib().vp_cdna_kernel_norm_bwd(ptr(raw), ptr(out), ptr(dout), ptr(draw), b, kh, kw, nk, stream_ptr()))
+
+
+def dense_bwd(x, x_stride, w, dy, dy_stride, b, k, j, dx=None, dx_stride=0, dx_accumulate=False, dw=None, dbias=None,
+              inv_scale=None):
+    check(lib().vp_dense_bwd(ptr(x), x_stride, ptr(w), ptr(inv_scale), ptr(dy), dy_stride, ptr(dx), dx_stride,
+                             int(dx_accumulate), ptr(dw), ptr(dbias), b, k, j, stream_ptr()))
+
+
+def lstm_cell_bwd(gates, c_prev, c_new, dh, dc_next, dgates, dc_prev, b, units, forget_bias=1.0):
+    check(lib().vp_lstm_cell_bwd(ptr(gates), ptr(c_prev), ptr(c_new), ptr(dh), ptr(dc_next), ptr(dgates), ptr(dc_prev), b, units,
+                                 _f(forget_bias), stream_ptr()))
+
+
+def colsum(x_addr, x_cs, out, n, positions, c, scale=1.0, out_stride=None):
+    check(lib().vp_colsum(addr(x_addr), x_cs, ptr(out), c if out_stride is None else out_stride, n, C.c_longlong(positions), c,
+                          _f(scale), stream_ptr()))
+
+
+def axpy_channels(src_addr, src_cs, dst_addr, dst_cs, rows, c, scale=1.0, row_mask=None, rows_per_mask=1, accumulate=True):
+    check(lib().vp_axpy_channels(addr(src_addr), src_cs, addr(dst_addr), dst_cs, C.c_longlong(rows), c, _f(scale), ptr(row_mask),
+                                 C.c_longlong(rows_per_mask), int(accumulate), stream_ptr()))
+
+
+def act_bwd(y_addr, y_cs, dya_addr, dya_cs, dyb_addr, dyb_cs, dx_addr, dx_cs, rows, c, act, alpha=0.0):
+    check(lib().vp_act_bwd(addr(y_addr), y_cs, addr(dya_addr), dya_cs, addr(dyb_addr or 0), dyb_cs, addr(dx_addr), dx_cs,
+                           C.c_longlong(rows), c, act, _f(alpha), stream_ptr()))
+
+
+def avgpool_bwd(dy, dx, dx_cs, n, positions, c):
+    check(lib().vp_avgpool_bwd(ptr(dy), ptr(dx), dx_cs, n, positions, c, stream_ptr()))
+
+
+def sample_z_bwd(mu, lss, eps, dz, dmu, dlss, total, kl_scale):
+    check(lib().vp_sample_z_bwd(ptr(mu), ptr(lss), ptr(eps), ptr(dz), ptr(dmu), ptr(dlss), total, _f(kl_scale), stream_ptr()))
+
+
+def pixel_loss(pred_addr, pred_cs, target_addr, target_cs, dpred_addr, dpred_cs, rows, c, mode, mean_count, grad_scale, out):
+    check(lib().vp_pixel_loss(addr(pred_addr), pred_cs, addr(target_addr), target_cs, addr(dpred_addr or 0), dpred_cs,
+                              C.c_longlong(rows), c, mode, C.c_longlong(mean_count), _f(grad_scale), ptr(out), stream_ptr()))
+
+
+def lsgan_loss(logits, label, n, grad_scale, dlogits, out):
+    check(lib().vp_lsgan_loss(ptr(logits), _f(label), n, _f(grad_scale), ptr(dlogits), ptr(out), stream_ptr()))
+
+
+def kl_loss(mu, lss, rows, nz, out):
+    check(lib().vp_kl_loss(ptr(mu), ptr(lss), rows, nz, ptr(out), stream_ptr()))
+
+
+def cosine_distance(a, b, da, rows, c, grad_scale, out):
+    check(lib().vp_cosine_distance(ptr(a), ptr(b), ptr(da), C.c_longlong(rows), c, _f(grad_scale), ptr(out), stream_ptr()))
+
+
+def adam(p, g, m, v, n, lr, beta1, beta2, step, grad_scale=1.0, eps=1e-8):
+    check(lib().vp_adam(ptr(p), ptr(g), ptr(m), ptr(v), C.c_longlong(n), _f(lr), _f(beta1), _f(beta2), _f(eps), step,
+                        _f(grad_scale), stream_ptr()))
+
+
+def spectral_norm_fwd(w, u, rows, cols, v, s, u_new, scal):
+    check(lib().vp_spectral_norm_fwd(ptr(w), ptr(u), rows, cols, ptr(v), ptr(s), ptr(u_new), ptr(scal), stream_ptr()))
+
+
+def spectral_norm_bwd(w, u, g_wbar, rows, cols, v, s, scal, gs, gt, dw):
+    check(lib().vp_spectral_norm_bwd(ptr(w), ptr(u), ptr(g_wbar), rows, cols, ptr(v), ptr(s), ptr(scal), ptr(gs), ptr(gt), ptr(dw),
+                                     stream_ptr()))
+
+
+def gather_clip(video, t_start, clip, clips, clip_len, pixels, video_batch, batch_offset):
+    check(lib().vp_gather_clip(ptr(video), ptr(t_start), ptr(clip), clips, clip_len, C.c_longlong(pixels), video_batch,
+                               batch_offset, stream_ptr()))
+
+
+def scatter_clip(dclip, t_start, dvideo, clips, clip_len, pixels, video_batch, batch_offset):
+    check(lib().vp_scatter_clip(ptr(dclip), ptr(t_start), ptr(dvideo), clips, clip_len, C.c_longlong(pixels), video_batch,
+                                batch_offset, stream_ptr()))

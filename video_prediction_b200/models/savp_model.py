@@ -22,6 +22,7 @@ import torch
 
 from .. import lib as L
 from .base_model import VideoPredictionModel
+from .savp_train import TrainMixin
 
 RELU_SHIFT = 1e-12
 
@@ -85,6 +86,36 @@ class ConvLayer(object):
         self.wp, self.n_pad, self.kc = L.pack_weights(w, self.k, self.ci_ref, self.co, self.kind, L.WLAYOUT_FWD,
                                                       ci_int=self.ci_int, cmap=self.cmap, out=self.wp)
 
+    def prepare_backward(self):
+        self.geom_bwd = L.geom(self.ke, self.stride, self.pad, not self.transposed)
+        self.wpd = self.dwp = None
+        self.pack_bwd()
+        self.dwp = torch.zeros(L.eff_taps(self.k, self.kind) * self.n_pad * self.kc * 32, device=self.model.device)
+
+    def pack_bwd(self):
+        w = self.model.params[self.wname]
+        self.wpd, self.n_pad_d, self.kc_d = L.pack_weights(w, self.k, self.ci_ref, self.co, self.kind, L.WLAYOUT_DGRAD,
+                                                          ci_int=self.ci_int, cmap=self.cmap, out=getattr(self, 'wpd', None))
+
+    def dgrad(self, dy, dx, dy_c=None, accumulate=False):
+        """dx[.., ci_int] (+)= conv^T(dy): the same engine with the transposed flag flipped."""
+        dyv = L.tensor_view(dy.view((-1,) + tuple(dy.shape[-3:])), self.co if dy_c is None else dy_c)
+        dxv = L.tensor_view(dx.view((-1,) + tuple(dx.shape[-3:])), self.ci_int)
+        L.conv_igemm(dyv, self.geom_bwd, self.wpd, self.n_pad_d, self.kc_d, dxv, None, L.ACT_NONE, 0.0, 1, accumulate)
+
+    def wgrad(self, x, dy, dy_c=None):
+        """grads[w] += dL/dw from ONE GEMM over every position of the (time-stacked) tensors."""
+        xv = L.tensor_view(x.reshape((-1,) + tuple(x.shape[-3:])), self.ci_int)
+        dyv = L.tensor_view(dy.reshape((-1,) + tuple(dy.shape[-3:])), self.co if dy_c is None else dy_c)
+        taps = L.eff_taps(self.k, self.kind)
+        tiles = ((self.n_pad + 127) // 128) * ((self.kc + 3) // 4) * taps
+        pix = xv.n * max(xv.h, dyv.h) * max(xv.w, dyv.w)
+        splits = max(1, min(pix // 256, (592 + tiles - 1) // tiles))
+        self.dwp.zero_()
+        L.conv_wgrad(xv, dyv, self.geom, self.dwp, self.n_pad, self.kc, split_k=splits)
+        L.unpack_wgrad(self.dwp, self.k, self.ci_ref, self.co, self.kind, self.model.grads[self.wname], self.n_pad, self.kc,
+                       ci_int=self.ci_int, cmap=self.cmap)
+
     def fwd(self, x, out, out_off=0, out_c=None, act=L.ACT_NONE, alpha=0.0, split_k=1):
         """x: stacked buffer [.., h, w, cstride] (4-D or 5-D torch tensor, leading dims folded into n)."""
         xv = L.tensor_view(x.view((-1,) + tuple(x.shape[-3:])), self.ci_int)
@@ -93,13 +124,18 @@ class ConvLayer(object):
         L.conv_igemm(xv, self.geom, self.wp, self.n_pad, self.kc, ov, bias, act, alpha, split_k)
 
 
-class SAVPVideoPredictionModel(VideoPredictionModel):
+class SAVPVideoPredictionModel(TrainMixin, VideoPredictionModel):
     def __init__(self, *args, **kwargs):
         super(SAVPVideoPredictionModel, self).__init__(*args, **kwargs)
         self.deterministic = not self.hparams.nz
         self.device = None
         self.params = None
+        self.grads = None
         self.built = False
+        self.world_size = 1
+        self._pending_params = None
+        self.g_adam_t = self.d_adam_t = 0
+        self.dnets = OrderedDict()
 
     # ------------------------------------------------------------------ hparams (savp_model.py:779-846)
     def get_default_hparams_dict(self):
@@ -272,44 +308,85 @@ class SAVPVideoPredictionModel(VideoPredictionModel):
         if C > 4:
             raise NotImplementedError('at most 4 colour channels')
         self.param_specs = self._generator_param_specs()
-        if self.params is None:
-            self.init_params(seed=0)
+        if self.mode == 'train':
+            self.param_specs.update(self._discriminator_param_specs())
+        self._alloc_params()
+        self.init_params(seed=0)
+        if self._pending_params is not None:
+            self._apply_params(self._pending_params)
+            self._pending_params = None
         self._build_generator()
+        if self.mode == 'train':
+            self._build_discriminator()
+            self._build_training()
         self.built = True
         self.set_inputs(inputs)
 
+    def _alloc_params(self):
+        """Flat fp32 buffers (one per optimizer: generator / discriminator, base_model.py:486-487) with
+        per-variable views under the reference's variable names; same for gradients and Adam slots."""
+        dev = self.device
+        gn = [(k, v) for k, v in self.param_specs.items() if k.startswith('generator/')]
+        dn = [(k, v) for k, v in self.param_specs.items() if k.startswith('discriminator/') and v[1] != 'u']
+        un = [(k, v) for k, v in self.param_specs.items() if v[1] == 'u']
+        self.params, self.grads = OrderedDict(), OrderedDict()
+
+        def flat(items):
+            sizes = [(int(np.prod(shape)) + 3) // 4 * 4 for _, (shape, _) in items]   # keep every view 16B aligned
+            buf = torch.zeros(max(sum(sizes), 4), device=dev, dtype=torch.float32)
+            grad = torch.zeros_like(buf)
+            off = 0
+            for (name, (shape, _)), sz in zip(items, sizes):
+                n = int(np.prod(shape))
+                self.params[name] = buf[off:off + n].view(shape)
+                self.grads[name] = grad[off:off + n].view(shape)
+                off += sz
+            return buf, grad
+        self.g_flat, self.g_grad = flat(gn)
+        self.g_m, self.g_v = torch.zeros_like(self.g_flat), torch.zeros_like(self.g_flat)
+        self.d_flat, self.d_grad = flat(dn)
+        self.d_m, self.d_v = torch.zeros_like(self.d_flat), torch.zeros_like(self.d_flat)
+        for name, (shape, _) in un:
+            self.params[name] = torch.zeros(shape, device=dev, dtype=torch.float32)
+
     def init_params(self, seed=0):
+        """Reference initialisers: kernels truncated-normal(0.02), biases 0, gamma 1 / beta 0, u truncated-normal(1)."""
         rng = np.random.default_rng(seed)
         vals = OrderedDict()
+
+        def tn(shape, std):
+            x = rng.standard_normal(size=shape)
+            bad = np.abs(x) > 2.0
+            while bad.any():
+                x[bad] = rng.standard_normal(size=int(bad.sum()))
+                bad = np.abs(x) > 2.0
+            return (x * std).astype(np.float32)
         for name, (shape, init) in self.param_specs.items():
             if init == 'kernel':
-                x = rng.standard_normal(size=shape)
-                bad = np.abs(x) > 2.0
-                while bad.any():
-                    x[bad] = rng.standard_normal(size=int(bad.sum()))
-                    bad = np.abs(x) > 2.0
-                vals[name] = (x * 0.02).astype(np.float32)
+                vals[name] = tn(shape, 0.02)
+            elif init == 'u':
+                vals[name] = tn(shape, 1.0)
             elif init == 'ones':
                 vals[name] = np.ones(shape, np.float32)
             else:
                 vals[name] = np.zeros(shape, np.float32)
-        self.set_params(vals)
+        self._apply_params(vals)
+
+    def _apply_params(self, values):
+        for name, v in values.items():
+            if name not in self.params:
+                continue        # e.g. discriminator variables offered to a test-mode model
+            t = torch.as_tensor(np.asarray(v.detach().cpu() if torch.is_tensor(v) else v), dtype=torch.float32)
+            if tuple(t.shape) != tuple(self.params[name].shape):
+                raise ValueError('shape mismatch for %s: %s vs %s' % (name, tuple(t.shape), tuple(self.params[name].shape)))
+            self.params[name].copy_(t.to(self.device))
 
     def set_params(self, values):
         """values: name -> array/tensor with the reference's variable names and shapes."""
-        dev = self.device or torch.device('cuda', torch.cuda.current_device())
-        self.device = dev
-        specs = getattr(self, 'param_specs', None)
-        if self.params is None:
-            self.params = OrderedDict()
-        for name, v in values.items():
-            t = torch.as_tensor(np.asarray(v.detach().cpu() if torch.is_tensor(v) else v), dtype=torch.float32)
-            if specs is not None and name in specs and tuple(t.shape) != tuple(specs[name][0]):
-                raise ValueError('shape mismatch for %s: %s vs %s' % (name, tuple(t.shape), specs[name][0]))
-            if name in self.params:
-                self.params[name].copy_(t)
-            else:
-                self.params[name] = t.to(dev).contiguous()
+        if not self.built and self.params is None:
+            self._pending_params = dict(values)
+            return
+        self._apply_params(values)
         if self.built:
             self._pack_all()
 
@@ -457,6 +534,8 @@ class SAVPVideoPredictionModel(VideoPredictionModel):
     def _pack_all(self):
         for c in self.convs:
             c.pack()
+            if getattr(c, 'wpd', None) is not None:
+                c.pack_bwd()
 
     # ------------------------------------------------------------------ inputs
     def set_inputs(self, inputs, noise=None, sampling=None):
@@ -535,7 +614,6 @@ class SAVPVideoPredictionModel(VideoPredictionModel):
         L.sample_z(Bf['zmu'], Bf['zlss'], Bf['eps'], Bf['zpost'], S * B * hp.nz)
         # zs for the two unrolls: posterior half, prior half = [z_post[:ctx-1], z_prior] (savp_model.py:724-725)
         nz = hp.nz
-        L.copy_channels(Bf['zpost'].data_ptr(), nz, Bf['zs'].data_ptr(), 2 * B * nz // 2 * 0 + nz, 0, nz)  # no-op (rows=0)
         zs = Bf['zs']
         for t in range(S):
             L.copy_channels(Bf['zpost'][t].data_ptr(), nz, zs[t, :B].data_ptr(), nz, B, nz)
@@ -668,7 +746,7 @@ class SAVPVideoPredictionModel(VideoPredictionModel):
         L.composite(Bf['mlog'][t], 8, mk.data_ptr() + 4 * msp.off('l0'), msp.cstride, Bf['masks'][t], 8, Bf['gen'][t],
                     NB * HW, self.nlayers)
 
-    def generator_forward(self):
+    def generator_forward(self, collect=True):
         hp = self.hparams
         if hp.nz:
             self._posterior_forward()
@@ -684,7 +762,8 @@ class SAVPVideoPredictionModel(VideoPredictionModel):
                 z[..., sp.off('h'):sp.off('h') + d['oc']] = 0
         for t in range(self.S):
             self._gen_step(t)
-        self._collect_outputs()
+        if collect:
+            self._collect_outputs()
 
     def _collect_outputs(self):
         B, C = self.B, self.C

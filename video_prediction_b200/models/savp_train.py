@@ -1,0 +1,566 @@
+"""Training half of the SAVP path on B200: spectrally-normalised video discriminators, losses,
+back-propagation through time over the time-stacked buffers, and the two TF-style Adam steps.
+
+Restates the reference's single-tower training graph (base_model.py:402-516): per step
+  UPDATE_OPS(u) -> D forward on {enc_real, enc_fake, real, fake} -> d_loss -> D grads -> Adam(D)
+  -> D forward again with the updated weights (new clip offsets) -> g_loss_post -> G grads -> Adam(G).
+All convolution gradients run on the tcgen05 engine: dgrad = the same implicit GEMM with the
+transposed-flag flipped and [ci][co] tap matrices; wgrad = one MN-major GEMM per layer over ALL
+timesteps of the unroll at once (GEMM-K = (T-1)*NB*H*W pixels) instead of per-step accumulation."""
+from __future__ import annotations
+
+from collections import OrderedDict
+
+import numpy as np
+import torch
+
+from .. import lib as L
+
+VIDEO_D_LAYERS = [  # networks.py:83-102: (scope, ndf multiplier, kernel, strides (t,h,w))
+    ('sn_conv0_0', 1, 3, (1, 1, 1)), ('sn_conv0_1', 2, 4, (1, 2, 2)),
+    ('sn_conv1_0', 2, 3, (1, 1, 1)), ('sn_conv1_1', 4, 4, (1, 2, 2)),
+    ('sn_conv2_0', 4, 3, (1, 1, 1)), ('sn_conv2_1', 8, 4, (2, 2, 2)),
+    ('sn_conv3_0', 8, 3, (1, 1, 1)),
+]
+
+LOSS_SLOTS = ['gen_l1_loss', 'gen_l2_loss', 'gen_kl_loss', 'gen_video_sn_gan_loss', 'gen_video_sn_vae_gan_loss',
+              'gen_video_sn_vae_gan_feature_cdist_loss', 'gen_video_sn_gan_feature_cdist_loss',
+              'discrim_video_sn_gan_loss', 'discrim_video_sn_vae_gan_loss']
+
+
+def _ceil4(v):
+    return (v + 3) // 4 * 4
+
+
+class SNLayer(object):
+    """A spectrally-normalised conv3d (or the final dense) of the video discriminator."""
+
+    def __init__(self, model, scope, name, k, stride, cin_ref, cin_int, cmap, co, is_fc=False, fc_in=0):
+        self.m, self.is_fc = model, is_fc
+        self.k, self.stride, self.co = k, stride, co
+        self.cin_ref, self.cin_int = cin_ref, cin_int
+        sub = 'dense' if is_fc else 'conv3d'
+        self.wname = '%s/%s/%s/kernel' % (scope, name, sub)
+        self.uname = '%s/%s/%s/u' % (scope, name, sub)
+        self.bname = '%s/%s/%s/bias' % (scope, name, sub)
+        self.rows = fc_in if is_fc else k * k * k * cin_ref
+        self.cols = co
+        dev = model.device
+        z = lambda *s: torch.zeros(*s, device=dev, dtype=torch.float32)
+        self.v, self.s, self.u_new, self.scal = z(self.rows), z(self.cols), z(self.cols), z(4)
+        self.gs, self.gt = z(self.cols), z(self.rows)
+        self.gwbar = z(self.rows * self.cols)
+        self.u_next = z(self.cols)
+        self.cmap = None if cmap is None else torch.tensor(cmap, dtype=torch.int32, device=dev)
+        if not is_fc:
+            self.geom = L.geom((k, k, k), stride, (1, 1, 1), False)
+            self.geom_t = L.geom((k, k, k), stride, (1, 1, 1), True)
+            self.wp = self.wpd = self.dwp = None
+
+    @property
+    def sigma(self):
+        return self.scal[2:3]
+
+    def sn_forward(self):
+        P = self.m.params
+        L.spectral_norm_fwd(P[self.wname], P[self.uname], self.rows, self.cols, self.v, self.s, self.u_new, self.scal)
+
+    def pack(self):
+        if self.is_fc:
+            return
+        w = self.m.params[self.wname]
+        kk = (self.k,) * 3
+        self.wp, self.n_pad, self.kc = L.pack_weights(w, kk, self.cin_ref, self.co, L.WKIND_PLAIN, L.WLAYOUT_FWD,
+                                                      ci_int=self.cin_int, cmap=self.cmap, inv_scale=self.sigma, out=self.wp)
+        self.wpd, self.n_pad_d, self.kc_d = L.pack_weights(w, kk, self.cin_ref, self.co, L.WKIND_PLAIN, L.WLAYOUT_DGRAD,
+                                                          ci_int=self.cin_int, cmap=self.cmap, inv_scale=self.sigma, out=self.wpd)
+        if self.dwp is None:
+            self.dwp = torch.zeros(self.k ** 3 * self.n_pad * self.kc * 32, device=w.device)
+
+    def fwd(self, x, out):
+        L.conv_igemm(L.tensor_view(x, self.cin_int), self.geom, self.wp, self.n_pad, self.kc, L.tensor_view(out, self.co),
+                     self.m.params[self.bname], L.ACT_LRELU, 0.1)
+
+    def dgrad(self, dy, dx):
+        L.conv_igemm(L.tensor_view(dy, self.co), self.geom_t, self.wpd, self.n_pad_d, self.kc_d, L.tensor_view(dx, self.cin_int))
+
+    def wgrad(self, x, dy):
+        """dW += SN-backward(dL/dWbar) with dL/dWbar from the tensor-core wgrad GEMM."""
+        m = self.m
+        self.dwp.zero_()
+        L.conv_wgrad(L.tensor_view(x, self.cin_int), L.tensor_view(dy, self.co), self.geom, self.dwp, self.n_pad, self.kc,
+                     split_k=m.wgrad_splits(x))
+        self.gwbar.zero_()
+        L.unpack_wgrad(self.dwp, (self.k,) * 3, self.cin_ref, self.co, L.WKIND_PLAIN, self.gwbar, self.n_pad, self.kc,
+                       ci_int=self.cin_int, cmap=self.cmap)
+        self.sn_backward()
+
+    def sn_backward(self):
+        P = self.m.params
+        L.spectral_norm_bwd(P[self.wname], P[self.uname], self.gwbar, self.rows, self.cols, self.v, self.s, self.scal, self.gs,
+                            self.gt, self.m.grads[self.wname])
+
+
+class TrainMixin(object):
+    # ------------------------------------------------------------------ parameter specs
+    def _d_scopes(self):
+        hp = self.hparams
+        scopes = []
+        if hp.video_sn_gan_weight or hp.video_sn_vae_gan_weight:
+            if hp.nz:
+                scopes.append('discriminator/encoder/video')
+            scopes.append('discriminator/video')
+        return scopes
+
+    def _d_shapes(self):
+        """Output dims (T',H',W',C') of the 7 conv3d layers for clips [clip_length,H,W,C]."""
+        hp = self.hparams
+        dims = (hp.clip_length, self.H, self.W)
+        out = []
+        for name, mult, k, st in VIDEO_D_LAYERS:
+            dims = tuple((d + 2 - k) // s + 1 for d, s in zip(dims, st))
+            out.append(dims + (hp.ndf * mult,))
+        return out
+
+    def _discriminator_param_specs(self):
+        hp = self.hparams
+        specs = OrderedDict()
+        shapes = self._d_shapes()
+        for scope in self._d_scopes():
+            cin = self.C
+            for (name, mult, k, st), shp in zip(VIDEO_D_LAYERS, shapes):
+                co = hp.ndf * mult
+                specs['%s/%s/conv3d/kernel' % (scope, name)] = ((k, k, k, cin, co), 'kernel')
+                specs['%s/%s/conv3d/u' % (scope, name)] = ((1, co), 'u')
+                specs['%s/%s/conv3d/bias' % (scope, name)] = ((co,), 'zeros')
+                cin = co
+            f = int(np.prod(shapes[-1]))
+            specs['%s/sn_fc4/dense/kernel' % scope] = ((f, 1), 'kernel')
+            specs['%s/sn_fc4/dense/u' % scope] = ((1, 1), 'u')
+            specs['%s/sn_fc4/dense/bias' % scope] = ((1,), 'zeros')
+        return specs
+
+    # ------------------------------------------------------------------ build (training side)
+    def wgrad_splits(self, x):
+        """K-splits for the wgrad GEMM so that the grid covers the 148 SMs a few times."""
+        pix = int(np.prod(x.shape[:-1]))
+        return max(1, min(64, pix // (64 * 24)))
+
+    def _build_discriminator(self):
+        hp = self.hparams
+        B, H, W, C = self.B, self.H, self.W, self.C
+        z = self._z
+        shapes = self._d_shapes()
+        self.dnets = OrderedDict()
+        for scope in self._d_scopes():
+            net = dict(scope=scope, layers=[], feat=[], dfeat=[], dcd=[])
+            cin_ref, cin_int, cmap = C, 4, list(range(C)) + [-1] * (4 - C)
+            nb = 2 * B
+            net['clip'] = z(nb, hp.clip_length, H, W, 4)
+            net['dclip'] = z(nb, hp.clip_length, H, W, 4)
+            for (name, mult, k, st), shp in zip(VIDEO_D_LAYERS, shapes):
+                co = hp.ndf * mult
+                net['layers'].append(SNLayer(self, scope, name, k, st, cin_ref, cin_int, cmap, co))
+                net['feat'].append(z(nb, *shp))
+                net['dfeat'].append(z(nb, *shp))
+                net['dcd'].append(z(B, *shp))
+                cin_ref, cin_int, cmap = co, co, None
+            f = int(np.prod(shapes[-1]))
+            net['fc'] = SNLayer(self, scope, 'sn_fc4', 1, None, f, f, None, 1, is_fc=True, fc_in=f)
+            net['logits'] = z(nb)
+            net['dlogits'] = z(nb)
+            net['tstart'] = torch.zeros(2, B, dtype=torch.int32, device=self.device)
+            self.dnets[scope] = net
+
+    def _build_training(self):
+        """Gradient buffers mirroring the forward buffers (time-stacked) + dgrad weight packs."""
+        Bf, z = self.Bf, self._z
+        S, NB, H, W = self.S, self.NB, self.H, self.W
+        G = self.Gb = {}
+        hp = self.hparams
+        for d in self.gl:
+            li = d['li']
+            G['din%d' % li] = torch.zeros_like(Bf['in%d' % li])
+            G['dpre%d' % li] = torch.zeros_like(Bf['pre%d' % li])
+            if d['use']:
+                G['drin%d' % li] = torch.zeros_like(Bf['rin%d' % li])
+                G['dgpre%d' % li] = torch.zeros_like(Bf['gpre%d' % li])
+                G['dc%d' % li] = torch.zeros_like(Bf['c%d' % li])
+        ngf = hp.ngf
+        G['dgen'] = z(S, NB, H, W, 4)
+        G['dimg'] = z(S, NB, H, W, 4)
+        G['dmlog'] = z(S, NB, H, W, 8)
+        G['dlay'] = z(S, NB, H, W, 4 * self.nlayers)
+        G['dmk'] = torch.zeros_like(Bf['mk'])
+        G['dmpre'] = z(S, NB, H, W, ngf)
+        G['dspre'] = z(S, NB, H, W, ngf)
+        G['dsimg'] = z(S, NB, H, W, 4)
+        G['dhs'] = z(S, NB, H, W, ngf)
+        G['dtop'] = z(S, NB, H, W, self.gl[-1]['oc'])
+        G['dkern'] = torch.zeros_like(Bf['kern'])
+        G['dkraw'] = torch.zeros_like(Bf['kraw'])
+        G['dsmall'] = torch.zeros_like(Bf['small'])
+        if self.Zc:
+            G['dzvec'] = torch.zeros_like(Bf['zvec'])
+        if hp.nz:
+            nz = hp.nz
+            G['dzh'] = z(S + 1, NB, nz)        # gradient w.r.t. rnn_z h[t+1] (slot t+1)
+            G['dzc'] = z(S + 1, NB, nz)
+            G['dzgates'] = z(S, NB, 4 * nz)
+            G['dzcat'] = z(S, NB, 2 * nz)
+            G['dzpost'] = z(S, self.B, nz)
+            G['dzmu'] = z(S, self.B, nz)
+            G['dzlss'] = z(S, self.B, nz)
+            G['depool'] = torch.zeros_like(Bf['epool'])
+            for i, el in enumerate(self.enc_layers):
+                G['depre%d' % i] = torch.zeros_like(Bf['epre%d' % i])
+                if i > 0:
+                    G['deact%d' % i] = torch.zeros_like(Bf['eact%d' % i])
+        self.loss_vals = z(len(LOSS_SLOTS))
+        for c in self.convs:
+            c.prepare_backward()
+
+    # ------------------------------------------------------------------ discriminator forward / backward
+    def _d_sn_and_pack(self):
+        for net in self.dnets.values():
+            for lay in net['layers'] + [net['fc']]:
+                lay.sn_forward()
+                lay.pack()
+
+    def _d_gather(self, net, which, t_real, t_fake, fake_off, rows_real=True):
+        """Fills net['clip']: rows [0,B) real clip (optional), rows [B,2B) fake clip."""
+        hp = self.hparams
+        B, NB, HW = self.B, self.NB, self.H * self.W
+        Bf = self.Bf
+        if rows_real:
+            L.gather_clip(Bf['x'][1:], t_real, net['clip'][:B], B, hp.clip_length, HW, NB, 0)
+        L.gather_clip(Bf['gen'], t_fake, net['clip'][B:], B, hp.clip_length, HW, NB, fake_off)
+
+    def _d_forward(self, net, r0, r1):
+        """Runs the tower on clip rows [r0, r1)."""
+        x = net['clip'][r0:r1]
+        for lay, feat in zip(net['layers'], net['feat']):
+            lay.fwd(x, feat[r0:r1])
+            x = feat[r0:r1]
+        fc = net['fc']
+        n = r1 - r0
+        net['logits'][r0:r1].zero_()
+        P = self.params
+        L.dense_fwd(x, fc.rows, P[fc.wname], P[fc.bname], net['logits'][r0:r1], 1, n, fc.rows, 1, k_splits=64,
+                    inv_scale=fc.sigma)
+
+    def _d_backward(self, net, r0, r1, with_wgrad, to_clip, dcd=None):
+        """Back-propagates net['dlogits'][r0:r1] (and optional per-layer feature gradients dcd, rows [0, r1-r0))."""
+        P, Gp = self.params, self.grads
+        n = r1 - r0
+        fc = net['fc']
+        feats, dfeats = net['feat'], net['dfeat']
+        last = feats[-1][r0:r1]
+        L.dense_bwd(last, fc.rows, P[fc.wname], net['dlogits'][r0:r1], 1, n, fc.rows, 1, dx=dfeats[-1][r0:r1], dx_stride=fc.rows,
+                    inv_scale=fc.sigma)
+        if with_wgrad:
+            fc.gwbar.zero_()
+            L.dense_bwd(last, fc.rows, P[fc.wname], net['dlogits'][r0:r1], 1, n, fc.rows, 1, dw=fc.gwbar, dbias=Gp[fc.bname])
+            fc.sn_backward()
+        for l in range(len(feats) - 1, -1, -1):
+            lay = net['layers'][l]
+            y, dy = feats[l][r0:r1], dfeats[l][r0:r1]
+            rows = int(np.prod(y.shape[:-1]))
+            co = lay.co
+            extra = dcd[l][:n] if dcd is not None else None
+            L.act_bwd(y.data_ptr(), co, dy.data_ptr(), co, extra.data_ptr() if extra is not None else 0, co, dy.data_ptr(), co,
+                      rows, co, L.ACT_LRELU, 0.1)
+            x = feats[l - 1][r0:r1] if l > 0 else net['clip'][r0:r1]
+            if with_wgrad:
+                L.colsum(dy.data_ptr(), co, Gp[lay.bname], 1, rows, co)
+                lay.wgrad(x, dy)
+            if l > 0:
+                lay.dgrad(dy, dfeats[l - 1][r0:r1])
+            elif to_clip:
+                lay.dgrad(dy, net['dclip'][r0:r1])
+
+    # ------------------------------------------------------------------ generator backward
+    def _gen_backward_step(self, t):
+        hp = self.hparams
+        Bf, G, P, Gp = self.Bf, self.Gb, self.params, self.grads
+        NB, H, W, C = self.NB, self.H, self.W, self.C
+        HW = H * W
+        S = self.S
+        sc = 'generator/rnn/savp_cell'
+        nl, ngf = self.nl, hp.ngf
+        msp = self.mk_spec
+        mk, dmk = Bf['mk'][t], G['dmk'][t]
+        nlay = self.nlayers
+        # compositing + masks conv
+        L.composite_bwd(G['dgen'][t], Bf['masks'][t], 8, mk.data_ptr() + 4 * msp.off('l0'), msp.cstride, G['dmlog'][t], 8,
+                        G['dlay'][t], 4 * nlay, NB * HW, nlay)
+        self.conv_masks.dgrad(G['dmlog'][t], dmk, dy_c=nlay)
+        # h_masks branch
+        nm = '%s/h%d_masks/InstanceNorm' % (sc, nl)
+        L.inorm_act_bwd(Bf['mpre'][t].data_ptr(), ngf, [(dmk.data_ptr() + 4 * msp.off('hm'), msp.cstride)], G['dmpre'][t].data_ptr(),
+                        ngf, NB, HW, ngf, P[nm + '/gamma'], P[nm + '/beta'], Bf['mst'][t], L.ACT_RELU, 0.0, Gp[nm + '/gamma'],
+                        Gp[nm + '/beta'])
+        self.conv_hmasks.dgrad(G['dmpre'][t], G['dtop'][t])
+        # scratch branch
+        so = msp.off('l%d' % (nlay - 1))
+        L.act_bwd(mk.data_ptr() + 4 * so, msp.cstride, dmk.data_ptr() + 4 * so, msp.cstride,
+                  G['dlay'][t].data_ptr() + 4 * 4 * (nlay - 1), 4 * nlay, G['dsimg'][t].data_ptr(), 4, NB * HW, C, L.ACT_SIGMOID)
+        self.conv_simg.dgrad(G['dsimg'][t], G['dhs'][t], dy_c=C)
+        nm = '%s/h%d_scratch/InstanceNorm' % (sc, nl)
+        L.inorm_act_bwd(Bf['spre'][t].data_ptr(), ngf, [(G['dhs'][t].data_ptr(), ngf)], G['dspre'][t].data_ptr(), ngf, NB, HW, ngf,
+                        P[nm + '/gamma'], P[nm + '/beta'], Bf['sst'][t], L.ACT_RELU, 0.0, Gp[nm + '/gamma'], Gp[nm + '/beta'])
+        self.conv_scratch.dgrad(G['dspre'][t], G['dtop'][t], accumulate=True)
+        # CDNA
+        nk, kh, kw = self.nk, self.kh, self.kw
+        G['dimg'][t].zero_()
+        G['dkern'][t].zero_()
+        L.cdna_apply_bwd(Bf['img'][t], Bf['kern'][t], dmk.data_ptr() + 4 * msp.off('l0'), msp.cstride, G['dlay'][t].data_ptr(),
+                         4 * nlay, G['dimg'][t], G['dkern'][t], NB, H, W, kh, kw, nk)
+        L.cdna_kernel_norm_bwd(Bf['kraw'][t], Bf['kern'][t], G['dkern'][t], G['dkraw'][t], NB, kh, kw, nk)
+        K = Bf['small'].shape[-1]
+        dn = sc + '/cdna_kernels/dense'
+        L.dense_bwd(Bf['small'][t], K, P[dn + '/kernel'], G['dkraw'][t], kh * kw * nk, NB, K, kh * kw * nk, dx=G['dsmall'][t],
+                    dx_stride=K, dw=Gp[dn + '/kernel'], dbias=Gp[dn + '/bias'])
+        # encoder/decoder stack in reverse
+        n_enc = len(self.enc_specs)
+        for li in range(nl - 1, -1, -1):
+            d = self.gl[li]
+            oc, hh, ww = d['oc'], d['h'], d['w']
+            srcs = []
+            if li == nl - 1:
+                srcs.append((G['dtop'][t].data_ptr(), oc))
+            else:
+                sp = self.gl[li + 1]['in_spec']
+                srcs.append((G['din%d' % (li + 1)][t].data_ptr() + 4 * sp.off('x'), sp.cstride))
+            if li < n_enc - 1:
+                i = n_enc - 1 - li
+                sp = self.gl[n_enc + i]['in_spec']
+                srcs.append((G['din%d' % (n_enc + i)][t].data_ptr() + 4 * sp.off('skip'), sp.cstride))
+            if li == n_enc - 1:
+                srcs.append((G['dsmall'][t].data_ptr(), oc))
+            nm = '%s/h%d/InstanceNorm' % (sc, li)
+            if d['use']:
+                rsp = d['rin_spec']
+                if t + 1 < S:
+                    srcs.append((G['drin%d' % li][t + 1].data_ptr() + 4 * rsp.off('h'), rsp.cstride))
+                b = d['rname']
+                L.lstm_gates_bwd(Bf['gpre%d' % li][t], NB, hh * ww, oc, Bf['c%d' % li][t],
+                                 P[b + '/input_transform_forget_output/gamma'], P[b + '/input_transform_forget_output/beta'],
+                                 P[b + '/state/gamma'], P[b + '/state/beta'], Bf['gst1_%d' % li][t], Bf['gst2_%d' % li][t], srcs,
+                                 G['dc%d' % li][t + 1] if t + 1 < S else None, G['dgpre%d' % li][t], G['dc%d' % li][t],
+                                 Gp[b + '/input_transform_forget_output/gamma'], Gp[b + '/input_transform_forget_output/beta'],
+                                 Gp[b + '/state/gamma'], Gp[b + '/state/beta'])
+                d['rconv'].dgrad(G['dgpre%d' % li][t], G['drin%d' % li][t])
+                srcs = [(G['drin%d' % li][t].data_ptr() + 4 * rsp.off('x'), rsp.cstride)]
+            L.inorm_act_bwd(Bf['pre%d' % li][t].data_ptr(), oc, srcs, G['dpre%d' % li][t].data_ptr(), oc, NB, hh * ww, oc,
+                            P[nm + '/gamma'], P[nm + '/beta'], Bf['nst%d' % li][t], L.ACT_RELU, 0.0, Gp[nm + '/gamma'],
+                            Gp[nm + '/beta'])
+            d['conv'].dgrad(G['dpre%d' % li][t], G['din%d' % li][t])
+        # gradient w.r.t. the input image of this step: CDNA path + first conv's 'image' slot
+        sp = self.gl[0]['in_spec']
+        L.axpy_channels(G['din0'][t].data_ptr() + 4 * sp.off('image'), sp.cstride, G['dimg'][t].data_ptr(), 4, NB * HW, 4)
+        if t > 0:   # image_t was gen_{t-1} wherever ground truth was not used (sel == 0)
+            L.axpy_channels(G['dimg'][t].data_ptr(), 4, G['dgen'][t - 1].data_ptr(), 4, NB * HW, 4, row_mask=Bf['sel'][t],
+                            rows_per_mask=HW)
+
+    def _gen_backward_params(self):
+        """Time-batched weight/bias gradients + the z path (dense LSTM on z, posterior encoder)."""
+        hp = self.hparams
+        Bf, G, P, Gp = self.Bf, self.Gb, self.params, self.grads
+        S, NB, B, H, W, C = self.S, self.NB, self.B, self.H, self.W, self.C
+        rows_top = S * NB * H * W
+        for d in self.gl:
+            li = d['li']
+            d['conv'].wgrad(Bf['in%d' % li], G['dpre%d' % li])
+            L.colsum(G['dpre%d' % li].data_ptr(), d['oc'], Gp[d['conv'].bname], 1, S * NB * d['h'] * d['w'], d['oc'])
+            if d['use']:
+                d['rconv'].wgrad(Bf['rin%d' % li][:S], G['dgpre%d' % li])
+        top = Bf['out%d' % (self.nl - 1)]
+        ngf = hp.ngf
+        self.conv_scratch.wgrad(top, G['dspre'])
+        L.colsum(G['dspre'].data_ptr(), ngf, Gp[self.conv_scratch.bname], 1, rows_top, ngf)
+        self.conv_hmasks.wgrad(top, G['dmpre'])
+        L.colsum(G['dmpre'].data_ptr(), ngf, Gp[self.conv_hmasks.bname], 1, rows_top, ngf)
+        self.conv_simg.wgrad(Bf['hs'], G['dsimg'], dy_c=C)
+        L.colsum(G['dsimg'].data_ptr(), 4, Gp[self.conv_simg.bname], 1, rows_top, C)
+        self.conv_masks.wgrad(Bf['mk'], G['dmlog'], dy_c=self.nlayers)
+        L.colsum(G['dmlog'].data_ptr(), 8, Gp[self.conv_masks.bname], 1, rows_top, self.nlayers)
+        if not self.Zc:
+            return
+        # tile_concat adjoint: sum the z-slot gradients of every concat buffer over space
+        Zc, Zp = self.Zc, _ceil4(self.Zc)
+        G['dzvec'].zero_()
+        for d in self.gl:
+            li = d['li']
+            for key, spn in (('din%d' % li, 'in_spec'), ('drin%d' % li, 'rin_spec')):
+                if spn == 'rin_spec' and not d['use']:
+                    continue
+                buf = G[key][:S]
+                sp = d[spn]
+                L.colsum(buf.data_ptr() + 4 * sp.off('z'), sp.cstride, G['dzvec'], S * NB, buf.shape[2] * buf.shape[3], Zc, out_stride=Zp)
+        if not hp.nz:
+            return
+        nz, A = hp.nz, self.A
+        b = 'generator/rnn/savp_cell/lstm_z/basic_lstm_cell'
+        G['dzh'].zero_()
+        for t in range(S - 1, -1, -1):
+            # dh[t+1] = z-slot gradient (rnn_z part) + recurrent part already accumulated in dzh[t+1]
+            L.axpy_channels(G['dzvec'][t].data_ptr() + 4 * A, Zp, G['dzh'][t + 1].data_ptr(), nz, NB, nz)
+            L.lstm_cell_bwd(Bf['zgates'][t], Bf['zc'][t], Bf['zc'][t + 1], G['dzh'][t + 1], G['dzc'][t + 1] if t + 1 < S else None,
+                            G['dzgates'][t], G['dzc'][t], NB, nz)
+            L.dense_bwd(Bf['zcat'][t], 2 * nz, P[b + '/kernel'], G['dzgates'][t], 4 * nz, NB, 2 * nz, 4 * nz, dx=G['dzcat'][t],
+                        dx_stride=2 * nz, dw=Gp[b + '/kernel'], dbias=Gp[b + '/bias'])
+            L.axpy_channels(G['dzcat'][t].data_ptr() + 4 * nz, 2 * nz, G['dzh'][t].data_ptr(), nz, NB, nz)
+        # dzs -> posterior sample: posterior half always, prior half for the context steps (savp_model.py:724-725)
+        for t in range(S):
+            L.axpy_channels(G['dzcat'][t, :B].data_ptr(), 2 * nz, G['dzpost'][t].data_ptr(), nz, B, nz, accumulate=False)
+            if t < hp.context_frames - 1:
+                L.axpy_channels(G['dzcat'][t, B:].data_ptr(), 2 * nz, G['dzpost'][t].data_ptr(), nz, B, nz)
+        klw = self.kl_weight_at(self.global_step) if hp.kl_weight else 0.0
+        L.sample_z_bwd(Bf['zmu'], Bf['zlss'], Bf['eps'], G['dzpost'], G['dzmu'], G['dzlss'], S * B * nz, (klw or 0.0) / (S * B))
+        sc = 'generator/encoder'
+        last = self.enc_layers[-1]
+        oc = last['oc']
+        L.dense_bwd(Bf['epool'], oc, P[sc + '/z_mu/dense/kernel'], G['dzmu'], nz, S * B, oc, nz, dx=G['depool'], dx_stride=oc,
+                    dw=Gp[sc + '/z_mu/dense/kernel'], dbias=Gp[sc + '/z_mu/dense/bias'])
+        L.dense_bwd(Bf['epool'], oc, P[sc + '/z_log_sigma_sq/dense/kernel'], G['dzlss'], nz, S * B, oc, nz, dx=G['depool'],
+                    dx_stride=oc, dx_accumulate=True, dw=Gp[sc + '/z_log_sigma_sq/dense/kernel'],
+                    dbias=Gp[sc + '/z_log_sigma_sq/dense/bias'])
+        n_l = len(self.enc_layers)
+        for i in range(n_l - 1, -1, -1):
+            el = self.enc_layers[i]
+            oc, pos = el['oc'], el['h'] * el['w']
+            if i == n_l - 1:
+                dact = G['deact%d' % i] if i > 0 else G['depre0']
+                L.avgpool_bwd(G['depool'], dact, oc, S * B, pos, oc)
+            if i > 0:
+                nm = '%s/layer_%d/InstanceNorm' % (sc, i + 1)
+                L.inorm_act_bwd(Bf['epre%d' % i].data_ptr(), oc, [(G['deact%d' % i].data_ptr(), oc)], G['depre%d' % i].data_ptr(), oc,
+                                S * B, pos, oc, P[nm + '/gamma'], P[nm + '/beta'], Bf['est%d' % i], L.ACT_LRELU, 0.2,
+                                Gp[nm + '/gamma'], Gp[nm + '/beta'])
+                x_in = Bf['eact%d' % (i - 1)] if i > 1 else Bf['epre0']
+                dst = G['deact%d' % (i - 1)] if i > 1 else G['depre0']
+                el['conv'].dgrad(G['depre%d' % i], dst)
+            else:
+                # layer 1 stored the lrelu OUTPUT (activation fused in the conv epilogue)
+                L.act_bwd(Bf['epre0'].data_ptr(), oc, G['depre0'].data_ptr(), oc, 0, oc, G['depre0'].data_ptr(), oc, S * B * pos, oc,
+                          L.ACT_LRELU, 0.2)
+                x_in = Bf['pairs']
+            el['conv'].wgrad(x_in, G['depre%d' % i])
+            L.colsum(G['depre%d' % i].data_ptr(), oc, Gp[el['conv'].bname], 1, S * B * pos, oc)
+
+    # ------------------------------------------------------------------ one optimisation step
+    def _slot(self, name):
+        return self.loss_vals[LOSS_SLOTS.index(name):LOSS_SLOTS.index(name) + 1]
+
+    def _set_tstarts(self, noise):
+        hp = self.hparams
+        hi = self.S - hp.clip_length + 1
+        keys = {'discriminator/encoder/video': ('enc_real', 'enc_fake'), 'discriminator/video': ('real', 'fake')}
+        for scope, net in self.dnets.items():
+            for w, which in enumerate(('d_pre', 'd_post')):
+                for r, key in enumerate(keys[scope]):
+                    if noise is not None and which in noise:
+                        v = torch.as_tensor(noise[which][key]).to(torch.int32)
+                    else:
+                        g = torch.Generator().manual_seed(1000003 * self.global_step + 17 * w + r + 1)
+                        v = torch.randint(0, hi, (self.B,), generator=g, dtype=torch.int32)
+                    net.setdefault('ts', {})[(which, r)] = v.to(self.device)
+
+    def train_step(self, inputs=None, noise=None, sampling=None, allreduce=None):
+        """One optimisation step (D then G, base_model.py:477-516).  Returns dict of loss values (python floats)
+        unless `fetch_losses=False` was set on the model.  `allreduce(flat_grad)` (optional) is called on the flat
+        discriminator and generator gradient buffers before their Adam steps (data parallel)."""
+        hp = self.hparams
+        if inputs is not None:
+            self.set_inputs(inputs, noise, sampling)
+        Bf, G, P = self.Bf, self.Gb, self.params
+        B, NB, S, C = self.B, self.NB, self.S, self.C
+        HW = self.H * self.W
+        step = self.global_step
+        lr = self.learning_rate_at(step)
+        self.loss_vals.zero_()
+        self.generator_forward(collect=False)
+        has_d = bool(self.dnets)
+        world = float(self.world_size)
+        if has_d:
+            self._set_tstarts(noise)
+            self.d_grad.zero_()
+            self._d_sn_and_pack()
+            for net in self.dnets.values():     # UPDATE_OPS (ops.py:1046-1048): u' of the start-of-step weights
+                for lay in net['layers'] + [net['fc']]:
+                    lay.u_next.copy_(lay.u_new)
+            for scope, net in self.dnets.items():
+                enc = scope.endswith('encoder/video')
+                w = hp.video_sn_vae_gan_weight if enc else hp.video_sn_gan_weight
+                self._d_gather(net, 'pre', net['ts'][('d_pre', 0)], net['ts'][('d_pre', 1)], 0 if enc else (B if hp.nz else 0))
+                self._d_forward(net, 0, 2 * B)
+                slot = self._slot('discrim_video_sn_vae_gan_loss' if enc else 'discrim_video_sn_gan_loss')
+                L.lsgan_loss(net['logits'][:B], 1.0, B, w, net['dlogits'][:B], slot)
+                L.lsgan_loss(net['logits'][B:], 0.0, B, w, net['dlogits'][B:], slot)
+                self._d_backward(net, 0, 2 * B, with_wgrad=True, to_clip=False)
+            if allreduce is not None:
+                allreduce(self.d_grad)
+            self.d_adam_t += 1
+            L.adam(self.d_flat, self.d_grad, self.d_m, self.d_v, self.d_flat.numel(), lr, hp.beta1, hp.beta2, self.d_adam_t,
+                   1.0 / world)
+            # post-update discriminator forward (fresh reads of the updated variables, tf_utils.replace_read_ops)
+            self._d_sn_and_pack()
+        # ---- generator loss seeds
+        G['dgen'].zero_()
+        self.g_grad.zero_()
+        r0, r1 = 0, B       # L1/L2 compare gen_images_enc (posterior half) when it exists (base_model.py:737)
+        if not hp.nz:
+            r1 = NB
+        cnt = S * (r1 - r0) * HW * C
+        for t in range(S):
+            for mode, wgt, nm in ((0, hp.l1_weight, 'gen_l1_loss'), (1, hp.l2_weight, 'gen_l2_loss')):
+                if wgt:
+                    # both write dgen; with l1 and l2 both enabled the second overwrites -> not supported together
+                    L.pixel_loss(Bf['gen'][t, r0:r1].data_ptr(), 4, Bf['x'][t + 1, r0:r1].data_ptr(), 4, G['dgen'][t, r0:r1].data_ptr(), 4,
+                                 (r1 - r0) * HW, C, mode, cnt, wgt, self._slot(nm))
+        if hp.kl_weight and hp.nz:
+            L.kl_loss(Bf['zmu'], Bf['zlss'], S * B, hp.nz, self._slot('gen_kl_loss'))
+        if has_d:
+            for scope, net in self.dnets.items():
+                enc = scope.endswith('encoder/video')
+                w = hp.video_sn_vae_gan_weight if enc else hp.video_sn_gan_weight
+                cd_w = hp.vae_gan_feature_cdist_weight if enc else hp.gan_feature_cdist_weight
+                foff = 0 if enc else (B if hp.nz else 0)
+                need_real = bool(cd_w)
+                self._d_gather(net, 'post', net['ts'][('d_post', 0)], net['ts'][('d_post', 1)], foff, rows_real=need_real)
+                self._d_forward(net, 0 if need_real else B, 2 * B)
+                if w:
+                    L.lsgan_loss(net['logits'][B:], 1.0, B, w, net['dlogits'][B:],
+                                 self._slot('gen_video_sn_vae_gan_loss' if enc else 'gen_video_sn_gan_loss'))
+                else:
+                    net['dlogits'][B:].zero_()
+                dcd = None
+                if cd_w:
+                    dcd = net['dcd']
+                    slot = self._slot('gen_video_sn_vae_gan_feature_cdist_loss' if enc else 'gen_video_sn_gan_feature_cdist_loss')
+                    for l, feat in enumerate(net['feat']):
+                        dcd[l].zero_()
+                        co = feat.shape[-1]
+                        rows = int(np.prod(feat.shape[1:-1])) * B
+                        L.cosine_distance(feat[B:], feat[:B], dcd[l], rows, co, cd_w, slot)
+                self._d_backward(net, B, 2 * B, with_wgrad=False, to_clip=True, dcd=dcd)
+                L.scatter_clip(net['dclip'][B:], net['ts'][('d_post', 1)], G['dgen'], B, hp.clip_length, HW, NB, foff)
+        # ---- BPTT
+        for t in range(S - 1, -1, -1):
+            self._gen_backward_step(t)
+        self._gen_backward_params()
+        if allreduce is not None:
+            allreduce(self.g_grad)
+        self.g_adam_t += 1
+        L.adam(self.g_flat, self.g_grad, self.g_m, self.g_v, self.g_flat.numel(), lr, hp.beta1, hp.beta2, self.g_adam_t, 1.0 / world)
+        if has_d:   # every forward of this step read the start-of-step u; store u' now
+            for net in self.dnets.values():
+                for lay in net['layers'] + [net['fc']]:
+                    self.params[lay.uname].view(-1).copy_(lay.u_next)
+        self._pack_all()
+        self.global_step += 1
+
+    def losses(self):
+        vals = self.loss_vals.detach().cpu().numpy()
+        return OrderedDict((k, float(v)) for k, v in zip(LOSS_SLOTS, vals))
