@@ -176,9 +176,9 @@ int vp_axpy_channels(const float* src, int src_cstride, float* dst, int dst_cstr
 int vp_act_bwd(const float* y, int y_cstride, const float* dy_a, int dy_a_cstride, const float* dy_b, int dy_b_cstride,
                float* dx, int dx_cstride, long long rows, int c, int act, float alpha, vp_stream_t stream);
 int vp_avgpool_bwd(const float* dy, float* dx, int dx_cstride, int n, int positions, int c, vp_stream_t stream);
-/* kl_scale = kl_weight / rows (rows = (T-1)*B); dz may be NULL */
+/* *kl_scale (device scalar, may be NULL = 0) = kl_weight(step) / rows, rows = (T-1)*B; dz may be NULL */
 int vp_sample_z_bwd(const float* mu, const float* lss, const float* eps, const float* dz, float* dmu, float* dlss,
-                    int total, float kl_scale, vp_stream_t stream);
+                    int total, const float* kl_scale, vp_stream_t stream);
 
 /* ---- losses (losses.py:6-67): out[0] += value; optional gradient = grad_scale * d value / d pred -------- */
 int vp_pixel_loss(const float* pred, int pred_cstride, const float* target, int target_cstride, float* dpred,
@@ -189,9 +189,12 @@ int vp_kl_loss(const float* mu, const float* lss, int rows, int nz, float* out, 
 /* cosine_distance(a, b) over rows of c channels; da += grad (gradient w.r.t. a only) */
 int vp_cosine_distance(const float* a, const float* b, float* da, long long rows, int c, float grad_scale, float* out,
                        vp_stream_t stream);
-/* tf.train.AdamOptimizer (TF1 epsilon-hat form), step is 1-based; g is multiplied by grad_scale first */
-int vp_adam(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2, float eps,
-            int step, float grad_scale, vp_stream_t stream);
+/* tf.train.AdamOptimizer (TF1 epsilon-hat form).  *lr_t (device scalar) = lr*sqrt(1-beta2^t)/(1-beta1^t): step-dependent
+ * scalars live in device memory so that a captured CUDA graph of the step stays valid.  g is multiplied by grad_scale. */
+int vp_adam(float* p, const float* g, float* m, float* v, long long n, const float* lr_t, float beta1, float beta2,
+            float eps, float grad_scale, vp_stream_t stream);
+/* number of kernels this library has launched in this process (bench.py's gpu_launches) */
+long long vp_launch_count(void);
 
 /* ---- discriminator helpers ------------------------------------------------------------------------
  * spectral_normed_weight (ops.py:1020-1049): w [rows][cols] (rows = prod(kernel dims)*cin), u [cols].

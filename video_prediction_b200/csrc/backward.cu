@@ -501,9 +501,10 @@ __global__ void avgpool_bwd_kernel(const float* __restrict__ dy, float* __restri
 // dmu = dz + klw*mu/rows ; dlss = dz*eps*0.5*sqrt(exp(lss)) + klw*0.5*(exp(lss)-1)/rows ; zero where lss was clipped
 __global__ void sample_z_bwd_kernel(const float* __restrict__ mu, const float* __restrict__ lss, const float* __restrict__ eps,
                                     const float* __restrict__ dz, float* __restrict__ dmu, float* __restrict__ dlss, int total,
-                                    float kl_scale) {
+                                    const float* __restrict__ kl_scale_dev) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
+  const float kl_scale = kl_scale_dev ? __ldg(kl_scale_dev) : 0.f;
   const float l = lss[idx], e = expf(l);
   const float d = dz ? dz[idx] : 0.f;
   dmu[idx] = d + kl_scale * mu[idx];
@@ -609,9 +610,10 @@ __global__ void __launch_bounds__(256) cosine_distance_kernel(const float* __res
 // gscale folds the 1/world_size of the data-parallel gradient mean (tf_utils.py:473-474).
 // ------------------------------------------------------------------------------------------------
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
-                            long long n, float lr_t, float b1, float b2, float eps, float gscale) {
+                            long long n, const float* __restrict__ lr_t_dev, float b1, float b2, float eps, float gscale) {
   const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (idx >= n) return;
+  const float lr_t = __ldg(lr_t_dev);
   const float gv = g[idx] * gscale;
   const float mv = b1 * m[idx] + (1.f - b1) * gv;
   const float vv = b2 * v[idx] + (1.f - b2) * gv * gv;
@@ -744,7 +746,7 @@ extern "C" int vp_avgpool_bwd(const float* dy, float* dx, int dx_cstride, int n,
 }
 
 extern "C" int vp_sample_z_bwd(const float* mu, const float* lss, const float* eps, const float* dz, float* dmu, float* dlss,
-                               int total, float kl_scale, vp_stream_t stream) {
+                               int total, const float* kl_scale, vp_stream_t stream) {
   sample_z_bwd_kernel<<<grid_for(total, 128), 128, 0, as_stream(stream)>>>(mu, lss, eps, dz, dmu, dlss, total, kl_scale);
   return check_launch("sample_z_bwd_kernel");
 }
@@ -777,9 +779,8 @@ extern "C" int vp_cosine_distance(const float* a, const float* b, float* da, lon
   return check_launch("cosine_distance_kernel");
 }
 
-extern "C" int vp_adam(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2, float eps,
-                       int step, float grad_scale, vp_stream_t stream) {
-  const float lr_t = lr * sqrtf(1.f - powf(beta2, static_cast<float>(step))) / (1.f - powf(beta1, static_cast<float>(step)));
+extern "C" int vp_adam(float* p, const float* g, float* m, float* v, long long n, const float* lr_t, float beta1, float beta2,
+                       float eps, float grad_scale, vp_stream_t stream) {
   adam_kernel<<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(p, g, m, v, n, lr_t, beta1, beta2, eps, grad_scale);
   return check_launch("adam_kernel");
 }

@@ -8,7 +8,9 @@
 
 namespace vp {
 int set_error(const char* fmt, ...);
+void count_launch(int n);
 inline int check_launch(const char* what) {
+  count_launch(1);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error("%s launch failed: %s", what, cudaGetErrorString(e));
   return 0;

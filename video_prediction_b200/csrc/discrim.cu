@@ -153,6 +153,7 @@ extern "C" int vp_spectral_norm_fwd(const float* w, const float* u, int rows, in
   dim3 grid((cols + 31) / 32, (rows + rpb - 1) / rpb);
   sn_coldot_kernel<<<grid, 256, 0, st>>>(w, v, s, rows, cols, rpb);                   // s = v W
   sn_finish_kernel<<<1, 1024, 0, st>>>(s, u_new, cols, scal);                         // u' = l2n(s), sigma
+  count_launch(3);
   return check_launch("spectral_norm_fwd");
 }
 
@@ -166,6 +167,7 @@ extern "C" int vp_spectral_norm_bwd(const float* w, const float* u, const float*
   sn_rowdot_kernel<<<(rows + 7) / 8, 256, 0, st>>>(w, gs, gt, rows, cols);            // gv = W gs
   sn_bwd_gt_kernel<<<1, 1024, 0, st>>>(v, gt, rows, scal);
   sn_bwd_final_kernel<<<grid_for(n, 256), 256, 0, st>>>(g_wbar, v, gs, gt, u, dw, n, cols, scal);
+  count_launch(4);
   return check_launch("spectral_norm_bwd");
 }
 

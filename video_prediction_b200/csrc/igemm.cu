@@ -497,6 +497,7 @@ extern "C" int vp_conv_igemm(const vp_tensor* in, const vp_conv_geom* g, const f
   }
   dim3 grid(A.tiles_w * A.tiles_h * A.tiles_d * A.tiles_n, n_pad / A.bn_tile, A.num_phases * A.splits);
   igemm_fwd_kernel<<<grid, 192, smem, static_cast<cudaStream_t>(stream)>>>(A);
+  count_launch(1);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error("igemm_fwd_kernel launch failed: %s", cudaGetErrorString(e));
   return 0;
@@ -537,6 +538,7 @@ extern "C" int vp_conv_wgrad(const vp_tensor* x, const vp_tensor* dy, const vp_c
   const size_t smem = static_cast<size_t>(kStagesWg) * 8 * kWgPix * 128 + 1024;
   dim3 grid(A.m_tiles * A.n_tiles, ntaps, A.splits);
   igemm_wgrad_kernel<<<grid, 192, smem, static_cast<cudaStream_t>(stream)>>>(A);
+  count_launch(1);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error("igemm_wgrad_kernel launch failed: %s", cudaGetErrorString(e));
   return 0;

@@ -254,8 +254,8 @@ def avgpool_bwd(dy, dx, dx_cs, n, positions, c):
     check(lib().vp_avgpool_bwd(ptr(dy), ptr(dx), dx_cs, n, positions, c, stream_ptr()))
 
 
-def sample_z_bwd(mu, lss, eps, dz, dmu, dlss, total, kl_scale):
-    check(lib().vp_sample_z_bwd(ptr(mu), ptr(lss), ptr(eps), ptr(dz), ptr(dmu), ptr(dlss), total, _f(kl_scale), stream_ptr()))
+def sample_z_bwd(mu, lss, eps, dz, dmu, dlss, total, kl_scale_dev):
+    check(lib().vp_sample_z_bwd(ptr(mu), ptr(lss), ptr(eps), ptr(dz), ptr(dmu), ptr(dlss), total, ptr(kl_scale_dev), stream_ptr()))
 
 
 def pixel_loss(pred_addr, pred_cs, target_addr, target_cs, dpred_addr, dpred_cs, rows, c, mode, mean_count, grad_scale, out):
@@ -275,9 +275,15 @@ def cosine_distance(a, b, da, rows, c, grad_scale, out):
     check(lib().vp_cosine_distance(ptr(a), ptr(b), ptr(da), C.c_longlong(rows), c, _f(grad_scale), ptr(out), stream_ptr()))
 
 
-def adam(p, g, m, v, n, lr, beta1, beta2, step, grad_scale=1.0, eps=1e-8):
-    check(lib().vp_adam(ptr(p), ptr(g), ptr(m), ptr(v), C.c_longlong(n), _f(lr), _f(beta1), _f(beta2), _f(eps), step,
+def adam(p, g, m, v, n, lr_t_dev, beta1, beta2, grad_scale=1.0, eps=1e-8):
+    check(lib().vp_adam(ptr(p), ptr(g), ptr(m), ptr(v), C.c_longlong(n), ptr(lr_t_dev), _f(beta1), _f(beta2), _f(eps),
                         _f(grad_scale), stream_ptr()))
+
+
+def launch_count():
+    f = lib().vp_launch_count
+    f.restype = C.c_longlong
+    return int(f())
 
 
 def spectral_norm_fwd(w, u, rows, cols, v, s, u_new, scal):

@@ -217,6 +217,8 @@ class TrainMixin(object):
                 if i > 0:
                     G['deact%d' % i] = torch.zeros_like(Bf['eact%d' % i])
         self.loss_vals = z(len(LOSS_SLOTS))
+        self.step_scalars = z(4)      # [lr_t(D), lr_t(G), kl_scale, -]  refreshed from the host every step
+        self._scal_host = torch.zeros(4, dtype=torch.float32).pin_memory()
         for c in self.convs:
             c.prepare_backward()
 
@@ -416,8 +418,7 @@ class TrainMixin(object):
             L.axpy_channels(G['dzcat'][t, :B].data_ptr(), 2 * nz, G['dzpost'][t].data_ptr(), nz, B, nz, accumulate=False)
             if t < hp.context_frames - 1:
                 L.axpy_channels(G['dzcat'][t, B:].data_ptr(), 2 * nz, G['dzpost'][t].data_ptr(), nz, B, nz)
-        klw = self.kl_weight_at(self.global_step) if hp.kl_weight else 0.0
-        L.sample_z_bwd(Bf['zmu'], Bf['zlss'], Bf['eps'], G['dzpost'], G['dzmu'], G['dzlss'], S * B * nz, (klw or 0.0) / (S * B))
+        L.sample_z_bwd(Bf['zmu'], Bf['zlss'], Bf['eps'], G['dzpost'], G['dzmu'], G['dzlss'], S * B * nz, self.step_scalars[2:3])
         sc = 'generator/encoder'
         last = self.enc_layers[-1]
         oc = last['oc']
@@ -465,7 +466,10 @@ class TrainMixin(object):
                     else:
                         g = torch.Generator().manual_seed(1000003 * self.global_step + 17 * w + r + 1)
                         v = torch.randint(0, hi, (self.B,), generator=g, dtype=torch.int32)
-                    net.setdefault('ts', {})[(which, r)] = v.to(self.device)
+                    if 'ts' not in net:
+                        net['ts'] = {(a, b): torch.zeros(self.B, dtype=torch.int32, device=self.device)
+                                     for a in ('d_pre', 'd_post') for b in (0, 1)}
+                    net['ts'][(which, r)].copy_(v)
 
     def train_step(self, inputs=None, noise=None, sampling=None, allreduce=None):
         """One optimisation step (D then G, base_model.py:477-516).  Returns dict of loss values (python floats)
@@ -477,8 +481,7 @@ class TrainMixin(object):
         Bf, G, P = self.Bf, self.Gb, self.params
         B, NB, S, C = self.B, self.NB, self.S, self.C
         HW = self.H * self.W
-        step = self.global_step
-        lr = self.learning_rate_at(step)
+        self._stage_step_scalars()
         self.loss_vals.zero_()
         self.generator_forward(collect=False)
         has_d = bool(self.dnets)
@@ -501,8 +504,7 @@ class TrainMixin(object):
                 self._d_backward(net, 0, 2 * B, with_wgrad=True, to_clip=False)
             if allreduce is not None:
                 allreduce(self.d_grad)
-            self.d_adam_t += 1
-            L.adam(self.d_flat, self.d_grad, self.d_m, self.d_v, self.d_flat.numel(), lr, hp.beta1, hp.beta2, self.d_adam_t,
+            L.adam(self.d_flat, self.d_grad, self.d_m, self.d_v, self.d_flat.numel(), self.step_scalars[0:1], hp.beta1, hp.beta2,
                    1.0 / world)
             # post-update discriminator forward (fresh reads of the updated variables, tf_utils.replace_read_ops)
             self._d_sn_and_pack()
@@ -552,14 +554,31 @@ class TrainMixin(object):
         self._gen_backward_params()
         if allreduce is not None:
             allreduce(self.g_grad)
-        self.g_adam_t += 1
-        L.adam(self.g_flat, self.g_grad, self.g_m, self.g_v, self.g_flat.numel(), lr, hp.beta1, hp.beta2, self.g_adam_t, 1.0 / world)
+        L.adam(self.g_flat, self.g_grad, self.g_m, self.g_v, self.g_flat.numel(), self.step_scalars[1:2], hp.beta1, hp.beta2, 1.0 / world)
         if has_d:   # every forward of this step read the start-of-step u; store u' now
             for net in self.dnets.values():
                 for lay in net['layers'] + [net['fc']]:
                     self.params[lay.uname].view(-1).copy_(lay.u_next)
         self._pack_all()
         self.global_step += 1
+
+    def _stage_step_scalars(self):
+        """Host -> device: the step-dependent scalars (TF Adam's lr_t for both optimizers, annealed KL weight)."""
+        import math
+        hp = self.hparams
+        step = self.global_step
+        lr = self.learning_rate_at(step)
+        if self.dnets:
+            self.d_adam_t += 1
+        self.g_adam_t += 1
+
+        def lr_t(t):
+            return lr * math.sqrt(1.0 - hp.beta2 ** t) / (1.0 - hp.beta1 ** t) if t > 0 else 0.0
+        klw = (self.kl_weight_at(step) or 0.0) if (hp.kl_weight and hp.nz) else 0.0
+        self._scal_host[0] = lr_t(self.d_adam_t)
+        self._scal_host[1] = lr_t(self.g_adam_t)
+        self._scal_host[2] = klw / float(self.S * self.B)
+        self.step_scalars.copy_(self._scal_host, non_blocking=True)
 
     def losses(self):
         vals = self.loss_vals.detach().cpu().numpy()
