@@ -1,0 +1,321 @@
+#!/usr/bin/env python
+"""bench.py -- SAVP training hot path on B200 (frames/sec, BASELINE.json metric).
+
+  python bench.py --gpus N --steps K --warmup W            (N>1: launched by torch.distributed.run, one rank per GPU)
+  python bench.py --impl reference ...                      (the CPU arm: the oracle port on the host cores)
+
+A "step" is one full optimisation step of config[1] of BASELINE.json (SAVP, bair_action_free/ours_savp hparams:
+VAE+GAN, 64x64x3, 2 context + 10 predicted, batch 16 per GPU): generator forward (posterior + prior unrolls),
+4 discriminator towers, D backward + Adam(D), post-update D forward, G backward (BPTT) + Adam(G).
+frames/sec = global_batch * (T-1) generated frames per step / step time.
+
+`value`   : inputs resident in HBM, the whole step replayed from a CUDA graph, timed with CUDA events, max over ranks.
+`e2e`     : the public API call (model.train_step(inputs)) with HOST inputs: pinned H2D of the batch + D2H of the losses
+            inside the timed region.
+`roofline`: the ConvLSTM gate convolutions (rnn_ops.py:121; the north-star kernel) timed alone with CUDA events.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SAVP_HPARAMS = dict(  # hparams/bair_action_free/ours_savp/model_hparams.json + dataset-provided frame counts
+    context_frames=2, sequence_length=12, batch_size=16, lr=0.0002, beta1=0.5, beta2=0.999, l1_weight=100.0, l2_weight=0.0,
+    kl_weight=1.0, video_sn_vae_gan_weight=0.1, video_sn_gan_weight=0.1, vae_gan_feature_cdist_weight=10.0,
+    gan_feature_cdist_weight=0.0, state_weight=0.0)
+IMAGE = (64, 64, 3)
+PER_GPU_BATCH = 16
+
+
+def load_peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d['hbm_gbs'], bf16=d['bf16_tflops'], bf16_sustained=d.get('bf16_tflops_sustained'), src='measured')
+    return dict(hbm=6650.0, bf16=1590.0, bf16_sustained=1400.0, src='fallback')
+
+
+class ClockSampler(threading.Thread):
+    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+
+    def __init__(self, index=0):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+             'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + q, '--format=csv,noheader,nounits'],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(',')])
+            except Exception:
+                pass
+            time.sleep(0.15)
+
+    def summary(self):
+        if not self.rows:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=['unavailable'])
+        sm = sorted(int(float(r[0])) for r in self.rows if r[0].replace('.', '').isdigit())
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith('active') for r in self.rows if len(r) > 2 + i)]
+        return dict(sm_mhz=sm[len(sm) // 2] if sm else None, sm_max_mhz=int(float(self.rows[0][1])), reasons=reasons,
+                    samples=len(self.rows))
+
+
+def synthetic_batch(batch, seed):
+    """U[0,1) images (dataset contract base_dataset.py:189), one fresh batch per step, as pinned host tensors."""
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    T = SAVP_HPARAMS['sequence_length']
+    imgs = torch.rand(batch, T, *IMAGE, generator=g)
+    return {'images': imgs.pin_memory() if torch.cuda.is_available() else imgs}
+
+
+def oracle_step_time(batch, steps, threads):
+    """Times full SAVP training steps of the CPU oracle (the port of the reference's TF1 graph) at batch `batch`."""
+    import torch
+    from oracle import savp_oracle as O
+    torch.set_num_threads(threads)
+    hk = {k: v for k, v in SAVP_HPARAMS.items() if k != 'batch_size'}
+    hp = O.make_hparams(**hk)
+    params, _ = O.init_params(hp, IMAGE, seed=0)
+    opt = dict(m={k: torch.zeros_like(v) for k, v in params.items()}, v={k: torch.zeros_like(v) for k, v in params.items()}, t=0)
+    times = []
+    for s in range(steps + 1):
+        inputs, noise = O.make_synthetic_inputs(hp, batch, IMAGE, seed=s, smooth=False)
+        t0 = time.time()
+        res = O.train_step(params, opt, hp, inputs, noise, step=s)
+        times.append(time.time() - t0)
+        params = res['params']
+    times = times[1:] if len(times) > 1 else times     # first step warms the allocator / oneDNN primitive cache
+    return sum(times) / len(times)
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    sample_b = 2
+    frames = sample_b * (SAVP_HPARAMS['sequence_length'] - 1)
+    k = max(1, min(args.steps, 3))
+    t = oracle_step_time(sample_b, k, cores)
+    fps = frames / t
+    sample = '%d full SAVP training steps at batch %d (of %d) on the host, torch/oneDNN fp32' % (k, sample_b, PER_GPU_BATCH)
+    line = dict(metric='frames/sec SAVP 64x64 2+10 (training)', value=fps, unit='frames/s', n_gpus=args.gpus, steps=k,
+                warmup=1, ms_per_step=t * 1e3, higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f32',
+                data='synthetic', impl='reference',
+                config=dict(workload='BASELINE configs[1]: SAVP (VAE+GAN) bair_action_free hparams, 64x64x3, 2+10; CPU sample batch %d' % sample_b,
+                            note='the TF1 reference cannot run here (needs tensorflow 1.x); this is its line-by-line CPU port (oracle/)'),
+                cpu_baseline=dict(value=fps, unit='frames/s', cores=cores, kind='port', sample=sample),
+                e2e=dict(value=fps, unit='frames/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    print(json.dumps(line))
+
+
+def time_gate_kernels(model, iters=3):
+    """CUDA-event timing of the five ConvLSTM gate convolutions (one launch per timestep buffer, cycling through all
+    T-1 timesteps so consecutive launches touch different HBM lines; working set > L2)."""
+    import torch
+    flops, ms = 0.0, 0.0
+    per_layer = []
+    for d in model.gl:
+        if not d['use']:
+            continue
+        li = d['li']
+        conv = d['rconv']
+        rin, gpre = model.Bf['rin%d' % li], model.Bf['gpre%d' % li]
+        S = model.S
+        for t in range(S):
+            conv.fwd(rin[t], gpre[t])
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            for t in range(S):
+                conv.fwd(rin[t], gpre[t])
+        e1.record()
+        torch.cuda.synchronize()
+        t_ms = e0.elapsed_time(e1) / (iters * S)
+        M = model.NB * d['h'] * d['w']
+        fl = 2.0 * M * (4 * d['oc']) * (25 * conv.ci_ref)        # algorithmic: reference channel count, no padding
+        per_layer.append(dict(layer='lstm_h%d' % li, M=M, N=4 * d['oc'], K=25 * conv.ci_ref, ms=t_ms, tflops=fl / t_ms / 1e9))
+        flops += fl
+        ms += t_ms
+    return flops, ms, per_layer
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from video_prediction_b200 import lib as L
+    from video_prediction_b200.models import SAVPVideoPredictionModel
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    B = PER_GPU_BATCH
+    model = SAVPVideoPredictionModel(mode='train', hparams_dict=dict(SAVP_HPARAMS), num_gpus=1)
+    model.world_size = world
+    batch0 = synthetic_batch(B, seed=1000 * rank)
+    model.build_graph(batch0)
+    if world > 1:   # identical initial weights on every replica (base_model.py:640-646: post_init_ops copy tower 0)
+        dist.broadcast(model.g_flat, 0)
+        dist.broadcast(model.d_flat, 0)
+        for k, v in model.params.items():
+            if k.endswith('/u'):
+                dist.broadcast(v, 0)
+        model._pack_all()
+    allreduce = (lambda buf: dist.all_reduce(buf)) if world > 1 else None
+    S = model.S
+    frames_per_step = world * B * S
+
+    # ---------------- e2e: public API with host inputs (H2D + D2H inside the timed region)
+    batches = [synthetic_batch(B, seed=1000 * rank + i) for i in range(4)]
+    h2d = sum(v.numel() * 4 for v in batches[0].values())
+    for i in range(max(3, args.warmup)):
+        model.train_step(batches[i % 4], allreduce=allreduce)
+        model.losses()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    k_e2e = max(3, min(args.steps, 10))
+    t0 = time.time()
+    e0.record()
+    for i in range(k_e2e):
+        model.train_step(batches[i % 4], allreduce=allreduce)
+        lv = model.losses()              # D2H of the step's losses
+    e1.record()
+    torch.cuda.synchronize()
+    e2e_ms = max(e0.elapsed_time(e1), (time.time() - t0) * 1e3) / k_e2e
+    d2h = model.loss_vals.numel() * 4
+
+    # ---------------- value: HBM-resident inputs, whole step as one CUDA graph
+    use_graph = not args.no_graph
+    graph = None
+    launches_per_step = None
+    model.set_inputs(batches[0])
+    if use_graph:
+        try:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                model.train_step(allreduce=allreduce)         # warm-up on a side stream
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            c0 = L.launch_count()
+            model.stage_step()
+            with torch.cuda.graph(graph):
+                model.train_step(allreduce=allreduce, staged=True)
+            model.global_step += 1
+            launches_per_step = L.launch_count() - c0
+        except Exception as ex:     # noqa: BLE001
+            sys.stderr.write('CUDA graph capture failed (%s); timing eager launches instead\n' % ex)
+            graph = None
+            torch.cuda.synchronize()
+
+    def one_step():
+        if graph is not None:
+            model.stage_step()
+            graph.replay()
+            model.global_step += 1
+        else:
+            model.train_step(allreduce=allreduce)
+    if launches_per_step is None:
+        c0 = L.launch_count()
+        model.train_step(allreduce=allreduce)
+        launches_per_step = L.launch_count() - c0
+    for _ in range(max(3, args.warmup)):
+        one_step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(args.steps):
+        one_step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.steps
+    sampler.stop_flag = True
+    if world > 1:
+        t = torch.tensor([ms, e2e_ms], device='cuda')
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, e2e_ms = t[0].item(), t[1].item()
+        dist.barrier()
+    losses = model.losses()
+    finite = all(v == v for v in losses.values())
+
+    # ---------------- roofline of the dominant kernel + CPU baseline (rank 0, N = 1 only for the CPU leg)
+    if rank == 0:
+        peaks = load_peaks()
+        flops, gate_ms, per_layer = time_gate_kernels(model)
+        achieved = flops / gate_ms / 1e9     # TFLOP/s over the five gate convolutions of one timestep
+        roof = dict(bound='tensor', kernel='igemm_fwd_kernel (ConvLSTM gate convolutions, tcgen05 kind::tf32)',
+                    achieved=achieved, peak=peaks['bf16'], unit='TFLOP/s', frac=achieved / peaks['bf16'],
+                    peak_source=peaks['src'] + ' cuBLAS bf16 (burst); tf32 MMA rate is half of bf16',
+                    peak_tf32_equiv=peaks['bf16'] / 2, frac_of_tf32_peak=achieved / (peaks['bf16'] / 2),
+                    traffic=None, per_layer=per_layer)
+        cpu = None
+        if world == 1 and not args.no_cpu:
+            cores = os.cpu_count() or 1
+            sb = 2
+            tcpu = oracle_step_time(sb, 2, cores)
+            cpu = dict(value=sb * S / tcpu, unit='frames/s', cores=cores, kind='port',
+                       sample='2 full SAVP training steps at batch %d (of %d) with the CPU oracle (torch/oneDNN fp32)' % (sb, B))
+        clocks = sampler.summary()
+        line = dict(metric='frames/sec SAVP 64x64 2+10 (training)', value=frames_per_step / ms * 1e3, unit='frames/s',
+                    n_gpus=world, steps=args.steps, warmup=max(3, args.warmup), ms_per_step=ms, higher_is_better=True,
+                    scaling='weak', vs_baseline=None, dtype='tf32 tensor-core convolutions, fp32 accumulate / state / optimizer',
+                    data='synthetic',
+                    config=dict(workload='BASELINE configs[1]: SAVP (VAE+GAN) bair_action_free/ours_savp hparams, synthetic 64x64x3, '
+                                         '2 context + 10 predicted, batch %d per GPU; full step = G fwd (2 unrolls) + 4 D towers + '
+                                         'Adam(D) + post-update D fwd + G BPTT + Adam(G)' % B,
+                                global_batch=world * B, per_gpu_batch=B, sequence_length=12, parallelism='dp%d' % world,
+                                cuda_graph=graph is not None,
+                                l2='working set of one step (~8 GB of activations) is far larger than the 126 MB L2'),
+                    e2e=dict(value=frames_per_step / e2e_ms * 1e3, unit='frames/s', ms_per_step=e2e_ms, h2d_bytes_per_step=h2d,
+                             d2h_bytes_per_step=d2h, api='SAVPVideoPredictionModel.train_step(host inputs) + .losses()'),
+                    gpu_launches=int(launches_per_step) * args.steps, gpu_launches_per_step=int(launches_per_step),
+                    roofline=roof, cpu_baseline=cpu, clocks=clocks, losses_finite=finite,
+                    losses={k: round(v, 6) for k, v in losses.items() if v})
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--no-graph', action='store_true')
+    ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == '__main__':
+    main()

@@ -1,0 +1,288 @@
+"""GPU unit tests (-m gpu): every hand-written kernel against the oracle's op (fp32 / fp64, torch autograd for the
+backward kernels).  HBM-bound kernels are plain fp32 -> tight tolerances; tensor-core convolutions compute on
+TF32-truncated operands -> compared with an fp64 reference on TF32-rounded inputs, relative tolerance 2e-3."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import savp_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def L():
+    if not torch.cuda.is_available():
+        pytest.skip('no CUDA device')
+    from video_prediction_b200 import lib
+    lib.lib()
+    return lib
+
+
+def rnd(*s, seed=0, scale=1.0):
+    g = torch.Generator(device='cpu').manual_seed(seed)
+    return (torch.randn(*s, generator=g) * scale).cuda()
+
+
+def tf32(x):
+    xi = x.contiguous().view(torch.int32)
+    xi = (xi + 0x0FFF + ((xi >> 13) & 1)) & ~0x1FFF
+    return xi.view(torch.float32)
+
+
+def close(a, b, tol, what=''):
+    err = (a.double().cpu() - b.double().cpu()).abs().max().item()
+    sc = b.double().abs().max().item() + 1e-30
+    assert err <= tol * max(sc, 1.0), '%s: max err %g (ref max %g)' % (what, err, sc)
+
+
+# ------------------------------------------------------------------ tensor-core engine
+def _ke(L, k, kind):
+    return k if kind == L.WKIND_PLAIN else ((1, k[1] + 1, k[2] + 1) if kind == L.WKIND_POOLED else (1, k[1] + 3, k[2] + 3))
+
+
+def _fwd(L, x, c_used, w, k, s, p, out_shape, kind=0, transposed=False, bias=None, act=0, alpha=0.0, split_k=1):
+    ci_ref, co = w.shape[-2], w.shape[-1]
+    wp, n_pad, kc = L.pack_weights(w.contiguous(), k, ci_ref, co, kind, L.WLAYOUT_FWD, ci_int=c_used)
+    out = torch.zeros(*out_shape, co, device='cuda')
+    L.conv_igemm(L.tensor_view(x, c_used), L.geom(_ke(L, k, kind), s, p, transposed), wp, n_pad, kc, L.tensor_view(out, co), bias,
+                 act, alpha, split_k)
+    torch.cuda.synchronize()
+    return out
+
+
+@pytest.mark.parametrize('B,H,Cin,Cout', [(4, 32, 72, 128), (6, 8, 264, 512), (3, 16, 136, 256)])
+def test_convlstm_gate_conv(L, B, H, Cin, Cout):
+    x, w = rnd(B, H, H, Cin), rnd(5, 5, Cin, Cout, seed=1, scale=0.05)
+    y = _fwd(L, x, Cin, w, (1, 5, 5), (1, 1, 1), (0, 2, 2), (B, H, H))
+    ref = O.conv2d_tf(tf32(x).double(), tf32(w).double(), padding='SAME')
+    close(y, ref, 2e-3, 'gate conv')
+    y2 = _fwd(L, x, Cin, w, (1, 5, 5), (1, 1, 1), (0, 2, 2), (B, H, H), split_k=3)
+    close(y2, ref, 2e-3, 'gate conv split-k')
+
+
+def test_conv_pool2d_and_upsample_conv2d(L):
+    x, w, b = rnd(2, 64, 64, 16), rnd(5, 5, 14, 32, seed=1, scale=0.1), rnd(32, seed=2)
+    y = _fwd(L, x, 14, w, (1, 5, 5), (1, 2, 2), (0, 2, 2), (2, 32, 32), kind=L.WKIND_POOLED, bias=b)
+    close(y, O.conv_pool2d(tf32(x)[..., :14].double(), w.double(), b.double()), 2e-3, 'conv_pool2d')
+    x, w, b = rnd(2, 8, 8, 136), rnd(3, 3, 136, 64, seed=1, scale=0.05), rnd(64, seed=2)
+    y = _fwd(L, x, 136, w, (1, 3, 3), (1, 2, 2), (0, 2, 2), (2, 16, 16), kind=L.WKIND_UPSAMPLED, transposed=True, bias=b)
+    close(y, O.upsample_conv2d(tf32(x).double(), w.double(), b.double()), 2e-3, 'upsample_conv2d')
+
+
+@pytest.mark.parametrize('k,s,cin,cout,shape', [(3, (1, 1, 1), 3, 32, (2, 6, 16, 16)), (4, (1, 2, 2), 32, 64, (2, 10, 32, 32)),
+                                                (4, (2, 2, 2), 64, 128, (2, 8, 16, 16))])
+def test_conv3d_padded_valid(L, k, s, cin, cout, shape):
+    cs = (cin + 3) // 4 * 4
+    x, w, b = rnd(*shape, cs), rnd(k, k, k, cin, cout, seed=1, scale=0.05), rnd(cout, seed=2)
+    od = tuple((d + 2 - k) // st + 1 for d, st in zip(shape[1:], s))
+    y = _fwd(L, x, cin, w, (k, k, k), s, (1, 1, 1), (shape[0],) + od, bias=b, act=L.ACT_LRELU, alpha=0.1)
+    xp = F.pad(tf32(x)[..., :cin].double(), (0, 0, 1, 1, 1, 1, 1, 1))
+    ref = O.lrelu(O.conv3d_tf_valid(xp, tf32(w).double(), s, b.double()), 0.1)
+    close(y, ref, 2e-3, 'conv3d')
+
+
+def test_dgrad_and_wgrad_match_autograd(L):
+    for kind, k, s, p, transposed, xs, ys, cin, cout, fn in [
+        (L.WKIND_PLAIN, (1, 5, 5), (1, 1, 1), (0, 2, 2), False, (2, 16, 16), (2, 16, 16), 72, 128,
+         lambda x, w: O.conv2d_tf(x, w, padding='SAME')),
+        (L.WKIND_POOLED, (1, 3, 3), (1, 2, 2), (0, 1, 1), False, (2, 32, 32), (2, 16, 16), 40, 64,
+         lambda x, w: O.conv_pool2d(x, w, torch.zeros(64, device='cuda', dtype=torch.float64))),
+        (L.WKIND_UPSAMPLED, (1, 3, 3), (1, 2, 2), (0, 2, 2), True, (2, 8, 8), (2, 16, 16), 136, 64,
+         lambda x, w: O.upsample_conv2d(x, w, torch.zeros(64, device='cuda', dtype=torch.float64))),
+    ]:
+        x, dy = rnd(*xs, cin), rnd(*ys, cout, seed=1)
+        w = rnd(k[1], k[2], cin, cout, seed=2, scale=0.05)
+        xd = tf32(x).double().requires_grad_(True)
+        wd = w.double().requires_grad_(True)
+        gx, gw = torch.autograd.grad(fn(xd, wd), (xd, wd), tf32(dy).double())
+        wpd, n_pad, kc = L.pack_weights(w, k, cin, cout, kind, L.WLAYOUT_DGRAD, ci_int=cin)
+        dx = torch.zeros(*xs, cin, device='cuda')
+        L.conv_igemm(L.tensor_view(dy, cout), L.geom(_ke(L, k, kind), s, p, not transposed), wpd, n_pad, kc, L.tensor_view(dx, cin))
+        close(dx, gx, 3e-3, 'dgrad kind %d' % kind)
+        n_pad, kc = L.pad_to(cout, 16), L.pad_to(cin, 32) // 32
+        ke = _ke(L, k, kind)
+        dwp = torch.zeros(ke[1] * ke[2] * n_pad * kc * 32, device='cuda')
+        L.conv_wgrad(L.tensor_view(x, cin), L.tensor_view(dy, cout), L.geom(ke, s, p, transposed), dwp, n_pad, kc, 4)
+        dw = torch.zeros(k[1], k[2], cin, cout, device='cuda')
+        L.unpack_wgrad(dwp, k, cin, cout, kind, dw, n_pad, kc, ci_int=cin)
+        close(dw, gw, 3e-3, 'wgrad kind %d' % kind)
+
+
+# ------------------------------------------------------------------ HBM-bound kernels, forward + backward
+def test_inorm_act_fwd_bwd(L):
+    N, P, C = 3, 256, 16
+    x, g, b, dy = rnd(N, P, C) * 2 + 1, rnd(C, seed=1), rnd(C, seed=2), rnd(N, P, C, seed=3)
+    y = torch.zeros(N, P, 24, device='cuda')
+    st = torch.zeros(N, C, 2, device='cuda')
+    L.inorm_act(x.data_ptr(), C, y.data_ptr() + 16, 24, N, P, C, g, b, L.ACT_LRELU, 0.2, st)
+    xr = x.double().requires_grad_(True)
+    gr, br = g.double().requires_grad_(True), b.double().requires_grad_(True)
+    ref = O.lrelu(O.instance_norm(xr, gr, br), 0.2)
+    close(y[..., 4:20], ref, 1e-5, 'inorm fwd')
+    gx, gg, gb = torch.autograd.grad(ref, (xr, gr, br), dy.double())
+    dx, dg, db = torch.zeros_like(x), torch.zeros(C, device='cuda'), torch.zeros(C, device='cuda')
+    half = dy * 0.5
+    L.inorm_act_bwd(x.data_ptr(), C, [(half.data_ptr(), C), (half.data_ptr(), C)], dx.data_ptr(), C, N, P, C, g, b, st, L.ACT_LRELU, 0.2,
+                    dg, db)
+    close(dx, gx, 2e-5, 'inorm dx')
+    close(dg, gg, 2e-5, 'inorm dgamma')
+    close(db, gb, 2e-5, 'inorm dbeta')
+
+
+def test_lstm_gates_fwd_bwd(L):
+    N, P, Fl = 2, 64, 8
+    pre, c0 = rnd(N, P, 4 * Fl), rnd(N, P, Fl, seed=1)
+    g1, b1, g2, b2 = rnd(4 * Fl, seed=2) * 0.3 + 1, rnd(4 * Fl, seed=3) * 0.1, rnd(Fl, seed=4) * 0.3 + 1, rnd(Fl, seed=5) * 0.1
+    c1, h = torch.zeros(N, P, Fl, device='cuda'), torch.zeros(N, P, 12, device='cuda')
+    s1, s2 = torch.zeros(N, 4 * Fl, 2, device='cuda'), torch.zeros(N, Fl, 2, device='cuda')
+    L.lstm_gates_fwd(pre, N, P, Fl, c0, g1, b1, g2, b2, c1, [(h.data_ptr() + 16, 12)], s1, s2)
+    prd, c0d = pre.double().requires_grad_(True), c0.double().requires_grad_(True)
+    ps = [t.double().requires_grad_(True) for t in (g1, b1, g2, b2)]
+    cat = O.instance_norm(prd, ps[0], ps[1])
+    i, j, f, o = torch.split(cat, Fl, dim=-1)
+    nc = O.instance_norm(c0d * torch.sigmoid(f + 1.0) + torch.sigmoid(i) * torch.tanh(j), ps[2], ps[3])
+    nh = torch.tanh(nc) * torch.sigmoid(o)
+    close(c1, nc, 1e-5, 'gates c')
+    close(h[..., 4:12], nh, 1e-5, 'gates h')
+    dh, dc = rnd(N, P, Fl, seed=6), rnd(N, P, Fl, seed=7)
+    grads = torch.autograd.grad((nh * dh.double()).sum() + (nc * dc.double()).sum(), [prd, c0d] + ps)
+    dpre, dc0 = torch.zeros_like(pre), torch.zeros_like(c0)
+    dgs = [torch.zeros_like(t) for t in (g1, b1, g2, b2)]
+    L.lstm_gates_bwd(pre, N, P, Fl, c0, g1, b1, g2, b2, s1, s2, [(dh.data_ptr(), Fl)], dc, dpre, dc0, dgs[0], dgs[1], dgs[2], dgs[3])
+    close(dpre, grads[0], 3e-5, 'gates dpre')
+    close(dc0, grads[1], 3e-5, 'gates dc_prev')
+    for a, b_, nm in zip(dgs, grads[2:], ('dg1', 'db1', 'dg2', 'db2')):
+        close(a, b_, 3e-5, 'gates ' + nm)
+
+
+def test_cdna_and_composite_fwd_bwd(L):
+    N, H, W, C, nk = 2, 16, 12, 3, 4
+    img = torch.zeros(N, H, W, 4, device='cuda')
+    img[..., :C] = torch.rand(N, H, W, C, device='cuda')
+    first = torch.zeros_like(img)
+    first[..., :C] = torch.rand(N, H, W, C, device='cuda')
+    raw = rnd(N, 25 * nk, scale=0.3)
+    kern = torch.zeros_like(raw)
+    L.cdna_kernel_norm(raw, kern, N, 5, 5, nk)
+    rawd = raw.double().view(N, 5, 5, nk).requires_grad_(True)
+    k = torch.relu(rawd + torch.tensor(O.identity_kernel((5, 5)), device='cuda')[None, :, :, None] - 1e-12) + 1e-12
+    k = k / k.sum(dim=(1, 2), keepdim=True)
+    close(kern.view(N, 5, 5, nk), k, 1e-6, 'cdna kernel norm')
+    nl = nk + 3
+    layers = torch.zeros(N, H, W, 4 * nl, device='cuda')
+    L.cdna_apply(img, first, kern, layers.data_ptr(), 4 * nl, N, H, W, 5, 5, nk)
+    imgd = img[..., :C].double().requires_grad_(True)
+    tr = O.apply_cdna_kernels(imgd, k) + [imgd, first[..., :C].double()]
+    for l in range(nk + 2):
+        close(layers[..., 4 * l:4 * l + C], tr[l], 1e-5, 'cdna layer %d' % l)
+    scratch = torch.rand(N, H, W, C, device='cuda')
+    layers[..., 4 * (nl - 1):4 * (nl - 1) + C] = scratch
+    logits = rnd(N, H, W, 8, seed=3)
+    masks, gen = torch.zeros(N, H, W, 8, device='cuda'), torch.zeros(N, H, W, 4, device='cuda')
+    L.composite(logits, 8, layers.data_ptr(), 4 * nl, masks, 8, gen, N * H * W, nl)
+    lgd = logits[..., :nl].double().requires_grad_(True)
+    scd = scratch.double().requires_grad_(True)
+    m = torch.softmax(lgd, dim=-1)
+    full = tr + [scd]
+    gref = sum(full[l] * m[..., l:l + 1] for l in range(nl))
+    close(gen[..., :C], gref, 1e-5, 'composite gen')
+    dgen = torch.zeros(N, H, W, 4, device='cuda')
+    dgen[..., :C] = rnd(N, H, W, C, seed=4)
+    g_l, g_s, g_i, g_r = torch.autograd.grad(gref, (lgd, scd, imgd, rawd), dgen[..., :C].double())
+    dlog, dlay = torch.zeros(N, H, W, 8, device='cuda'), torch.zeros(N, H, W, 4 * nl, device='cuda')
+    L.composite_bwd(dgen, masks, 8, layers.data_ptr(), 4 * nl, dlog, 8, dlay, 4 * nl, N * H * W, nl)
+    close(dlog[..., :nl], g_l, 2e-5, 'composite dlogits')
+    close(dlay[..., 4 * (nl - 1):4 * (nl - 1) + C], g_s, 2e-5, 'composite dscratch')
+    dimg, dk = torch.zeros(N, H, W, 4, device='cuda'), torch.zeros_like(kern)
+    zero = torch.zeros_like(dlay)
+    L.cdna_apply_bwd(img, kern, dlay.data_ptr(), 4 * nl, zero.data_ptr(), 4 * nl, dimg, dk, N, H, W, 5, 5, nk)
+    close(dimg[..., :C], g_i, 3e-5, 'cdna dimage')
+    draw = torch.zeros_like(raw)
+    L.cdna_kernel_norm_bwd(raw, kern, dk, draw, N, 5, 5, nk)
+    close(draw.view(N, 5, 5, nk), g_r, 3e-5, 'cdna draw')
+
+
+def test_dense_and_small_lstm_fwd_bwd(L):
+    B, K, J = 5, 300, 10
+    x, w, b, dy = rnd(B, K), rnd(K, J, seed=1, scale=0.1), rnd(J, seed=2), rnd(B, J, seed=3)
+    y = torch.zeros(B, J, device='cuda')
+    L.dense_fwd(x, K, w, b, y, J, B, K, J, k_splits=4)
+    xd, wd, bd = [t.double().requires_grad_(True) for t in (x, w, b)]
+    ref = xd @ wd + bd
+    close(y, ref, 1e-5, 'dense fwd')
+    gx, gw, gb = torch.autograd.grad(ref, (xd, wd, bd), dy.double())
+    dx, dw, db = torch.zeros_like(x), torch.zeros_like(w), torch.zeros_like(b)
+    L.dense_bwd(x, K, w, dy, J, B, K, J, dx=dx, dx_stride=K, dw=dw, dbias=db)
+    close(dx, gx, 1e-5, 'dense dx'); close(dw, gw, 1e-5, 'dense dw'); close(db, gb, 1e-5, 'dense db')
+    U = 8
+    gates, c0, dh, dc = rnd(B, 4 * U), rnd(B, U, seed=1), rnd(B, U, seed=2), rnd(B, U, seed=3)
+    c1, h1 = torch.zeros(B, U, device='cuda'), torch.zeros(B, U, device='cuda')
+    L.lstm_cell_fwd(gates, c0, c1, h1, B, U)
+    gd, cd = gates.double().requires_grad_(True), c0.double().requires_grad_(True)
+    i, j, f, o = torch.split(gd, U, dim=-1)
+    nc = torch.sigmoid(f + 1.0) * cd + torch.sigmoid(i) * torch.tanh(j)
+    nh = torch.tanh(nc) * torch.sigmoid(o)
+    close(c1, nc, 1e-6, 'lstm c'); close(h1, nh, 1e-6, 'lstm h')
+    gg, gc = torch.autograd.grad((nh * dh.double()).sum() + (nc * dc.double()).sum(), (gd, cd))
+    dg, dc0 = torch.zeros_like(gates), torch.zeros_like(c0)
+    L.lstm_cell_bwd(gates, c0, c1, dh, dc, dg, dc0, B, U)
+    close(dg, gg, 1e-5, 'lstm dgates'); close(dc0, gc, 1e-5, 'lstm dc')
+
+
+def test_losses_and_adam(L):
+    rows, C = 1000, 3
+    pred, tgt = torch.rand(rows, 4, device='cuda'), torch.rand(rows, 4, device='cuda')
+    out, dp = torch.zeros(2, device='cuda'), torch.zeros(rows, 4, device='cuda')
+    L.pixel_loss(pred.data_ptr(), 4, tgt.data_ptr(), 4, dp.data_ptr(), 4, rows, C, 0, rows * C, 2.0, out[0:1])
+    pd = pred[:, :C].double().requires_grad_(True)
+    ref = O.l1_loss(pd, tgt[:, :C].double())
+    close(out[0:1], ref.reshape(1), 1e-5, 'l1 value')
+    close(dp[:, :C], torch.autograd.grad(2.0 * ref, pd)[0], 1e-6, 'l1 grad')
+    a, b = rnd(40, 16), rnd(40, 16, seed=1)
+    da = torch.zeros_like(a)
+    L.cosine_distance(a, b, da, 40, 16, 3.0, out[1:2])
+    ad = a.double().requires_grad_(True)
+    ref = O.cosine_distance(ad, b.double())
+    close(out[1:2], ref.reshape(1), 1e-5, 'cdist value')
+    close(da, torch.autograd.grad(3.0 * ref, ad)[0], 1e-5, 'cdist grad')
+    n = 1000
+    p, g = rnd(n), rnd(n, seed=1)
+    m, v = torch.zeros(n, device='cuda'), torch.zeros(n, device='cuda')
+    pr, mr, vr = p.clone().cpu(), torch.zeros(n), torch.zeros(n)
+    import math
+    for t in (1, 2, 3):
+        lr_t = torch.tensor([1e-3 * math.sqrt(1 - 0.999 ** t) / (1 - 0.5 ** t)], device='cuda')
+        L.adam(p, g, m, v, n, lr_t, 0.5, 0.999)
+        pr, mr, vr = O.adam_tf(pr, g.cpu(), mr, vr, 1e-3, 0.5, 0.999, t)
+    close(p, pr, 1e-6, 'adam')
+
+
+def test_spectral_norm_fwd_bwd(L):
+    R, Cc = 27 * 4, 32
+    W, u, G = rnd(R, Cc, scale=0.1), rnd(1, Cc, seed=1), rnd(R, Cc, seed=2)
+    v, s, un, scal = [torch.zeros(n, device='cuda') for n in (R, Cc, Cc, 4)]
+    L.spectral_norm_fwd(W, u, R, Cc, v, s, un, scal)
+    Wd = W.double().requires_grad_(True)
+    Wb, u1 = O.spectral_normed_weight(Wd, u.double())
+    sigma = (Wd / Wb).mean()
+    close(scal[2:3], sigma.reshape(1), 1e-5, 'sigma')
+    close(un, u1.reshape(-1), 1e-5, 'u_new')
+    (gW,) = torch.autograd.grad(Wb, Wd, G.double())
+    gs, gt, dW = torch.zeros(Cc, device='cuda'), torch.zeros(R, device='cuda'), torch.zeros_like(W)
+    L.spectral_norm_bwd(W, u, G, R, Cc, v, s, scal, gs, gt, dW)
+    close(dW, gW, 3e-5, 'sn backward')
+
+
+def test_clip_gather_scatter(L):
+    T, NB, P, B, clip = 7, 4, 10, 2, 3
+    video = rnd(T, NB, P, 4)
+    ts = torch.tensor([1, 4], dtype=torch.int32, device='cuda')
+    out = torch.zeros(B, clip, P, 4, device='cuda')
+    L.gather_clip(video, ts, out, B, clip, P, NB, 2)
+    for b in range(B):
+        assert torch.equal(out[b], video[int(ts[b]):int(ts[b]) + clip, 2 + b])
+    dv = torch.zeros_like(video)
+    L.scatter_clip(out, ts, dv, B, clip, P, NB, 2)
+    assert torch.equal(dv[1:4, 2], video[1:4, 2]) and float(dv[:, :2].abs().sum()) == 0.0

@@ -471,23 +471,36 @@ class TrainMixin(object):
                                      for a in ('d_pre', 'd_post') for b in (0, 1)}
                     net['ts'][(which, r)].copy_(v)
 
-    def train_step(self, inputs=None, noise=None, sampling=None, allreduce=None):
-        """One optimisation step (D then G, base_model.py:477-516).  Returns dict of loss values (python floats)
-        unless `fetch_losses=False` was set on the model.  `allreduce(flat_grad)` (optional) is called on the flat
-        discriminator and generator gradient buffers before their Adam steps (data parallel)."""
-        hp = self.hparams
+    def stage_step(self, noise=None):
+        """Host-side staging of one step: step-dependent scalars (lr_t, KL weight) and the discriminators' random
+        clip offsets are written into static device buffers, so the device part can be a replayed CUDA graph."""
+        self._stage_step_scalars()
+        if self.dnets:
+            self._set_tstarts(noise)
+
+    def train_step(self, inputs=None, noise=None, sampling=None, allreduce=None, staged=False):
+        """One optimisation step (D then G, base_model.py:477-516); loss values are left on the device (`losses()`).
+        `allreduce(flat_grad)` (optional) is called on the flat discriminator / generator gradient buffers before
+        their Adam steps (data parallel, tf_utils.py:450-480).  staged=True: `stage_step()` was already called and
+        the caller advances `global_step` (used when the device part is captured into a CUDA graph)."""
         if inputs is not None:
             self.set_inputs(inputs, noise, sampling)
+        if not staged:
+            self.stage_step(noise)
+        self._step_device(allreduce)
+        if not staged:
+            self.global_step += 1
+
+    def _step_device(self, allreduce=None):
+        hp = self.hparams
         Bf, G, P = self.Bf, self.Gb, self.params
         B, NB, S, C = self.B, self.NB, self.S, self.C
         HW = self.H * self.W
-        self._stage_step_scalars()
         self.loss_vals.zero_()
         self.generator_forward(collect=False)
         has_d = bool(self.dnets)
         world = float(self.world_size)
         if has_d:
-            self._set_tstarts(noise)
             self.d_grad.zero_()
             self._d_sn_and_pack()
             for net in self.dnets.values():     # UPDATE_OPS (ops.py:1046-1048): u' of the start-of-step weights
@@ -560,7 +573,6 @@ class TrainMixin(object):
                 for lay in net['layers'] + [net['fc']]:
                     self.params[lay.uname].view(-1).copy_(lay.u_next)
         self._pack_all()
-        self.global_step += 1
 
     def _stage_step_scalars(self):
         """Host -> device: the step-dependent scalars (TF Adam's lr_t for both optimizers, annealed KL weight)."""
