@@ -170,7 +170,9 @@ def run_ours(args):
     model = SAVPVideoPredictionModel(mode='train', hparams_dict=dict(SAVP_HPARAMS), num_gpus=1)
     model.world_size = world
     batch0 = synthetic_batch(B, seed=1000 * rank)
+    log('building model (batch %d per GPU)' % B)
     model.build_graph(batch0)
+    log('built; warming up the eager path')
     if world > 1:   # identical initial weights on every replica (base_model.py:640-646: post_init_ops copy tower 0)
         dist.broadcast(model.g_flat, 0)
         dist.broadcast(model.d_flat, 0)
@@ -189,6 +191,7 @@ def run_ours(args):
         model.train_step(batches[i % 4], allreduce=allreduce)
         model.losses()
     torch.cuda.synchronize()
+    log('timing e2e')
     if world > 1:
         dist.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -202,6 +205,7 @@ def run_ours(args):
     torch.cuda.synchronize()
     e2e_ms = max(e0.elapsed_time(e1), (time.time() - t0) * 1e3) / k_e2e
     d2h = model.loss_vals.numel() * 4
+    log('e2e %.2f ms/step; capturing CUDA graph' % e2e_ms)
 
     # ---------------- value: HBM-resident inputs, whole step as one CUDA graph
     use_graph = not args.no_graph
@@ -239,9 +243,11 @@ def run_ours(args):
         c0 = L.launch_count()
         model.train_step(allreduce=allreduce)
         launches_per_step = L.launch_count() - c0
+    log('graph=%s launches/step=%s; warm-up' % (graph is not None, launches_per_step))
     for _ in range(max(3, args.warmup)):
         one_step()
     torch.cuda.synchronize()
+    log('timing %d steps' % args.steps)
     if world > 1:
         dist.barrier()
     sampler = ClockSampler(local)
@@ -256,6 +262,7 @@ def run_ours(args):
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / args.steps
     sampler.stop_flag = True
+    log('%.2f ms/step' % ms)
     if world > 1:
         t = torch.tensor([ms, e2e_ms], device='cuda')
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -268,6 +275,7 @@ def run_ours(args):
     if rank == 0:
         peaks = load_peaks()
         flops, gate_ms, per_layer = time_gate_kernels(model)
+        log('gate kernels timed; cpu baseline leg')
         achieved = flops / gate_ms / 1e9     # TFLOP/s over the five gate convolutions of one timestep
         roof = dict(bound='tensor', kernel='igemm_fwd_kernel (ConvLSTM gate convolutions, tcgen05 kind::tf32)',
                     achieved=achieved, peak=peaks['bf16'], unit='TFLOP/s', frac=achieved / peaks['bf16'],
@@ -302,7 +310,18 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def log(msg):
+    sys.stderr.write('[bench %.1fs] %s\n' % (time.time() - T0, msg))
+    sys.stderr.flush()
+
+
+T0 = time.time()
+
+
 def main():
+    import faulthandler
+    faulthandler.enable()
+    faulthandler.dump_traceback_later(int(os.environ.get('BENCH_WATCHDOG_S', '420')), exit=True)   # a hang dumps all stacks and exits
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=20)
