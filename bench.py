@@ -82,11 +82,11 @@ def synthetic_batch(batch, seed):
     return {'images': imgs.pin_memory() if torch.cuda.is_available() else imgs}
 
 
-def oracle_step_time(batch, steps, threads):
-    """Times full SAVP training steps of the CPU oracle (the port of the reference's TF1 graph) at batch `batch`."""
+def oracle_step_time(batch, steps):
+    """Times full SAVP training steps of the CPU oracle (the port of the reference's TF1 graph) at batch `batch`.
+    Returns (seconds per step, threads used)."""
     import torch
     from oracle import savp_oracle as O
-    torch.set_num_threads(threads)
     hk = {k: v for k, v in SAVP_HPARAMS.items() if k != 'batch_size'}
     hp = O.make_hparams(**hk)
     params, _ = O.init_params(hp, IMAGE, seed=0)
@@ -99,18 +99,31 @@ def oracle_step_time(batch, steps, threads):
         times.append(time.time() - t0)
         params = res['params']
     times = times[1:] if len(times) > 1 else times     # first step warms the allocator / oneDNN primitive cache
-    return sum(times) / len(times)
+    return sum(times) / len(times), torch.get_num_threads()
+
+
+def cpu_baseline_subprocess(batch, steps, timeout_s=240):
+    """Runs the oracle timing in a fresh interpreter (no CUDA context, torch's default intra-op thread pool = the
+    host's physical cores) so that the GPU process's threads cannot interfere; bounded by a timeout."""
+    code = ('import sys, json; sys.path.insert(0, %r); import bench; '
+            't, n = bench.oracle_step_time(%d, %d); print(json.dumps(dict(sec_per_step=t, threads=n)))' % (ROOT, batch, steps))
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES='')
+    try:
+        r = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, timeout=timeout_s, env=env)
+        line = [l for l in r.stdout.splitlines() if l.startswith('{')]
+        return json.loads(line[-1]) if line else None
+    except subprocess.TimeoutExpired:
+        return None
 
 
 def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
     sample_b = 2
     frames = sample_b * (SAVP_HPARAMS['sequence_length'] - 1)
     k = max(1, min(args.steps, 3))
-    t = oracle_step_time(sample_b, k, cores)
+    t, cores = oracle_step_time(sample_b, k)
     fps = frames / t
     sample = '%d full SAVP training steps at batch %d (of %d) on the host, torch/oneDNN fp32' % (k, sample_b, PER_GPU_BATCH)
     line = dict(metric='frames/sec SAVP 64x64 2+10 (training)', value=fps, unit='frames/s', n_gpus=args.gpus, steps=k,
@@ -284,11 +297,14 @@ def run_ours(args):
                     traffic=None, per_layer=per_layer)
         cpu = None
         if world == 1 and not args.no_cpu:
-            cores = os.cpu_count() or 1
             sb = 2
-            tcpu = oracle_step_time(sb, 2, cores)
-            cpu = dict(value=sb * S / tcpu, unit='frames/s', cores=cores, kind='port',
-                       sample='2 full SAVP training steps at batch %d (of %d) with the CPU oracle (torch/oneDNN fp32)' % (sb, B))
+            r = cpu_baseline_subprocess(sb, 2)
+            if r is not None:
+                cpu = dict(value=sb * S / r['sec_per_step'], unit='frames/s', cores=r['threads'], kind='port',
+                           sample='2 full SAVP training steps at batch %d (of %d) with the CPU oracle (torch/oneDNN fp32, '
+                                  '%d intra-op threads, %d logical CPUs)' % (sb, B, r['threads'], os.cpu_count() or 0))
+            else:
+                cpu = dict(value=None, unit='frames/s', cores=os.cpu_count(), kind='port', sample='timed out')
         clocks = sampler.summary()
         line = dict(metric='frames/sec SAVP 64x64 2+10 (training)', value=frames_per_step / ms * 1e3, unit='frames/s',
                     n_gpus=world, steps=args.steps, warmup=max(3, args.warmup), ms_per_step=ms, higher_is_better=True,
