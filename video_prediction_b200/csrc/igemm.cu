@@ -54,6 +54,8 @@ struct alignas(64) IgemmArgs {
   int32_t accumulate;
   // wgrad only
   int32_t rows_from_shifted, m_tiles, n_tiles, kpad;
+  int32_t tap_group, num_taps, rows_valid, wg_stages, stages;
+  uint32_t wg_stage_bytes;
   Tap taps[kMaxTaps];
 };
 
@@ -70,7 +72,7 @@ __device__ __forceinline__ float apply_act(float v, int act, float alpha) {
 // ------------------------------------------------------------------------------------------------
 // forward / dgrad kernel: one CTA = one (128-pixel tile, BN-column tile, phase, k-split)
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(192, 1) igemm_fwd_kernel(const __grid_constant__ IgemmArgs a) {
+__global__ void __launch_bounds__(192, 2) igemm_fwd_kernel(const __grid_constant__ IgemmArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   __shared__ uint64_t full_bar[kStagesFwd], empty_bar[kStagesFwd], tmem_full_bar;
@@ -95,7 +97,7 @@ __global__ void __launch_bounds__(192, 1) igemm_fwd_kernel(const __grid_constant
   if (it1 <= it0) return;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < kStagesFwd; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    for (int i = 0; i < a.stages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
     mbar_init(&tmem_full_bar, 1);
     fence_barrier_init();
   }
@@ -107,8 +109,8 @@ __global__ void __launch_bounds__(192, 1) igemm_fwd_kernel(const __grid_constant
 
   if (warp == 0) {
     if (lane == 0) {
+      int s = 0, ph = 0;
       for (int it = it0; it < it1; ++it) {
-        const int li = it - it0, s = li % kStagesFwd, ph = (li / kStagesFwd) & 1;
         mbar_wait(&empty_bar[s], ph ^ 1);
         const Tap tp = a.taps[tb + it / a.kc];
         const int kci = it % a.kc;
@@ -117,13 +119,14 @@ __global__ void __launch_bounds__(192, 1) igemm_fwd_kernel(const __grid_constant
         mbar_expect_tx(&full_bar[s], stage_bytes);
         tma_load_5d(As, &a.amap[tp.map], &full_bar[s], kci * 32, x0 + tp.cw, y0 + tp.ch, d0 + tp.cd, s0);
         tma_load_2d(Bs, &a.bmap, &full_bar[s], kci * 32, tp.wslot * a.n_pad + n0);
+        if (++s == a.stages) { s = 0; ph ^= 1; }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       const uint32_t idesc = make_idesc_tf32(128, a.bn_tile, 0, 0);
+      int s = 0, ph = 0;
       for (int it = it0; it < it1; ++it) {
-        const int li = it - it0, s = li % kStagesFwd, ph = (li / kStagesFwd) & 1;
         mbar_wait(&full_bar[s], ph);
         tc_fence_after();
         const uint32_t a_addr = smem_u32(smem + s * stage_bytes);
@@ -132,9 +135,10 @@ __global__ void __launch_bounds__(192, 1) igemm_fwd_kernel(const __grid_constant
         for (int k = 0; k < 4; ++k) {
           const uint64_t ad = make_smem_desc(a_addr + k * 32, 16, 1024, 0);
           const uint64_t bd = make_smem_desc(b_addr + k * 32, 16, 1024, 0);
-          umma_tf32(tmem_base, ad, bd, idesc, (li > 0 || k > 0) ? 1u : 0u);
+          umma_tf32(tmem_base, ad, bd, idesc, (it > it0 || k > 0) ? 1u : 0u);
         }
         umma_commit(&empty_bar[s]);
+        if (++s == a.stages) { s = 0; ph ^= 1; }
       }
       umma_commit(&tmem_full_bar);
     }
@@ -196,34 +200,44 @@ __global__ void __launch_bounds__(192, 1) igemm_fwd_kernel(const __grid_constant
 }
 
 // ------------------------------------------------------------------------------------------------
-// wgrad kernel: one CTA = (128 dy-channels x up-to-128 x-channels, one tap, a range of pixel boxes)
-// Both operands are MN-major (channel-contiguous) 64-pixel boxes; GEMM-K = pixels.
+// wgrad kernel: one CTA = (128 dy-channels x up-to-128 x-channels) x a GROUP of filter taps x a range of
+// pixel boxes.  Both operands are MN-major (channel-contiguous) 64-pixel boxes; GEMM-K = pixels.
+// The un-shifted operand (dy for a conv, x for a transposed conv) is fetched ONCE per pixel box and reused
+// by every tap of the group (one TMEM accumulator per tap); only sub-tiles that hold real channels are
+// fetched.  This cuts the L2->smem traffic of the many-pixel / few-channel layers by 4-9x.
 // ------------------------------------------------------------------------------------------------
+constexpr int kWgMaxStages = 4;
 __global__ void __launch_bounds__(192, 1) igemm_wgrad_kernel(const __grid_constant__ IgemmArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  __shared__ uint64_t full_bar[kStagesWg], empty_bar[kStagesWg], tmem_full_bar;
+  __shared__ uint64_t full_bar[kWgMaxStages], empty_bar[kWgMaxStages], tmem_full_bar;
   __shared__ uint32_t tmem_base_smem;
   constexpr uint32_t kSub = kWgPix * 128;  // bytes of one 32-channel sub-tile
-  constexpr uint32_t kStage = 8 * kSub;    // 4 A sub-tiles + up to 4 B sub-tiles
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int mtile = blockIdx.x % a.m_tiles, ntile = blockIdx.x / a.m_tiles;
-  const int m0 = mtile * 128;                     // dy channel (row) origin
-  const int c0 = ntile * 128;                     // x channel (col) origin
-  const int nb = min(4, a.kc - ntile * 4);        // 32-channel boxes of x in this tile
-  const Tap tp = a.taps[blockIdx.y];
+  const int m0 = mtile * 128;                                   // dy channel (row) origin
+  const int c0 = ntile * 128;                                   // x channel (col) origin
+  const int nb = min(4, a.kc - ntile * 4);                      // 32-channel boxes of x in this tile
+  const int na = min(4, (a.rows_valid - m0 + 31) / 32);         // 32-channel boxes of dy that hold real channels
+  const int t0 = blockIdx.y * a.tap_group;
+  const int nt = min(a.tap_group, a.num_taps - t0);
+  const int ncols = 32 * nb;
+  const int stages = a.wg_stages;
+  const uint32_t stage_bytes = a.wg_stage_bytes;
+  const bool a_shifted = a.rows_from_shifted != 0;
+  const int n_shared = a_shifted ? nb : na, n_per = a_shifted ? na : nb;
   const int total = a.tiles_w * a.tiles_h * a.tiles_d * a.tiles_n;
   const int it0 = static_cast<int>(static_cast<long long>(total) * blockIdx.z / a.splits);
   const int it1 = static_cast<int>(static_cast<long long>(total) * (blockIdx.z + 1) / a.splits);
-  if (it1 <= it0) return;
+  if (it1 <= it0 || na <= 0) return;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < kStagesWg; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    for (int i = 0; i < stages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
     mbar_init(&tmem_full_bar, 1);
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(&tmem_base_smem, 128);
+  if (warp == 1) tmem_alloc(&tmem_base_smem, a.tmem_cols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -231,8 +245,8 @@ __global__ void __launch_bounds__(192, 1) igemm_wgrad_kernel(const __grid_consta
 
   if (warp == 0) {
     if (lane == 0) {
+      int s = 0, ph = 0;
       for (int it = it0; it < it1; ++it) {
-        const int li = it - it0, s = li % kStagesWg, ph = (li / kStagesWg) & 1;
         int mt = it;
         const int tw = mt % a.tiles_w; mt /= a.tiles_w;
         const int th = mt % a.tiles_h; mt /= a.tiles_h;
@@ -240,44 +254,43 @@ __global__ void __launch_bounds__(192, 1) igemm_wgrad_kernel(const __grid_consta
         const int tn = mt / a.tiles_d;
         const int x0 = tw * a.bw, y0 = th * a.bh, d0 = td * a.bd, s0 = tn * a.bn;
         mbar_wait(&empty_bar[s], ph ^ 1);
-        uint8_t* As = smem + s * kStage;
-        uint8_t* Bs = As + 4 * kSub;
-        mbar_expect_tx(&full_bar[s], (4 + nb) * kSub);
-        // rows (A) come from dy, cols (B) from x; exactly one of them is the tap-shifted operand
-        for (int i = 0; i < 4; ++i) {
-          if (a.rows_from_shifted)
-            tma_load_5d(As + i * kSub, &a.amap[tp.map], &full_bar[s], m0 + 32 * i, x0 + tp.cw, y0 + tp.ch,
-                        d0 + tp.cd, s0);
-          else
-            tma_load_5d(As + i * kSub, &a.bmap, &full_bar[s], m0 + 32 * i, x0, y0, d0, s0);
+        uint8_t* st = smem + s * stage_bytes;
+        mbar_expect_tx(&full_bar[s], (n_shared + nt * n_per) * kSub);
+        // shared (un-shifted) operand first, then one block per tap of the shifted operand
+        const int sh_c0 = a_shifted ? c0 : m0, pt_c0 = a_shifted ? m0 : c0;
+        for (int i = 0; i < n_shared; ++i) tma_load_5d(st + i * kSub, &a.bmap, &full_bar[s], sh_c0 + 32 * i, x0, y0, d0, s0);
+        for (int t = 0; t < nt; ++t) {
+          const Tap tp = a.taps[t0 + t];
+          for (int i = 0; i < n_per; ++i)
+            tma_load_5d(st + (n_shared + t * n_per + i) * kSub, &a.amap[tp.map], &full_bar[s], pt_c0 + 32 * i, x0 + tp.cw,
+                        y0 + tp.ch, d0 + tp.cd, s0);
         }
-        for (int j = 0; j < nb; ++j) {
-          if (a.rows_from_shifted)
-            tma_load_5d(Bs + j * kSub, &a.bmap, &full_bar[s], c0 + 32 * j, x0, y0, d0, s0);
-          else
-            tma_load_5d(Bs + j * kSub, &a.amap[tp.map], &full_bar[s], c0 + 32 * j, x0 + tp.cw, y0 + tp.ch,
-                        d0 + tp.cd, s0);
-        }
+        if (++s == stages) { s = 0; ph ^= 1; }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      const uint32_t idesc = make_idesc_tf32(128, 32 * nb, 1, 1);
+      const uint32_t idesc = make_idesc_tf32(128, ncols, 1, 1);
+      int s = 0, ph = 0;
       for (int it = it0; it < it1; ++it) {
-        const int li = it - it0, s = li % kStagesWg, ph = (li / kStagesWg) & 1;
         mbar_wait(&full_bar[s], ph);
         tc_fence_after();
-        const uint32_t a_addr = smem_u32(smem + s * kStage);
-        const uint32_t b_addr = a_addr + 4 * kSub;
+        const uint32_t base = smem_u32(smem + s * stage_bytes);
+        for (int t = 0; t < nt; ++t) {
+          const uint32_t per = base + (n_shared + t * n_per) * kSub;
+          const uint32_t a_addr = a_shifted ? per : base, b_addr = a_shifted ? base : per;
 #pragma unroll
-        for (int k = 0; k < kWgPix / 8; ++k) {
-          // MN-major tf32: 32-channel x 4-pixel atoms (512 B) with the 32-byte-granular 128B swizzle;
-          // LBO = stride between 32-channel groups, SBO = stride between 4-pixel groups.
-          const uint64_t ad = make_smem_desc(a_addr + k * 1024, kSub, 512, 0, 1);
-          const uint64_t bd = make_smem_desc(b_addr + k * 1024, kSub, 512, 0, 1);
-          umma_tf32(tmem_base, ad, bd, idesc, (li > 0 || k > 0) ? 1u : 0u);
+          for (int k = 0; k < kWgPix / 8; ++k) {
+            // MN-major tf32: 32-channel x 4-pixel atoms (512 B) with the 32-byte-granular 128B swizzle;
+            // LBO = stride between 32-channel groups, SBO = stride between 4-pixel groups.  M = 128 always reads
+            // four 32-channel groups; groups beyond `na` alias neighbouring data and only feed rows never stored.
+            const uint64_t ad = make_smem_desc(a_addr + k * 1024, kSub, 512, 0, 1);
+            const uint64_t bd = make_smem_desc(b_addr + k * 1024, kSub, 512, 0, 1);
+            umma_tf32(tmem_base + t * ncols, ad, bd, idesc, (it > it0 || k > 0) ? 1u : 0u);
+          }
         }
         umma_commit(&empty_bar[s]);
+        if (++s == stages) { s = 0; ph ^= 1; }
       }
       umma_commit(&tmem_full_bar);
     }
@@ -285,23 +298,26 @@ __global__ void __launch_bounds__(192, 1) igemm_wgrad_kernel(const __grid_consta
   } else {
     const int q = warp & 3;
     const int row = m0 + q * 32 + lane;
-    const bool rvalid = row < a.n_pad;
-    float* orow = a.out + (static_cast<long long>(tp.wslot) * a.n_pad + row) * a.kpad + c0;
+    const bool rvalid = row < a.n_pad && row < a.rows_valid;
     mbar_wait(&tmem_full_bar, 0);
     tc_fence_after();
-    for (int cc = 0; cc < 32 * nb; cc += 16) {
-      float v[16];
-      __syncwarp();
-      tmem_ld16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + cc, v);
-      if (rvalid) {
+    for (int t = 0; t < nt; ++t) {
+      const Tap tp = a.taps[t0 + t];
+      float* orow = a.out + (static_cast<long long>(tp.wslot) * a.n_pad + row) * a.kpad + c0;
+      for (int cc = 0; cc < ncols; cc += 16) {
+        float v[16];
+        __syncwarp();
+        tmem_ld16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + t * ncols + cc, v);
+        if (rvalid) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) atomicAdd(orow + cc + j, v[j]);
+          for (int j = 0; j < 16; ++j) atomicAdd(orow + cc + j, v[j]);
+        }
       }
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, 128);
+  if (warp == 1) tmem_dealloc(tmem_base, a.tmem_cols);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -488,7 +504,8 @@ extern "C" int vp_conv_igemm(const vp_tensor* in, const vp_conv_geom* g, const f
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return set_error("cuTensorMapEncodeTiled(weights) failed with %d", static_cast<int>(r));
   }
-  const size_t smem = static_cast<size_t>(kStagesFwd) * (16384 + A.bn_tile * 128) + 1024;
+  A.stages = A.bn_tile <= 128 ? 3 : kStagesFwd;     // <= 97 KB -> two CTAs per SM overlap prologue/epilogue with the main loop
+  const size_t smem = static_cast<size_t>(A.stages) * (16384 + A.bn_tile * 128) + 1024;
   static bool attr_set = false;
   if (!attr_set) {
     if (cudaFuncSetAttribute(igemm_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kStagesFwd * (16384 + 256 * 128) + 1024) != cudaSuccess)
@@ -523,20 +540,36 @@ extern "C" int vp_conv_wgrad(const vp_tensor* x, const vp_tensor* dy, const vp_c
   if (make_act_map(&A.bmap, plain, 0, 0, 0, 1, 1, 1, box, true)) return -1;
   A.rows_from_shifted = g->transposed ? 1 : 0;
   A.kc = kc; A.n_pad = n_pad; A.kpad = kc * 32;
-  A.m_tiles = ceil_div(n_pad, 128);
+  A.rows_valid = dy->c;
+  A.m_tiles = ceil_div(std::min(n_pad, ceil_div(dy->c, 32) * 32), 128);
   A.n_tiles = ceil_div(kc, 4);
+  A.num_taps = A.phase_begin[1];
+  // tap group: bounded by TMEM columns (one accumulator per tap) and by the per-stage shared-memory budget
+  const int nb_max = std::min(4, kc), na_max = std::min(4, ceil_div(dy->c, 32));
+  const int n_shared = A.rows_from_shifted ? nb_max : na_max, n_per = A.rows_from_shifted ? na_max : nb_max;
+  int tg = std::min(512 / (32 * nb_max), (12 - n_shared) / n_per);
+  tg = std::max(1, std::min(tg, A.num_taps));
+  const int groups = ceil_div(A.num_taps, tg);
+  tg = ceil_div(A.num_taps, groups);     // balance the groups
+  A.tap_group = tg;
+  A.tmem_cols = next_pow2_cols(tg * 32 * nb_max);
+  A.wg_stage_bytes = static_cast<uint32_t>(n_shared + tg * n_per) * kWgPix * 128;
+  A.wg_stages = std::max(2, std::min(kWgMaxStages, static_cast<int>((200u * 1024u) / A.wg_stage_bytes)));
   const int total = A.tiles_w * A.tiles_h * A.tiles_d * A.tiles_n;
-  A.splits = std::max(1, std::min(split_k, total));
+  const int ctas = A.m_tiles * A.n_tiles * groups;
+  if (split_k <= 0) split_k = ceil_div(2 * 148, ctas);       // auto: about two waves of CTAs
+  A.splits = std::max(1, std::min(split_k, std::max(1, total / 4)));
   A.out = dwpacked;
-  const int ntaps = A.phase_begin[1];
   static bool attr_set = false;
+  const size_t smem_max = 227 * 1024 - 2048;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(igemm_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kStagesWg * 8 * kWgPix * 128 + 1024) != cudaSuccess)
+    if (cudaFuncSetAttribute(igemm_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_max)) != cudaSuccess)
       return set_error("cudaFuncSetAttribute(igemm_wgrad_kernel) failed: %s", cudaGetErrorString(cudaGetLastError()));
     attr_set = true;
   }
-  const size_t smem = static_cast<size_t>(kStagesWg) * 8 * kWgPix * 128 + 1024;
-  dim3 grid(A.m_tiles * A.n_tiles, ntaps, A.splits);
+  const size_t smem = static_cast<size_t>(A.wg_stages) * A.wg_stage_bytes + 3 * kWgPix * 128 + 1024;
+  if (smem > smem_max) return set_error("vp_conv_wgrad: shared memory budget exceeded (%zu)", smem);
+  dim3 grid(A.m_tiles * A.n_tiles, groups, A.splits);
   igemm_wgrad_kernel<<<grid, 192, smem, static_cast<cudaStream_t>(stream)>>>(A);
   count_launch(1);
   cudaError_t e = cudaGetLastError();

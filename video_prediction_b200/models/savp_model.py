@@ -112,7 +112,7 @@ class ConvLayer(object):
         pix = xv.n * max(xv.h, dyv.h) * max(xv.w, dyv.w)
         splits = max(1, min(pix // 256, (592 + tiles - 1) // tiles))
         self.dwp.zero_()
-        L.conv_wgrad(xv, dyv, self.geom, self.dwp, self.n_pad, self.kc, split_k=splits)
+        L.conv_wgrad(xv, dyv, self.geom, self.dwp, self.n_pad, self.kc, split_k=0)
         L.unpack_wgrad(self.dwp, self.k, self.ci_ref, self.co, self.kind, self.model.grads[self.wname], self.n_pad, self.kc,
                        ci_int=self.ci_int, cmap=self.cmap)
 

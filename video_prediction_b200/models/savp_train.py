@@ -89,7 +89,7 @@ class SNLayer(object):
         m = self.m
         self.dwp.zero_()
         L.conv_wgrad(L.tensor_view(x, self.cin_int), L.tensor_view(dy, self.co), self.geom, self.dwp, self.n_pad, self.kc,
-                     split_k=m.wgrad_splits(x))
+                     split_k=0)
         self.gwbar.zero_()
         L.unpack_wgrad(self.dwp, (self.k,) * 3, self.cin_ref, self.co, L.WKIND_PLAIN, self.gwbar, self.n_pad, self.kc,
                        ci_int=self.cin_int, cmap=self.cmap)
