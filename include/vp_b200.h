@@ -63,6 +63,16 @@ int vp_conv_igemm(const vp_tensor* in, const vp_conv_geom* g, const float* wpack
                   const vp_tensor* out, const float* bias, int act, float alpha, int split_k, int accumulate,
                   vp_stream_t stream);
 
+/* Halo-resident variant of vp_conv_igemm for 2-D stride-1 convolutions (the ConvLSTM gate convolutions,
+ * rnn_ops.py:121, and their input gradients).  `in` is a zero-padded FLATTENED plane stack: dims (n, 1, Hp, P) with
+ * the valid valid_h x valid_w region in the top-left corner of each plane and zeros elsewhere; the gaps Hp - valid_h
+ * and P - valid_w must be >= the filter reach.  `out` is a dense (n, 1, valid_h, valid_w) view.  One halo tile per
+ * 32-channel chunk stays resident in shared memory and every filter tap is a shifted UMMA descriptor on it.
+ * desc_mode: 0 = descriptor base_offset 0 (swizzle keyed on the absolute address), 1 = base_offset from the address. */
+int vp_conv_flat(const vp_tensor* in, int valid_h, int valid_w, const vp_conv_geom* g, const float* wpacked, int n_pad,
+                 int kc, const vp_tensor* out, const float* bias, int act, float alpha, int split_k, int accumulate,
+                 int desc_mode, vp_stream_t stream);
+
 /* Weight gradient of the same convolution: dwpacked[tap][co][ci] += sum_o  dy.. * x..
  * (layout VP_WLAYOUT_FWD: rows = channels of dy (n_pad rows), cols = kc*32 channels of x).
  * Always accumulates atomically: caller zero-fills before the first call of a step. */

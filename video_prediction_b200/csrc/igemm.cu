@@ -504,7 +504,10 @@ extern "C" int vp_conv_igemm(const vp_tensor* in, const vp_conv_geom* g, const f
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return set_error("cuTensorMapEncodeTiled(weights) failed with %d", static_cast<int>(r));
   }
-  A.stages = A.bn_tile <= 128 ? 3 : kStagesFwd;     // <= 97 KB -> two CTAs per SM overlap prologue/epilogue with the main loop
+  const long long n_ctas = static_cast<long long>(A.tiles_w) * A.tiles_h * A.tiles_d * A.tiles_n * (n_pad / A.bn_tile) * A.num_phases * A.splits;
+  // more than one CTA per SM's worth of work: 3 stages (<= 97 KB) so two CTAs share an SM and overlap prologue/epilogue
+  // with the other's main loop; a single partial wave keeps the deeper 4-stage pipeline
+  A.stages = (A.bn_tile <= 128 && n_ctas > 148) ? 3 : kStagesFwd;
   const size_t smem = static_cast<size_t>(A.stages) * (16384 + A.bn_tile * 128) + 1024;
   static bool attr_set = false;
   if (!attr_set) {

@@ -82,6 +82,12 @@ def conv_igemm(x_view, g, wpacked, n_pad, kc, out_view, bias=None, act=ACT_NONE,
                               act, C.c_float(alpha), split_k, int(accumulate), stream_ptr()))
 
 
+def conv_flat(x_view, valid_h, valid_w, g, wpacked, n_pad, kc, out_view, bias=None, act=ACT_NONE, alpha=0.0, split_k=1,
+              accumulate=0, desc_mode=0):
+    check(lib().vp_conv_flat(C.byref(x_view), valid_h, valid_w, C.byref(g), ptr(wpacked), n_pad, kc, C.byref(out_view), ptr(bias),
+                             act, C.c_float(alpha), split_k, int(accumulate), desc_mode, stream_ptr()))
+
+
 def conv_wgrad(x_view, dy_view, g, dwpacked, n_pad, kc, split_k=1):
     check(lib().vp_conv_wgrad(C.byref(x_view), C.byref(dy_view), C.byref(g), ptr(dwpacked), n_pad, kc, split_k,
                               stream_ptr()))
