@@ -58,10 +58,19 @@ int vp_version(void);
  * wpacked: [kd*kh*kw][n_pad][kc*32] floats (see vp_pack_weights); GEMM N = n_pad (multiple of 16),
  * GEMM K = kc 32-channel chunks of in->c per tap.  out->c columns are stored.
  * split_k > 1: partial sums are atomically added into `out` (caller zero-fills; act must be NONE;
- * bias is added by split 0).  accumulate != 0: out += result (act must be NONE). */
+ * bias is added by split 0).  split_k == 0: automatic -- an under-filled grid with a long K loop is split and a DENSE
+ * output (out->c == out->cstride) is cleared by the call itself.  accumulate != 0: out += result (act must be NONE). */
 int vp_conv_igemm(const vp_tensor* in, const vp_conv_geom* g, const float* wpacked, int n_pad, int kc,
                   const vp_tensor* out, const float* bias, int act, float alpha, int split_k, int accumulate,
                   vp_stream_t stream);
+
+/* Input-gradient convolution fused with the backward of the previous layer's activation:
+ *   out = (conv(in) + addend) * act'(act_output),  act' evaluated from the activation OUTPUT (lrelu/relu/sigmoid/tanh);
+ * act_output / addend (optional) have exactly the layout of the dense `out`.  Used for the discriminator towers
+ * (lrelu(conv3d), networks.py:83-102), where it removes one full read+write pass per layer. */
+int vp_conv_igemm_actgrad(const vp_tensor* in, const vp_conv_geom* g, const float* wpacked, int n_pad, int kc,
+                          const vp_tensor* out, const float* act_output, const float* addend, int act, float alpha,
+                          vp_stream_t stream);
 
 /* Halo-resident variant of vp_conv_igemm for 2-D stride-1 convolutions (the ConvLSTM gate convolutions,
  * rnn_ops.py:121, and their input gradients).  `in` is a zero-padded FLATTENED plane stack: dims (n, 1, Hp, P) with

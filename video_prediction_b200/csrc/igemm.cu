@@ -52,6 +52,9 @@ struct alignas(64) IgemmArgs {
   int32_t act;
   float alpha;
   int32_t accumulate;
+  const float* aux_y;    // optional: activation OUTPUT with the layout of `out`; result is multiplied by act'(aux_y)
+  const float* aux_add;  // optional addend (same layout), added before the multiplication
+  int32_t aux_act;
   // wgrad only
   int32_t rows_from_shifted, m_tiles, n_tiles, kpad;
   int32_t tap_group, num_taps, rows_valid, wg_stages, stages;
@@ -157,7 +160,8 @@ __global__ void __launch_bounds__(192, 2) igemm_fwd_kernel(const __grid_constant
     const int od = (d0 + ld) * a.os_d + a.phase_ooff[phase][0];
     const int on = s0 + ln;
     const bool rvalid = (ow < a.out_w) && (oh < a.out_h) && (od < a.out_d) && (on < a.out_n);
-    float* orow = a.out + on * a.so_n + od * a.so_d + oh * a.so_h + ow * a.so_w;
+    const long long ooff = on * a.so_n + od * a.so_d + oh * a.so_h + ow * a.so_w;
+    float* orow = a.out + ooff;
     const bool add_bias = (a.bias != nullptr) && (split == 0);
     mbar_wait(&tmem_full_bar, 0);
     tc_fence_after();
@@ -177,6 +181,21 @@ __global__ void __launch_bounds__(192, 2) igemm_fwd_kernel(const __grid_constant
         } else {
 #pragma unroll
           for (int j = 0; j < 16; ++j) v[j] = apply_act(v[j], a.act, a.alpha);
+          if (a.aux_y != nullptr) {   // fused backward of the previous layer's activation: (v + add) * act'(y)
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              if (col0 + j < a.out_c) {
+                const float yv = __ldg(a.aux_y + ooff + col0 + j);
+                float t = v[j];
+                if (a.aux_add != nullptr) t += __ldg(a.aux_add + ooff + col0 + j);
+                if (a.aux_act == VP_ACT_LRELU) t = yv > 0.f ? t : a.alpha * t;
+                else if (a.aux_act == VP_ACT_RELU) t = yv > 0.f ? t : 0.f;
+                else if (a.aux_act == VP_ACT_SIGMOID) t *= yv * (1.f - yv);
+                else if (a.aux_act == VP_ACT_TANH) t *= (1.f - yv * yv);
+                v[j] = t;
+              }
+            }
+          }
           if (col0 + 16 <= a.out_c) {
             float4* o4 = reinterpret_cast<float4*>(orow + col0);
 #pragma unroll
@@ -461,30 +480,53 @@ static int next_pow2_cols(int n) { int c = 32; while (c < n) c *= 2; return c; }
 
 using namespace vp;
 
-extern "C" int vp_conv_igemm(const vp_tensor* in, const vp_conv_geom* g, const float* wpacked, int n_pad, int kc,
-                             const vp_tensor* out, const float* bias, int act, float alpha, int split_k,
-                             int accumulate, vp_stream_t stream) {
+static int conv_igemm_impl(const vp_tensor* in, const vp_conv_geom* g, const float* wpacked, int n_pad, int kc,
+                           const vp_tensor* out, const float* bias, int act, float alpha, int split_k, int accumulate,
+                           const float* aux_y, const float* aux_add, int aux_act, vp_stream_t stream) {
   if (check_tensor(in, "vp_conv_igemm(in)") || check_tensor(out, "vp_conv_igemm(out)")) return -1;
   if (!g || !wpacked) return set_error("vp_conv_igemm: null argument");
   if (n_pad % 16 || n_pad < 16) return set_error("vp_conv_igemm: n_pad must be a positive multiple of 16");
   if (kc < 1 || kc * 32 < in->c) return set_error("vp_conv_igemm: kc*32 must cover in->c");
   if (out->c > n_pad) return set_error("vp_conv_igemm: out->c exceeds n_pad");
   if (in->n != out->n) return set_error("vp_conv_igemm: batch mismatch");
-  if (split_k < 1) split_k = 1;
   if (split_k > 1 && act != VP_ACT_NONE) return set_error("vp_conv_igemm: split_k needs act NONE");
+  if (aux_y && split_k > 1) return set_error("vp_conv_igemm: the fused activation gradient needs split_k <= 1");
   static IgemmArgs A;  // large POD; host-side scratch (calls are serialized by the Python GIL / caller)
   std::memset(&A, 0, sizeof(A));
   const int lat[4] = {out->w, out->h, out->d, out->n};
   if (build_geometry(A, g, in, 128, lat)) return -1;
   A.kc = kc; A.n_pad = n_pad;
-  A.bn_tile = n_pad <= 256 ? n_pad : (n_pad % 256 == 0 ? 256 : (n_pad % 128 == 0 ? 128 : 0));
-  if (n_pad >= 256 && n_pad % 128 == 0) A.bn_tile = 128;  // more CTAs for the small-M ConvLSTM GEMMs
+  // N tiling: the whole N when it fits one UMMA (<= 256); 128-wide tiles for multiples of 128 (more CTAs for the
+  // small-M ConvLSTM GEMMs); otherwise the fewest equal tiles that are multiples of 16 (n_pad = tiles * bn_tile).
+  if (n_pad <= 256) A.bn_tile = n_pad;
+  if (n_pad >= 256 && n_pad % 128 == 0) A.bn_tile = 128;
+  if (A.bn_tile == 0) {
+    const int tiles = ceil_div(n_pad, 256);
+    if (n_pad % tiles == 0 && (n_pad / tiles) % 16 == 0) A.bn_tile = n_pad / tiles;
+  }
   if (A.bn_tile == 0) return set_error("vp_conv_igemm: unsupported n_pad %d", n_pad);
   A.tmem_cols = next_pow2_cols(A.bn_tile);
   int min_iters = 1 << 30;
   for (int p = 0; p < A.num_phases; ++p) min_iters = std::min(min_iters, (A.phase_begin[p + 1] - A.phase_begin[p]) * kc);
   if (min_iters < 1) return set_error("vp_conv_igemm: a phase has no taps");
-  A.splits = std::min(split_k, min_iters);
+  const long long base_ctas = 1LL * A.tiles_w * A.tiles_h * A.tiles_d * A.tiles_n * (n_pad / A.bn_tile) * A.num_phases;
+  if (split_k <= 0) {
+    // auto: an under-filled grid with a long K loop is split over K; the partial sums are reduced with atomics into a
+    // zero-filled output (only when the output view is dense so that it can be cleared here, and the epilogue is linear)
+    split_k = 1;
+    const bool dense = out->c == out->cstride;
+    if (dense && act == VP_ACT_NONE && !accumulate && !aux_y && base_ctas < 120 && min_iters >= 24) {
+      split_k = static_cast<int>(std::min<long long>(8, (296 + base_ctas - 1) / base_ctas));
+      split_k = std::max(1, std::min(split_k, min_iters / 12));
+      if (split_k > 1) {
+        const size_t bytes = static_cast<size_t>(out->n) * out->d * out->h * out->w * out->cstride * sizeof(float);
+        if (cudaMemsetAsync(out->ptr, 0, bytes, static_cast<cudaStream_t>(stream)) != cudaSuccess)
+          return set_error("vp_conv_igemm: cudaMemsetAsync failed");
+      }
+    }
+  }
+  A.splits = std::max(1, std::min(split_k, min_iters));
+  A.aux_y = aux_y; A.aux_add = aux_add; A.aux_act = aux_act;
   A.out = out->ptr;
   A.so_w = out->cstride; A.so_h = A.so_w * out->w; A.so_d = A.so_h * out->h; A.so_n = A.so_d * out->d;
   A.out_n = out->n; A.out_d = out->d; A.out_h = out->h; A.out_w = out->w; A.out_c = out->c;
@@ -521,6 +563,20 @@ extern "C" int vp_conv_igemm(const vp_tensor* in, const vp_conv_geom* g, const f
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error("igemm_fwd_kernel launch failed: %s", cudaGetErrorString(e));
   return 0;
+}
+
+extern "C" int vp_conv_igemm(const vp_tensor* in, const vp_conv_geom* g, const float* wpacked, int n_pad, int kc,
+                             const vp_tensor* out, const float* bias, int act, float alpha, int split_k,
+                             int accumulate, vp_stream_t stream) {
+  return conv_igemm_impl(in, g, wpacked, n_pad, kc, out, bias, act, alpha, split_k, accumulate, nullptr, nullptr, 0, stream);
+}
+
+extern "C" int vp_conv_igemm_actgrad(const vp_tensor* in, const vp_conv_geom* g, const float* wpacked, int n_pad, int kc,
+                                     const vp_tensor* out, const float* act_output, const float* addend, int act,
+                                     float alpha, vp_stream_t stream) {
+  if (!act_output) return set_error("vp_conv_igemm_actgrad: act_output is required");
+  if (out->c != out->cstride) return set_error("vp_conv_igemm_actgrad: dense output required");
+  return conv_igemm_impl(in, g, wpacked, n_pad, kc, out, nullptr, VP_ACT_NONE, alpha, 1, 0, act_output, addend, act, stream);
 }
 
 extern "C" int vp_conv_wgrad(const vp_tensor* x, const vp_tensor* dy, const vp_conv_geom* g, float* dwpacked,

@@ -82,6 +82,12 @@ def conv_igemm(x_view, g, wpacked, n_pad, kc, out_view, bias=None, act=ACT_NONE,
                               act, C.c_float(alpha), split_k, int(accumulate), stream_ptr()))
 
 
+def conv_igemm_actgrad(x_view, g, wpacked, n_pad, kc, out_view, act_output_addr, addend_addr, act, alpha=0.0):
+    check(lib().vp_conv_igemm_actgrad(C.byref(x_view), C.byref(g), ptr(wpacked), n_pad, kc, C.byref(out_view),
+                                      C.c_void_p(act_output_addr), C.c_void_p(addend_addr or 0), act, C.c_float(alpha),
+                                      stream_ptr()))
+
+
 def conv_flat(x_view, valid_h, valid_w, g, wpacked, n_pad, kc, out_view, bias=None, act=ACT_NONE, alpha=0.0, split_k=1,
               accumulate=0, desc_mode=0):
     check(lib().vp_conv_flat(C.byref(x_view), valid_h, valid_w, C.byref(g), ptr(wpacked), n_pad, kc, C.byref(out_view), ptr(bias),
@@ -105,13 +111,21 @@ def pad_to(v, m):
     return (v + m - 1) // m * m
 
 
+def choose_n_pad(rows):
+    """GEMM-N padding: multiple of 16; above 256 either a multiple of 128 (128-wide tiles) or the fewest equal tiles."""
+    n = pad_to(rows, 16)
+    if n <= 256 or n % 128 == 0:
+        return n
+    tiles = -(-n // 256)
+    bn = pad_to(-(-rows // tiles), 16)
+    return tiles * bn
+
+
 def pack_weights(w, k, ci_ref, co, kind, layout, ci_int=None, cmap=None, inv_scale=None, out=None):
     """Returns (wpacked, n_pad, kc)."""
     ci_int = ci_ref if ci_int is None else ci_int
     rows, cols = (co, ci_int) if layout == WLAYOUT_FWD else (ci_int, co)
-    n_pad, kc = pad_to(rows, 16), pad_to(cols, 32) // 32
-    if n_pad > 256:
-        n_pad = pad_to(n_pad, 128)
+    n_pad, kc = choose_n_pad(rows), pad_to(cols, 32) // 32
     taps = eff_taps(k, kind)
     if out is None:
         out = torch.empty(taps * n_pad * kc * 32, device=w.device, dtype=torch.float32)

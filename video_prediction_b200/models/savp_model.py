@@ -101,7 +101,8 @@ class ConvLayer(object):
         """dx[.., ci_int] (+)= conv^T(dy): the same engine with the transposed flag flipped."""
         dyv = L.tensor_view(dy.view((-1,) + tuple(dy.shape[-3:])), self.co if dy_c is None else dy_c)
         dxv = L.tensor_view(dx.view((-1,) + tuple(dx.shape[-3:])), self.ci_int)
-        L.conv_igemm(dyv, self.geom_bwd, self.wpd, self.n_pad_d, self.kc_d, dxv, None, L.ACT_NONE, 0.0, 1, accumulate)
+        L.conv_igemm(dyv, self.geom_bwd, self.wpd, self.n_pad_d, self.kc_d, dxv, None, L.ACT_NONE, 0.0, 1 if accumulate else 0,
+                     accumulate)
 
     def wgrad(self, x, dy, dy_c=None):
         """grads[w] += dL/dw from ONE GEMM over every position of the (time-stacked) tensors."""
@@ -116,7 +117,7 @@ class ConvLayer(object):
         L.unpack_wgrad(self.dwp, self.k, self.ci_ref, self.co, self.kind, self.model.grads[self.wname], self.n_pad, self.kc,
                        ci_int=self.ci_int, cmap=self.cmap)
 
-    def fwd(self, x, out, out_off=0, out_c=None, act=L.ACT_NONE, alpha=0.0, split_k=1):
+    def fwd(self, x, out, out_off=0, out_c=None, act=L.ACT_NONE, alpha=0.0, split_k=0):
         """x: stacked buffer [.., h, w, cstride] (4-D or 5-D torch tensor, leading dims folded into n)."""
         xv = L.tensor_view(x.view((-1,) + tuple(x.shape[-3:])), self.ci_int)
         ov = L.tensor_view(out.view((-1,) + tuple(out.shape[-3:])), self.co if out_c is None else out_c, out_off)

@@ -81,8 +81,15 @@ class SNLayer(object):
         L.conv_igemm(L.tensor_view(x, self.cin_int), self.geom, self.wp, self.n_pad, self.kc, L.tensor_view(out, self.co),
                      self.m.params[self.bname], L.ACT_LRELU, 0.1)
 
-    def dgrad(self, dy, dx):
-        L.conv_igemm(L.tensor_view(dy, self.co), self.geom_t, self.wpd, self.n_pad_d, self.kc_d, L.tensor_view(dx, self.cin_int))
+    def dgrad(self, dy, dx, act_y=None, addend=None):
+        """dx = conv^T(dy); with act_y: dx = (conv^T(dy) + addend) * lrelu'(act_y) -- the backward of the previous
+        layer's leaky relu fused into the epilogue."""
+        dyv, dxv = L.tensor_view(dy, self.co), L.tensor_view(dx, self.cin_int)
+        if act_y is None:
+            L.conv_igemm(dyv, self.geom_t, self.wpd, self.n_pad_d, self.kc_d, dxv, None, L.ACT_NONE, 0.0, 0)
+        else:
+            L.conv_igemm_actgrad(dyv, self.geom_t, self.wpd, self.n_pad_d, self.kc_d, dxv, act_y.data_ptr(),
+                                 addend.data_ptr() if addend is not None else 0, L.ACT_LRELU, 0.1)
 
     def wgrad(self, x, dy):
         """dW += SN-backward(dL/dWbar) with dL/dWbar from the tensor-core wgrad GEMM."""
@@ -269,15 +276,16 @@ class TrainMixin(object):
             y, dy = feats[l][r0:r1], dfeats[l][r0:r1]
             rows = int(np.prod(y.shape[:-1]))
             co = lay.co
-            extra = dcd[l][:n] if dcd is not None else None
-            L.act_bwd(y.data_ptr(), co, dy.data_ptr(), co, extra.data_ptr() if extra is not None else 0, co, dy.data_ptr(), co,
-                      rows, co, L.ACT_LRELU, 0.1)
+            if l == len(feats) - 1:     # lower layers get their leaky-relu backward fused into the dgrad epilogue below
+                extra = dcd[l][:n] if dcd is not None else None
+                L.act_bwd(y.data_ptr(), co, dy.data_ptr(), co, extra.data_ptr() if extra is not None else 0, co, dy.data_ptr(), co,
+                          rows, co, L.ACT_LRELU, 0.1)
             x = feats[l - 1][r0:r1] if l > 0 else net['clip'][r0:r1]
             if with_wgrad:
                 L.colsum(dy.data_ptr(), co, Gp[lay.bname], 1, rows, co)
                 lay.wgrad(x, dy)
             if l > 0:
-                lay.dgrad(dy, dfeats[l - 1][r0:r1])
+                lay.dgrad(dy, dfeats[l - 1][r0:r1], act_y=feats[l - 1][r0:r1], addend=dcd[l - 1][:n] if dcd is not None else None)
             elif to_clip:
                 lay.dgrad(dy, net['dclip'][r0:r1])
 
