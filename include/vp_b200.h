@@ -224,6 +224,12 @@ int vp_spectral_norm_fwd(const float* w, const float* u, int rows, int cols, flo
                          float* scal, vp_stream_t stream);
 int vp_spectral_norm_bwd(const float* w, const float* u, const float* g_wbar, int rows, int cols, const float* v,
                          const float* s, float* scal, float* gs, float* gt, float* dw, vp_stream_t stream);
+/* First discriminator layer on the CUDA cores (conv3d 3x3x3, stride 1, zero pad 1, <= 4 input channels stored as
+ * float4 voxels, 32 output channels, fused bias + leaky relu; networks.py:83-84).  w is the REFERENCE-layout kernel
+ * [3][3][3][ci][32]; it is divided by *inv_scale (spectral-norm sigma).  wgrad accumulates dL/d(w/sigma) into gw. */
+int vp_conv3d_c4_fwd(const float* x, const float* w, const float* inv_scale, const float* bias, float* out, int n, int d,
+                     int h, int wd, int ci, float lrelu_alpha, vp_stream_t stream);
+int vp_conv3d_c4_wgrad(const float* x, const float* dy, float* gw, int n, int d, int h, int wd, int ci, vp_stream_t stream);
 /* savp_model.py:97-102: clip[b][j][p] = video[t_start[b]+j][batch_offset+b][p]; pixels = H*W (4 floats each) */
 int vp_gather_clip(const float* video, const int32_t* t_start, float* clip, int clips, int clip_len, long long pixels,
                    int video_batch, int batch_offset, vp_stream_t stream);

@@ -15,6 +15,7 @@
 // Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA
 // issuer, warps 2..5 = epilogue (TMEM -> registers -> bias/activation -> global).
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <algorithm>
 #include <vector>
@@ -504,6 +505,7 @@ static int conv_igemm_impl(const vp_tensor* in, const vp_conv_geom* g, const flo
     const int tiles = ceil_div(n_pad, 256);
     if (n_pad % tiles == 0 && (n_pad / tiles) % 16 == 0) A.bn_tile = n_pad / tiles;
   }
+  if (const char* e = getenv("VP_FWD_BN")) { const int v = atoi(e); if (v >= 16 && v <= 256 && v % 16 == 0 && n_pad % v == 0) A.bn_tile = v; }
   if (A.bn_tile == 0) return set_error("vp_conv_igemm: unsupported n_pad %d", n_pad);
   A.tmem_cols = next_pow2_cols(A.bn_tile);
   int min_iters = 1 << 30;

@@ -11,6 +11,7 @@
 // L2 -> SM feed drops from ~128 B/cycle/SM to ~35 B/cycle/SM.
 //
 // Warp roles (224 threads): w0 weight producer, w1 MMA issuer + TMEM allocator, w2..5 epilogue, w6 halo producer.
+#include <cstdlib>
 #include <cstring>
 #include <algorithm>
 
@@ -224,6 +225,7 @@ extern "C" int vp_conv_flat(const vp_tensor* in, int valid_h, int valid_w, const
   A.kc = kc; A.n_pad = n_pad;
   A.bn_tile = n_pad <= 256 ? n_pad : (n_pad % 128 == 0 ? 128 : 0);
   if (n_pad > 128 && n_pad % 128 == 0) A.bn_tile = 128;
+  if (const char* e = getenv("VP_FLAT_BN")) { const int v = atoi(e); if (v >= 16 && v <= 256 && v % 16 == 0 && n_pad % v == 0) A.bn_tile = v; }
   if (A.bn_tile == 0) return set_error("vp_conv_flat: n_pad must be <= 256 or a multiple of 128");
   int tc = 32; while (tc < 2 * A.bn_tile) tc *= 2;
   A.tmem_cols = tc;

@@ -323,3 +323,11 @@ def gather_clip(video, t_start, clip, clips, clip_len, pixels, video_batch, batc
 def scatter_clip(dclip, t_start, dvideo, clips, clip_len, pixels, video_batch, batch_offset):
     check(lib().vp_scatter_clip(ptr(dclip), ptr(t_start), ptr(dvideo), clips, clip_len, C.c_longlong(pixels), video_batch,
                                 batch_offset, stream_ptr()))
+
+
+def conv3d_c4_fwd(x, w, inv_scale, bias, out, n, d, h, wd, ci, alpha):
+    check(lib().vp_conv3d_c4_fwd(ptr(x), ptr(w), ptr(inv_scale), ptr(bias), ptr(out), n, d, h, wd, ci, _f(alpha), stream_ptr()))
+
+
+def conv3d_c4_wgrad(x, dy, gw, n, d, h, wd, ci):
+    check(lib().vp_conv3d_c4_wgrad(ptr(x), ptr(dy), ptr(gw), n, d, h, wd, ci, stream_ptr()))

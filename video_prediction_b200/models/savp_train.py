@@ -77,7 +77,17 @@ class SNLayer(object):
         if self.dwp is None:
             self.dwp = torch.zeros(self.k ** 3 * self.n_pad * self.kc * 32, device=w.device)
 
+    @property
+    def cuda_core(self):
+        """First layer (3 colour channels -> 32): bandwidth-sized, runs on the CUDA cores (csrc/discrim.cu)."""
+        return (not self.is_fc) and self.k == 3 and tuple(self.stride) == (1, 1, 1) and self.cin_ref <= 3 and self.co == 32
+
     def fwd(self, x, out):
+        if self.cuda_core:
+            P = self.m.params
+            n, d, h, w = x.shape[:4]
+            L.conv3d_c4_fwd(x, P[self.wname], self.sigma, P[self.bname], out, n, d, h, w, self.cin_ref, 0.1)
+            return
         L.conv_igemm(L.tensor_view(x, self.cin_int), self.geom, self.wp, self.n_pad, self.kc, L.tensor_view(out, self.co),
                      self.m.params[self.bname], L.ACT_LRELU, 0.1)
 
@@ -94,6 +104,12 @@ class SNLayer(object):
     def wgrad(self, x, dy):
         """dW += SN-backward(dL/dWbar) with dL/dWbar from the tensor-core wgrad GEMM."""
         m = self.m
+        if self.cuda_core:
+            n, d, h, w = x.shape[:4]
+            self.gwbar.zero_()
+            L.conv3d_c4_wgrad(x, dy, self.gwbar, n, d, h, w, self.cin_ref)
+            self.sn_backward()
+            return
         self.dwp.zero_()
         L.conv_wgrad(L.tensor_view(x, self.cin_int), L.tensor_view(dy, self.co), self.geom, self.dwp, self.n_pad, self.kc,
                      split_k=0)
