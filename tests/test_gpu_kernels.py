@@ -286,3 +286,21 @@ def test_clip_gather_scatter(L):
     dv = torch.zeros_like(video)
     L.scatter_clip(out, ts, dv, B, clip, P, NB, 2)
     assert torch.equal(dv[1:4, 2], video[1:4, 2]) and float(dv[:, :2].abs().sum()) == 0.0
+
+
+def test_conv3d_c4_cuda_core_first_discriminator_layer(L):
+    N, D, H, W, C = 2, 5, 16, 12, 3
+    x = torch.zeros(N, D, H, W, 4, device='cuda')
+    x[..., :C] = torch.rand(N, D, H, W, C, device='cuda')
+    w, b, dy = rnd(3, 3, 3, C, 32, seed=1, scale=0.2), rnd(32, seed=2), rnd(N, D, H, W, 32, seed=3)
+    sigma = torch.tensor([1.7], device='cuda')
+    out = torch.zeros(N, D, H, W, 32, device='cuda')
+    L.conv3d_c4_fwd(x, w, sigma, b, out, N, D, H, W, C, 0.1)
+    wb = (w.double() / 1.7).requires_grad_(True)
+    xp = F.pad(x[..., :C].double(), (0, 0, 1, 1, 1, 1, 1, 1))
+    pre = O.conv3d_tf_valid(xp, wb, (1, 1, 1), b.double())
+    close(out, O.lrelu(pre, 0.1), 1e-5, 'conv3d_c4 fwd')
+    (gw,) = torch.autograd.grad(pre, wb, dy.double())
+    g = torch.zeros(27 * C * 32, device='cuda')
+    L.conv3d_c4_wgrad(x, dy, g, N, D, H, W, C)
+    close(g.view(3, 3, 3, C, 32), gw, 2e-5, 'conv3d_c4 wgrad')

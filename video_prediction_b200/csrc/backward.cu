@@ -53,7 +53,8 @@ __global__ void __launch_bounds__(256) inorm_act_bwd_kernel(const float* __restr
                                                             const float* __restrict__ gamma,
                                                             const float* __restrict__ beta,
                                                             const float* __restrict__ stats, int act, float alpha,
-                                                            float* __restrict__ dgamma, float* __restrict__ dbeta) {
+                                                            float* __restrict__ dgamma, float* __restrict__ dbeta, int staged) {
+  extern __shared__ float4 sbuf[];   // staged: [P] x values, then [P] summed upstream gradients
   __shared__ float scratch[8 * 32];
   const int n = blockIdx.y, c0 = blockIdx.x * 4;
   const float* xp = x + static_cast<long long>(n) * P * xs + c0;
@@ -79,6 +80,7 @@ __global__ void __launch_bounds__(256) inorm_act_bwd_kernel(const float* __restr
   for (int p = threadIdx.x; p < P; p += blockDim.x) {
     const float4 xv = *reinterpret_cast<const float4*>(xp + static_cast<long long>(p) * xs);
     const float4 dy = load_dy(p);
+    if (staged) { sbuf[p] = xv; sbuf[P + p] = dy; }
     const float xh[4] = {(xv.x - m[0]) * r[0], (xv.y - m[1]) * r[1], (xv.z - m[2]) * r[2], (xv.w - m[3]) * r[3]};
     const float dv[4] = {dy.x, dy.y, dy.z, dy.w};
 #pragma unroll
@@ -96,8 +98,8 @@ __global__ void __launch_bounds__(256) inorm_act_bwd_kernel(const float* __restr
   const float inv = 1.f / P;
   float* dp = dx + static_cast<long long>(n) * P * dxs + c0;
   for (int p = threadIdx.x; p < P; p += blockDim.x) {
-    const float4 xv = *reinterpret_cast<const float4*>(xp + static_cast<long long>(p) * xs);
-    const float4 dy = load_dy(p);
+    const float4 xv = staged ? sbuf[p] : *reinterpret_cast<const float4*>(xp + static_cast<long long>(p) * xs);
+    const float4 dy = staged ? sbuf[P + p] : load_dy(p);
     const float xh[4] = {(xv.x - m[0]) * r[0], (xv.y - m[1]) * r[1], (xv.z - m[2]) * r[2], (xv.w - m[3]) * r[3]};
     const float dv[4] = {dy.x, dy.y, dy.z, dy.w};
     float o[4];
@@ -120,11 +122,12 @@ __global__ void __launch_bounds__(256) lstm_gates_bwd_kernel(
     const float* __restrict__ stats1, const float* __restrict__ stats2, float forget_bias, SrcList dh_srcs,
     const float* __restrict__ dc_next, float* __restrict__ dpre, float* __restrict__ dc_prev, float* __restrict__ dg1,
     float* __restrict__ db1, float* __restrict__ dg2, float* __restrict__ db2) {
-  extern __shared__ float sm[];  // [16][P] gate grads, [4][P] dcn, [4][P] chat   (float4 granular)
+  extern __shared__ float sm[];  // [16][P] gate grads, [4][P] dcn, [4][P] chat, [16][P] staged pre-activations
   __shared__ float scratch[32 * 32];
   float4* sdg = reinterpret_cast<float4*>(sm);  // [4 gates][P]
   float4* sdc = sdg + 4 * P;
   float4* sch = sdc + P;
+  float4* spre = sch + P;                       // [4 gates][P]: the conv output is read from HBM/L2 exactly once
   const int n = blockIdx.y, c0 = blockIdx.x * 4;
   const float inv = 1.f / P;
   float ga[16], be[16], m1[16], r1[16];
@@ -148,8 +151,14 @@ __global__ void __launch_bounds__(256) lstm_gates_bwd_kernel(
   }
   const float* pp = pre + static_cast<long long>(n) * P * 4 * F;
   const float* cp = c_prev + static_cast<long long>(n) * P * F + c0;
+  for (int p = threadIdx.x; p < P; p += blockDim.x) {
+#pragma unroll
+    for (int g = 0; g < 4; ++g)
+      spre[g * P + p] = *reinterpret_cast<const float4*>(pp + static_cast<long long>(p) * 4 * F + g * F + c0);
+  }
+  __syncthreads();
   auto gate = [&](int p, int g, float* out) {  // normalised + affine gate values of 4 channels
-    const float4 v = *reinterpret_cast<const float4*>(pp + static_cast<long long>(p) * 4 * F + g * F + c0);
+    const float4 v = spre[g * P + p];
     out[0] = (v.x - m1[4 * g]) * r1[4 * g] * ga[4 * g] + be[4 * g];
     out[1] = (v.y - m1[4 * g + 1]) * r1[4 * g + 1] * ga[4 * g + 1] + be[4 * g + 1];
     out[2] = (v.z - m1[4 * g + 2]) * r1[4 * g + 2] * ga[4 * g + 2] + be[4 * g + 2];
@@ -223,7 +232,7 @@ __global__ void __launch_bounds__(256) lstm_gates_bwd_kernel(
     const float* dall[4] = {di, dj, df, dgo};
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
-      const float4 v = *reinterpret_cast<const float4*>(pp + static_cast<long long>(p) * 4 * F + g * F + c0);
+      const float4 v = spre[g * P + p];
       const float xv[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
@@ -244,7 +253,7 @@ __global__ void __launch_bounds__(256) lstm_gates_bwd_kernel(
   for (int p = threadIdx.x; p < P; p += blockDim.x) {
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
-      const float4 v = *reinterpret_cast<const float4*>(pp + static_cast<long long>(p) * 4 * F + g * F + c0);
+      const float4 v = spre[g * P + p];
       const float4 d4 = sdg[g * P + p];
       const float xv[4] = {v.x, v.y, v.z, v.w}, dv[4] = {d4.x, d4.y, d4.z, d4.w};
       float o[4];
@@ -639,8 +648,15 @@ extern "C" int vp_inorm_act_bwd(const float* x, int x_cstride, const float* cons
   if (!x || !dy || !dx || !stats || !gamma || !beta || !dgamma || !dbeta) return set_error("vp_inorm_act_bwd: null pointer");
   if (c % 4 || num_dy < 1 || num_dy > 4) return set_error("vp_inorm_act_bwd: bad channel count / source count");
   dim3 grid(c / 4, n);
-  inorm_act_bwd_kernel<<<grid, 256, 0, as_stream(stream)>>>(x, x_cstride, make_srcs(dy, dy_cstride, num_dy), dx, dx_cstride,
-                                                            positions, c, gamma, beta, stats, act, alpha, dgamma, dbeta);
+  const int staged = positions <= 4096 ? 1 : 0;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(inorm_act_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 4096 * 16);
+    attr_set = true;
+  }
+  inorm_act_bwd_kernel<<<grid, 256, staged ? static_cast<size_t>(positions) * 32 : 0, as_stream(stream)>>>(
+      x, x_cstride, make_srcs(dy, dy_cstride, num_dy), dx, dx_cstride, positions, c, gamma, beta, stats, act, alpha, dgamma, dbeta,
+      staged);
   return check_launch("inorm_act_bwd_kernel");
 }
 
@@ -651,10 +667,10 @@ extern "C" int vp_lstm_gates_bwd(const float* pre, int n, int positions, int fil
                                  float* dgamma2, float* dbeta2, vp_stream_t stream) {
   if (positions > 1024) return set_error("vp_lstm_gates_bwd: plane too large");
   if (filters % 4 || num_dh < 1 || num_dh > 4) return set_error("vp_lstm_gates_bwd: bad filters / source count");
-  const size_t smem = static_cast<size_t>(positions) * 24 * sizeof(float);
+  const size_t smem = static_cast<size_t>(positions) * 40 * sizeof(float);
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(lstm_gates_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 1024 * 24 * 4);
+    cudaFuncSetAttribute(lstm_gates_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 1024 * 40 * 4);
     attr_set = true;
   }
   dim3 grid(filters / 4, n);

@@ -47,10 +47,12 @@ __device__ __forceinline__ void block_sum(float* vals, float* scratch) {
 // mode on the [1,HW,1,N*C] view == per-(n,c) mean / biased variance), eps 1e-6.
 // One CTA per (sample, group of 4 channels); three passes over a plane that lives in L2.
 // ------------------------------------------------------------------------------------------------
+// The (sample, 4-channel) plane is staged once in shared memory (16 B per position): one HBM/L2 read, one write.
 __global__ void __launch_bounds__(256) inorm_act_kernel(const float* __restrict__ x, int xs, float* __restrict__ y,
                                                         int ys, int P, int C, const float* __restrict__ gamma,
                                                         const float* __restrict__ beta, float eps, int act,
-                                                        float alpha, float* __restrict__ stats) {
+                                                        float alpha, float* __restrict__ stats, int staged) {
+  extern __shared__ float4 splane[];
   __shared__ float scratch[4 * 32];
   const int n = blockIdx.y, c0 = blockIdx.x * 4;
   const float* xp = x + static_cast<long long>(n) * P * xs + c0;
@@ -58,6 +60,7 @@ __global__ void __launch_bounds__(256) inorm_act_kernel(const float* __restrict_
   float s[4] = {0.f, 0.f, 0.f, 0.f};
   for (int p = threadIdx.x; p < P; p += blockDim.x) {
     const float4 v = *reinterpret_cast<const float4*>(xp + static_cast<long long>(p) * xs);
+    if (staged) splane[p] = v;
     s[0] += v.x; s[1] += v.y; s[2] += v.z; s[3] += v.w;
   }
   block_sum<4>(s, scratch);
@@ -65,7 +68,7 @@ __global__ void __launch_bounds__(256) inorm_act_kernel(const float* __restrict_
   const float m[4] = {s[0] * inv, s[1] * inv, s[2] * inv, s[3] * inv};
   float q[4] = {0.f, 0.f, 0.f, 0.f};
   for (int p = threadIdx.x; p < P; p += blockDim.x) {
-    const float4 v = *reinterpret_cast<const float4*>(xp + static_cast<long long>(p) * xs);
+    const float4 v = staged ? splane[p] : *reinterpret_cast<const float4*>(xp + static_cast<long long>(p) * xs);
     q[0] += (v.x - m[0]) * (v.x - m[0]); q[1] += (v.y - m[1]) * (v.y - m[1]);
     q[2] += (v.z - m[2]) * (v.z - m[2]); q[3] += (v.w - m[3]) * (v.w - m[3]);
   }
@@ -82,7 +85,7 @@ __global__ void __launch_bounds__(256) inorm_act_kernel(const float* __restrict_
     stats[(static_cast<long long>(n) * C + c0 + threadIdx.x) * 2 + 1] = r[threadIdx.x];
   }
   for (int p = threadIdx.x; p < P; p += blockDim.x) {
-    const float4 v = *reinterpret_cast<const float4*>(xp + static_cast<long long>(p) * xs);
+    const float4 v = staged ? splane[p] : *reinterpret_cast<const float4*>(xp + static_cast<long long>(p) * xs);
     float4 o;
     o.x = act_fn(v.x * g[0] + b[0], act, alpha); o.y = act_fn(v.y * g[1] + b[1], act, alpha);
     o.z = act_fn(v.z * g[2] + b[2], act, alpha); o.w = act_fn(v.w * g[3] + b[3], act, alpha);
@@ -405,8 +408,15 @@ extern "C" int vp_inorm_act(const float* x, int x_cstride, float* y, int y_cstri
   if (!x || !y) return set_error("vp_inorm_act: null pointer");
   if (c % 4 || x_cstride % 4 || y_cstride % 4) return set_error("vp_inorm_act: channels/strides must be multiples of 4");
   dim3 grid(c / 4, n);
-  inorm_act_kernel<<<grid, 256, 0, as_stream(stream)>>>(x, x_cstride, y, y_cstride, positions, c, gamma, beta, eps, act,
-                                                        alpha, stats);
+  const int staged = positions <= 4096 ? 1 : 0;
+  const size_t smem = staged ? static_cast<size_t>(positions) * 16 : 0;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(inorm_act_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4096 * 16);
+    attr_set = true;
+  }
+  inorm_act_kernel<<<grid, 256, smem, as_stream(stream)>>>(x, x_cstride, y, y_cstride, positions, c, gamma, beta, eps, act,
+                                                           alpha, stats, staged);
   return check_launch("inorm_act_kernel");
 }
 

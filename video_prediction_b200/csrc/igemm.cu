@@ -127,25 +127,26 @@ __global__ void __launch_bounds__(192, 2) igemm_fwd_kernel(const __grid_constant
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc_tf32(128, a.bn_tile, 0, 0);
-      int s = 0, ph = 0;
-      for (int it = it0; it < it1; ++it) {
-        mbar_wait(&full_bar[s], ph);
-        tc_fence_after();
+    // whole warp converged; one elected lane issues (cheap uniform-datapath descriptor updates, no waterfall)
+    const uint32_t idesc = make_idesc_tf32(128, a.bn_tile, 0, 0);
+    const uint32_t leader = elect_one_sync();
+    int s = 0, ph = 0;
+    for (int it = it0; it < it1; ++it) {
+      mbar_wait(&full_bar[s], ph);
+      tc_fence_after();
+      if (leader) {
         const uint32_t a_addr = smem_u32(smem + s * stage_bytes);
-        const uint32_t b_addr = a_addr + 16384;
+        const uint64_t ad0 = make_smem_desc(a_addr, 16, 1024, 0);
+        const uint64_t bd0 = make_smem_desc(a_addr + 16384, 16, 1024, 0);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const uint64_t ad = make_smem_desc(a_addr + k * 32, 16, 1024, 0);
-          const uint64_t bd = make_smem_desc(b_addr + k * 32, 16, 1024, 0);
-          umma_tf32(tmem_base, ad, bd, idesc, (it > it0 || k > 0) ? 1u : 0u);
-        }
+        for (int k = 0; k < 4; ++k)
+          umma_tf32(tmem_base, desc_advance(ad0, k * 32), desc_advance(bd0, k * 32), idesc, (it > it0 || k > 0) ? 1u : 0u);
         umma_commit(&empty_bar[s]);
-        if (++s == a.stages) { s = 0; ph ^= 1; }
       }
-      umma_commit(&tmem_full_bar);
+      __syncwarp();
+      if (++s == a.stages) { s = 0; ph ^= 1; }
     }
+    if (leader) umma_commit(&tmem_full_bar);
     __syncwarp();
   } else {
     // ---- epilogue: warp w owns TMEM lanes 32*(w%4)..+31, thread <-> one output pixel
@@ -289,31 +290,32 @@ __global__ void __launch_bounds__(192, 1) igemm_wgrad_kernel(const __grid_consta
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc_tf32(128, ncols, 1, 1);
-      int s = 0, ph = 0;
-      for (int it = it0; it < it1; ++it) {
-        mbar_wait(&full_bar[s], ph);
-        tc_fence_after();
+    const uint32_t idesc = make_idesc_tf32(128, ncols, 1, 1);
+    const uint32_t leader = elect_one_sync();
+    int s = 0, ph = 0;
+    for (int it = it0; it < it1; ++it) {
+      mbar_wait(&full_bar[s], ph);
+      tc_fence_after();
+      if (leader) {
         const uint32_t base = smem_u32(smem + s * stage_bytes);
         for (int t = 0; t < nt; ++t) {
           const uint32_t per = base + (n_shared + t * n_per) * kSub;
-          const uint32_t a_addr = a_shifted ? per : base, b_addr = a_shifted ? base : per;
+          // MN-major tf32: 32-channel x 4-pixel atoms (512 B) with the 32-byte-granular 128B swizzle;
+          // LBO = stride between 32-channel groups, SBO = stride between 4-pixel groups.  M = 128 always reads
+          // four 32-channel groups; groups beyond `na` alias neighbouring data and only feed rows never stored.
+          const uint64_t ad0 = make_smem_desc(a_shifted ? per : base, kSub, 512, 0, 1);
+          const uint64_t bd0 = make_smem_desc(a_shifted ? base : per, kSub, 512, 0, 1);
 #pragma unroll
-          for (int k = 0; k < kWgPix / 8; ++k) {
-            // MN-major tf32: 32-channel x 4-pixel atoms (512 B) with the 32-byte-granular 128B swizzle;
-            // LBO = stride between 32-channel groups, SBO = stride between 4-pixel groups.  M = 128 always reads
-            // four 32-channel groups; groups beyond `na` alias neighbouring data and only feed rows never stored.
-            const uint64_t ad = make_smem_desc(a_addr + k * 1024, kSub, 512, 0, 1);
-            const uint64_t bd = make_smem_desc(b_addr + k * 1024, kSub, 512, 0, 1);
-            umma_tf32(tmem_base + t * ncols, ad, bd, idesc, (it > it0 || k > 0) ? 1u : 0u);
-          }
+          for (int k = 0; k < kWgPix / 8; ++k)
+            umma_tf32(tmem_base + t * ncols, desc_advance(ad0, k * 1024), desc_advance(bd0, k * 1024), idesc,
+                      (it > it0 || k > 0) ? 1u : 0u);
         }
         umma_commit(&empty_bar[s]);
-        if (++s == stages) { s = 0; ph ^= 1; }
       }
-      umma_commit(&tmem_full_bar);
+      __syncwarp();
+      if (++s == stages) { s = 0; ph ^= 1; }
     }
+    if (leader) umma_commit(&tmem_full_bar);
     __syncwarp();
   } else {
     const int q = warp & 3;
@@ -517,8 +519,8 @@ static int conv_igemm_impl(const vp_tensor* in, const vp_conv_geom* g, const flo
     // zero-filled output (only when the output view is dense so that it can be cleared here, and the epilogue is linear)
     split_k = 1;
     const bool dense = out->c == out->cstride;
-    if (dense && act == VP_ACT_NONE && !accumulate && !aux_y && base_ctas < 120 && min_iters >= 24) {
-      split_k = static_cast<int>(std::min<long long>(8, (296 + base_ctas - 1) / base_ctas));
+    if (dense && act == VP_ACT_NONE && !accumulate && !aux_y && base_ctas <= 96 && min_iters >= 24) {
+      split_k = static_cast<int>(std::min<long long>(3, (200 + base_ctas - 1) / base_ctas));   // measured: 3 splits on a 64-CTA grid 168 -> 237 TF/s
       split_k = std::max(1, std::min(split_k, min_iters / 12));
       if (split_k > 1) {
         const size_t bytes = static_cast<size_t>(out->n) * out->d * out->h * out->w * out->cstride * sizeof(float);

@@ -100,36 +100,37 @@ __global__ void __launch_bounds__(224, 1) igemm_flat_kernel(const __grid_constan
         }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc_tf32(128, a.bn_tile, 0, 0);
-      int s = 0, ph = 0;
-      for (int c = c_begin; c < c_end; ++c) {
-        const int li = c - c_begin, buf = li & 1, aph = (li >> 1) & 1;
-        mbar_wait(&a_full[buf], aph);
-        const uint32_t halo_addr = smem_u32(halo[buf]);
-        for (int t = 0; t < a.ntaps; ++t) {
-          mbar_wait(&b_full[s], ph);
-          tc_fence_after();
-          const uint32_t b_addr = smem_u32(bring + s * b_bytes);
-          const uint32_t shift = static_cast<uint32_t>(a.tap_off[t] - a.off_min) * 128u;
+    const uint32_t idesc = make_idesc_tf32(128, a.bn_tile, 0, 0);
+    const uint32_t leader = elect_one_sync();
+    int s = 0, ph = 0;
+    for (int c = c_begin; c < c_end; ++c) {
+      const int li = c - c_begin, buf = li & 1, aph = (li >> 1) & 1;
+      mbar_wait(&a_full[buf], aph);
+      const uint32_t halo_addr = smem_u32(halo[buf]);
+      for (int t = 0; t < a.ntaps; ++t) {
+        mbar_wait(&b_full[s], ph);
+        tc_fence_after();
+        if (leader) {
+          const uint64_t bd0 = make_smem_desc(smem_u32(bring + s * b_bytes), 16, 1024, 0);
+          const uint32_t a0 = halo_addr + static_cast<uint32_t>(a.tap_off[t] - a.off_min) * 128u;
 #pragma unroll
           for (int mt = 0; mt < 2; ++mt) {
-            const uint32_t a_addr = halo_addr + shift + mt * (128u * 128u);
-            const uint32_t bo = a.desc_mode ? ((a_addr >> 7) & 7u) : 0u;
+            const uint32_t a_addr = a0 + mt * (128u * 128u);
+            const uint64_t ad0 = make_smem_desc(a_addr, 16, 1024, a.desc_mode ? ((a_addr >> 7) & 7u) : 0u);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const uint64_t ad = make_smem_desc(a_addr + k * 32, 16, 1024, bo);
-              const uint64_t bd = make_smem_desc(b_addr + k * 32, 16, 1024, 0);
-              umma_tf32(tmem_base + mt * a.bn_tile, ad, bd, idesc, (li > 0 || t > 0 || k > 0) ? 1u : 0u);
-            }
+            for (int k = 0; k < 4; ++k)
+              umma_tf32(tmem_base + mt * a.bn_tile, desc_advance(ad0, k * 32), desc_advance(bd0, k * 32), idesc,
+                        (li > 0 || t > 0 || k > 0) ? 1u : 0u);
           }
           umma_commit(&b_empty[s]);
-          if (++s == a.b_stages) { s = 0; ph ^= 1; }
         }
-        umma_commit(&a_empty[buf]);
+        __syncwarp();
+        if (++s == a.b_stages) { s = 0; ph ^= 1; }
       }
-      umma_commit(&tmem_full_bar);
+      if (leader) umma_commit(&a_empty[buf]);
+      __syncwarp();
     }
+    if (leader) umma_commit(&tmem_full_bar);
     __syncwarp();
   } else {
     // epilogue: two passes of 128 rows; thread <-> one flattened position
@@ -237,6 +238,11 @@ extern "C" int vp_conv_flat(const vp_tensor* in, int valid_h, int valid_w, const
       A.tap_off[A.ntaps] = off; A.tap_wslot[A.ntaps] = r * g->kw + s; ++A.ntaps;
       omin = std::min(omin, off); omax = std::max(omax, off);
     }
+  if (getenv("VP_FLAT_ALIGN8")) {   // timing experiment only (wrong results): are row-unaligned descriptor starts slower?
+    omin = 1 << 30; omax = -(1 << 30);
+    for (int t = 0; t < A.ntaps; ++t) { A.tap_off[t] = (A.tap_off[t] / 8) * 8; omin = std::min(omin, A.tap_off[t]); omax = std::max(omax, A.tap_off[t]); }
+    omin = (omin / 8) * 8 - 8;
+  }
   A.off_min = omin;
   A.halo_rows = 256 + (omax - omin);
   A.nbox = (A.halo_rows + 255) / 256;
