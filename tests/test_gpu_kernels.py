@@ -304,3 +304,16 @@ def test_conv3d_c4_cuda_core_first_discriminator_layer(L):
     g = torch.zeros(27 * C * 32, device='cuda')
     L.conv3d_c4_wgrad(x, dy, g, N, D, H, W, C)
     close(g.view(3, 3, 3, C, 32), gw, 2e-5, 'conv3d_c4 wgrad')
+
+
+@pytest.mark.parametrize('B,H,Cin,Cout,split', [(5, 32, 72, 128, 1), (6, 8, 264, 512, 3), (4, 16, 136, 256, 1)])
+def test_halo_resident_flat_conv_matches_box_engine(L, B, H, Cin, Cout, split):
+    """vp_conv_flat (shifted UMMA descriptors on a resident halo tile) against the fp64 reference."""
+    xs, w = rnd(B, H, H, Cin), rnd(5, 5, Cin, Cout, seed=1, scale=0.03)
+    xp = torch.zeros(B, H + 2, H + 2, Cin, device='cuda')
+    xp[:, :H, :H] = xs
+    wp, n_pad, kc = L.pack_weights(w, (1, 5, 5), Cin, Cout, L.WKIND_PLAIN, L.WLAYOUT_FWD)
+    out = torch.zeros(B, H, H, Cout, device='cuda')
+    L.conv_flat(L.tensor_view(xp, Cin), H, H, L.geom((1, 5, 5), (1, 1, 1), (0, 2, 2), False), wp, n_pad, kc, L.tensor_view(out, Cout),
+                None, L.ACT_NONE, 0.0, split, 0, 0)
+    close(out, O.conv2d_tf(tf32(xs).double(), tf32(w).double(), padding='SAME'), 2e-3, 'flat conv')

@@ -112,10 +112,11 @@ __global__ void __launch_bounds__(192, 2) igemm_fwd_kernel(const __grid_constant
   const uint32_t tmem_base = tmem_base_smem;
 
   if (warp == 0) {
-    if (lane == 0) {
-      int s = 0, ph = 0;
-      for (int it = it0; it < it1; ++it) {
-        mbar_wait(&empty_bar[s], ph ^ 1);
+    const uint32_t leader = elect_one_sync();
+    int s = 0, ph = 0;
+    for (int it = it0; it < it1; ++it) {
+      mbar_wait(&empty_bar[s], ph ^ 1);
+      if (leader) {
         const Tap tp = a.taps[tb + it / a.kc];
         const int kci = it % a.kc;
         uint8_t* As = smem + s * stage_bytes;
@@ -123,8 +124,9 @@ __global__ void __launch_bounds__(192, 2) igemm_fwd_kernel(const __grid_constant
         mbar_expect_tx(&full_bar[s], stage_bytes);
         tma_load_5d(As, &a.amap[tp.map], &full_bar[s], kci * 32, x0 + tp.cw, y0 + tp.ch, d0 + tp.cd, s0);
         tma_load_2d(Bs, &a.bmap, &full_bar[s], kci * 32, tp.wslot * a.n_pad + n0);
-        if (++s == a.stages) { s = 0; ph ^= 1; }
       }
+      __syncwarp();
+      if (++s == a.stages) { s = 0; ph ^= 1; }
     }
   } else if (warp == 1) {
     // whole warp converged; one elected lane issues (cheap uniform-datapath descriptor updates, no waterfall)
@@ -265,16 +267,17 @@ __global__ void __launch_bounds__(192, 1) igemm_wgrad_kernel(const __grid_consta
   const uint32_t tmem_base = tmem_base_smem;
 
   if (warp == 0) {
-    if (lane == 0) {
-      int s = 0, ph = 0;
-      for (int it = it0; it < it1; ++it) {
+    const uint32_t leader = elect_one_sync();
+    int s = 0, ph = 0;
+    for (int it = it0; it < it1; ++it) {
+      mbar_wait(&empty_bar[s], ph ^ 1);
+      if (leader) {
         int mt = it;
         const int tw = mt % a.tiles_w; mt /= a.tiles_w;
         const int th = mt % a.tiles_h; mt /= a.tiles_h;
         const int td = mt % a.tiles_d;
         const int tn = mt / a.tiles_d;
         const int x0 = tw * a.bw, y0 = th * a.bh, d0 = td * a.bd, s0 = tn * a.bn;
-        mbar_wait(&empty_bar[s], ph ^ 1);
         uint8_t* st = smem + s * stage_bytes;
         mbar_expect_tx(&full_bar[s], (n_shared + nt * n_per) * kSub);
         // shared (un-shifted) operand first, then one block per tap of the shifted operand
@@ -286,8 +289,9 @@ __global__ void __launch_bounds__(192, 1) igemm_wgrad_kernel(const __grid_consta
             tma_load_5d(st + (n_shared + t * n_per + i) * kSub, &a.amap[tp.map], &full_bar[s], pt_c0 + 32 * i, x0 + tp.cw,
                         y0 + tp.ch, d0 + tp.cd, s0);
         }
-        if (++s == stages) { s = 0; ph ^= 1; }
       }
+      __syncwarp();
+      if (++s == stages) { s = 0; ph ^= 1; }
     }
   } else if (warp == 1) {
     const uint32_t idesc = make_idesc_tf32(128, ncols, 1, 1);

@@ -77,28 +77,32 @@ __global__ void __launch_bounds__(224, 1) igemm_flat_kernel(const __grid_constan
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
 
-  if (warp == 6) {
-    if (lane == 0) {  // halo producer: one tile per 32-channel chunk, double buffered
-      for (int c = c_begin; c < c_end; ++c) {
-        const int li = c - c_begin, buf = li & 1, ph = (li >> 1) & 1;
-        mbar_wait(&a_empty[buf], ph ^ 1);
+  if (warp == 6) {  // halo producer: one tile per 32-channel chunk, double buffered
+    const uint32_t leader = elect_one_sync();
+    for (int c = c_begin; c < c_end; ++c) {
+      const int li = c - c_begin, buf = li & 1, ph = (li >> 1) & 1;
+      mbar_wait(&a_empty[buf], ph ^ 1);
+      if (leader) {
         mbar_expect_tx(&a_full[buf], static_cast<uint32_t>(a.nbox * a.box_rows) * 128u);
         for (int b = 0; b < a.nbox; ++b)
           tma_load_2d(halo[buf] + static_cast<size_t>(b) * a.box_rows * 128, &a.amap, &a_full[buf], c * 32,
                       q0 + a.off_min + b * a.box_rows);
       }
+      __syncwarp();
     }
-  } else if (warp == 0) {
-    if (lane == 0) {  // weight producer: one [bn_tile x 32] tile per (chunk, tap)
-      int s = 0, ph = 0;
-      for (int c = c_begin; c < c_end; ++c)
-        for (int t = 0; t < a.ntaps; ++t) {
-          mbar_wait(&b_empty[s], ph ^ 1);
+  } else if (warp == 0) {  // weight producer: one [bn_tile x 32] tile per (chunk, tap)
+    const uint32_t leader = elect_one_sync();
+    int s = 0, ph = 0;
+    for (int c = c_begin; c < c_end; ++c)
+      for (int t = 0; t < a.ntaps; ++t) {
+        mbar_wait(&b_empty[s], ph ^ 1);
+        if (leader) {
           mbar_expect_tx(&b_full[s], b_bytes);
           tma_load_2d(bring + s * b_bytes, &a.bmap, &b_full[s], c * 32, a.tap_wslot[t] * a.n_pad + n0);
-          if (++s == a.b_stages) { s = 0; ph ^= 1; }
         }
-    }
+        __syncwarp();
+        if (++s == a.b_stages) { s = 0; ph ^= 1; }
+      }
   } else if (warp == 1) {
     const uint32_t idesc = make_idesc_tf32(128, a.bn_tile, 0, 0);
     const uint32_t leader = elect_one_sync();
