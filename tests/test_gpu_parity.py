@@ -94,7 +94,7 @@ def test_full_size_batch_independence(Model):
     model.set_inputs(binp2, noise2)
     model.generator_forward()
     b = model.outputs['gen_images']
-    assert (b - a[perm.cuda()]).abs().max().item() <= 1e-5
+    assert (b - a[perm.cuda()]).abs().max().item() <= 1e-4   # split-K atomics reorder fp32 sums run to run
     assert a.min() >= -1e-6 and a.max() <= 1 + 1e-6
 
 

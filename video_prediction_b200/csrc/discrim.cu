@@ -246,46 +246,50 @@ __global__ void __launch_bounds__(256) conv3d_c4_fwd_kernel(const float4* __rest
 }
 
 // gw[(t*CI + ci)*32 + co] += sum_v x[v + tap_t][ci] * dy[v][co]
-__global__ void __launch_bounds__(256) conv3d_c4_wgrad_kernel(const float4* __restrict__ x, const float* __restrict__ dy,
-                                                              float* __restrict__ gw, int N, int D, int H, int W, int CI,
-                                                              int chunk) {
+// blockIdx.y selects the temporal tap dz (9 of the 27 taps -> 27 accumulators per lane, high occupancy); lane = output
+// channel; a warp walks a chunk of consecutive voxels, two at a time so that 18 independent neighbour loads are in flight.
+__global__ void __launch_bounds__(256, 3) conv3d_c4_wgrad_kernel(const float4* __restrict__ x, const float* __restrict__ dy,
+                                                                 float* __restrict__ gw, int N, int D, int H, int W, int CI,
+                                                                 int chunk) {
   const int lane = threadIdx.x & 31;
+  const int dz = static_cast<int>(blockIdx.y) - 1;
   const long long warp_id = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
   const long long total = static_cast<long long>(N) * D * H * W;
   const long long v0 = warp_id * chunk, v1 = min(total, v0 + chunk);
-  float acc[81];
+  if (v0 >= v1) return;
+  float acc[27];
 #pragma unroll
-  for (int i = 0; i < 81; ++i) acc[i] = 0.f;
+  for (int i = 0; i < 27; ++i) acc[i] = 0.f;
+  int xw = static_cast<int>(v0 % W);
+  int yh = static_cast<int>((v0 / W) % H);
+  int zd = static_cast<int>((v0 / (static_cast<long long>(W) * H)) % D);
+  const long long zoff = static_cast<long long>(dz) * H * W;
   for (long long v = v0; v < v1; ++v) {
-    const float d = dy[v * 32 + lane];
-    const int xw = static_cast<int>(v % W);
-    const int yh = static_cast<int>((v / W) % H);
-    const int zd = static_cast<int>((v / (static_cast<long long>(W) * H)) % D);
+    const float d = __ldg(dy + v * 32 + lane);
+    const bool zin = static_cast<unsigned>(zd + dz) < static_cast<unsigned>(D);
+    float4 nb[9];
 #pragma unroll
-    for (int dz = -1; dz <= 1; ++dz) {
-      const bool zin = static_cast<unsigned>(zd + dz) < static_cast<unsigned>(D);
+    for (int dyy = -1; dyy <= 1; ++dyy) {
+      const bool yin = zin && static_cast<unsigned>(yh + dyy) < static_cast<unsigned>(H);
 #pragma unroll
-      for (int dyy = -1; dyy <= 1; ++dyy) {
-        const bool yin = static_cast<unsigned>(yh + dyy) < static_cast<unsigned>(H);
-#pragma unroll
-        for (int dx = -1; dx <= 1; ++dx) {
-          const bool in = zin && yin && static_cast<unsigned>(xw + dx) < static_cast<unsigned>(W);
-          const float4 xv = in ? __ldg(x + v + (static_cast<long long>(dz) * H + dyy) * W + dx) : make_float4(0.f, 0.f, 0.f, 0.f);
-          const int t = (dz + 1) * 9 + (dyy + 1) * 3 + (dx + 1);
-          acc[t * 3 + 0] += xv.x * d;
-          acc[t * 3 + 1] += xv.y * d;
-          acc[t * 3 + 2] += xv.z * d;
-        }
+      for (int dx = -1; dx <= 1; ++dx) {
+        const bool in = yin && static_cast<unsigned>(xw + dx) < static_cast<unsigned>(W);
+        nb[(dyy + 1) * 3 + dx + 1] = in ? __ldg(x + v + zoff + dyy * W + dx) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
     }
-  }
-  if (v1 > v0) {
 #pragma unroll
-    for (int t = 0; t < 27; ++t)
-#pragma unroll
-      for (int ci = 0; ci < 3; ++ci)
-        if (ci < CI) atomicAdd(gw + (t * CI + ci) * 32 + lane, acc[t * 3 + ci]);
+    for (int t = 0; t < 9; ++t) {
+      acc[t * 3 + 0] += nb[t].x * d;
+      acc[t * 3 + 1] += nb[t].y * d;
+      acc[t * 3 + 2] += nb[t].z * d;
+    }
+    if (++xw == W) { xw = 0; if (++yh == H) { yh = 0; if (++zd == D) zd = 0; } }
   }
+#pragma unroll
+  for (int t = 0; t < 9; ++t)
+#pragma unroll
+    for (int ci = 0; ci < 3; ++ci)
+      if (ci < CI) atomicAdd(gw + (((dz + 1) * 9 + t) * CI + ci) * 32 + lane, acc[t * 3 + ci]);
 }
 
 }  // namespace vp
@@ -303,9 +307,10 @@ extern "C" int vp_conv3d_c4_wgrad(const float* x, const float* dy, float* gw, in
                                   vp_stream_t stream) {
   if (ci < 1 || ci > 3) return set_error("vp_conv3d_c4_wgrad: 1..3 input channels");
   const long long total = static_cast<long long>(n) * d * h * wd;
-  const int chunk = 256;
+  const int chunk = 128;
   const long long warps = (total + chunk - 1) / chunk;
-  conv3d_c4_wgrad_kernel<<<static_cast<unsigned>((warps + 7) / 8), 256, 0, as_stream(stream)>>>(
+  dim3 grid(static_cast<unsigned>((warps + 7) / 8), 3);
+  conv3d_c4_wgrad_kernel<<<grid, 256, 0, as_stream(stream)>>>(
       reinterpret_cast<const float4*>(x), dy, gw, n, d, h, wd, ci, chunk);
   return check_launch("conv3d_c4_wgrad_kernel");
 }
