@@ -322,8 +322,14 @@ def run_ours(args):
                     roofline=roof, cpu_baseline=cpu, clocks=clocks, losses_finite=finite,
                     losses={k: round(v, 6) for k, v in losses.items() if v})
         print(json.dumps(line))
+        sys.stdout.flush()
     if world > 1:
-        dist.destroy_process_group()
+        # NCCL teardown with a captured graph alive can block; every rank is done, so synchronise and leave
+        torch.cuda.synchronize()
+        dist.barrier()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def log(msg):
@@ -350,6 +356,7 @@ def main():
         run_reference(args)
     else:
         run_ours(args)
+    faulthandler.cancel_dump_traceback_later()
 
 
 if __name__ == '__main__':

@@ -74,24 +74,19 @@ __device__ __forceinline__ float apply_act(float v, int act, float alpha) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// forward / dgrad kernel: one CTA = one (128-pixel tile, BN-column tile, phase, k-split)
+// forward / dgrad kernel.  A CTA owns one (BN-column tile, phase, k-split) and walks the 128-pixel tiles
+// m = blockIdx.x, blockIdx.x + gridDim.x, ... (persistent): the TMA ring keeps streaming across tiles and the two TMEM
+// accumulators alternate, so the epilogue of tile i overlaps the MMAs of tile i+1 and barriers / TMEM are set up once.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(192, 2) igemm_fwd_kernel(const __grid_constant__ IgemmArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  __shared__ uint64_t full_bar[kStagesFwd], empty_bar[kStagesFwd], tmem_full_bar;
+  __shared__ uint64_t full_bar[kStagesFwd], empty_bar[kStagesFwd], tmem_full_bar[2], tmem_empty_bar[2];
   __shared__ uint32_t tmem_base_smem;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t stage_bytes = 16384u + static_cast<uint32_t>(a.bn_tile) * 128u;
-
-  // ---- tile decode
-  int mt = blockIdx.x;
-  const int tw = mt % a.tiles_w; mt /= a.tiles_w;
-  const int th = mt % a.tiles_h; mt /= a.tiles_h;
-  const int td = mt % a.tiles_d;
-  const int tn = mt / a.tiles_d;
-  const int x0 = tw * a.bw, y0 = th * a.bh, d0 = td * a.bd, s0 = tn * a.bn;
+  const int num_mtiles = a.tiles_w * a.tiles_h * a.tiles_d * a.tiles_n;
   const int n0 = blockIdx.y * a.bn_tile;
   const int phase = blockIdx.z / a.splits, split = blockIdx.z % a.splits;
   const int tb = a.phase_begin[phase], te = a.phase_begin[phase + 1];
@@ -102,7 +97,7 @@ __global__ void __launch_bounds__(192, 2) igemm_fwd_kernel(const __grid_constant
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < a.stages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-    mbar_init(&tmem_full_bar, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full_bar[i], 1); mbar_init(&tmem_empty_bar[i], 4); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(&tmem_base_smem, a.tmem_cols);
@@ -114,42 +109,56 @@ __global__ void __launch_bounds__(192, 2) igemm_fwd_kernel(const __grid_constant
   if (warp == 0) {
     const uint32_t leader = elect_one_sync();
     int s = 0, ph = 0;
-    for (int it = it0; it < it1; ++it) {
-      mbar_wait(&empty_bar[s], ph ^ 1);
-      if (leader) {
-        const Tap tp = a.taps[tb + it / a.kc];
-        const int kci = it % a.kc;
-        uint8_t* As = smem + s * stage_bytes;
-        uint8_t* Bs = As + 16384;
-        mbar_expect_tx(&full_bar[s], stage_bytes);
-        tma_load_5d(As, &a.amap[tp.map], &full_bar[s], kci * 32, x0 + tp.cw, y0 + tp.ch, d0 + tp.cd, s0);
-        tma_load_2d(Bs, &a.bmap, &full_bar[s], kci * 32, tp.wslot * a.n_pad + n0);
+    for (int mtile = blockIdx.x; mtile < num_mtiles; mtile += gridDim.x) {
+      int mt = mtile;
+      const int tw = mt % a.tiles_w; mt /= a.tiles_w;
+      const int th = mt % a.tiles_h; mt /= a.tiles_h;
+      const int td = mt % a.tiles_d;
+      const int tn = mt / a.tiles_d;
+      const int x0 = tw * a.bw, y0 = th * a.bh, d0 = td * a.bd, s0 = tn * a.bn;
+      for (int it = it0; it < it1; ++it) {
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        if (leader) {
+          const Tap tp = a.taps[tb + it / a.kc];
+          const int kci = it % a.kc;
+          uint8_t* As = smem + s * stage_bytes;
+          uint8_t* Bs = As + 16384;
+          mbar_expect_tx(&full_bar[s], stage_bytes);
+          tma_load_5d(As, &a.amap[tp.map], &full_bar[s], kci * 32, x0 + tp.cw, y0 + tp.ch, d0 + tp.cd, s0);
+          tma_load_2d(Bs, &a.bmap, &full_bar[s], kci * 32, tp.wslot * a.n_pad + n0);
+        }
+        __syncwarp();
+        if (++s == a.stages) { s = 0; ph ^= 1; }
       }
-      __syncwarp();
-      if (++s == a.stages) { s = 0; ph ^= 1; }
     }
   } else if (warp == 1) {
     // whole warp converged; one elected lane issues (cheap uniform-datapath descriptor updates, no waterfall)
     const uint32_t idesc = make_idesc_tf32(128, a.bn_tile, 0, 0);
     const uint32_t leader = elect_one_sync();
-    int s = 0, ph = 0;
-    for (int it = it0; it < it1; ++it) {
-      mbar_wait(&full_bar[s], ph);
+    int s = 0, ph = 0, ti = 0;
+    for (int mtile = blockIdx.x; mtile < num_mtiles; mtile += gridDim.x, ++ti) {
+      const int acc = ti & 1, use = ti >> 1;
+      mbar_wait(&tmem_empty_bar[acc], (use & 1) ^ 1);   // epilogue has drained this accumulator (first use passes)
       tc_fence_after();
-      if (leader) {
-        const uint32_t a_addr = smem_u32(smem + s * stage_bytes);
-        const uint64_t ad0 = make_smem_desc(a_addr, 16, 1024, 0);
-        const uint64_t bd0 = make_smem_desc(a_addr + 16384, 16, 1024, 0);
+      const uint32_t d_tmem = tmem_base + acc * a.bn_tile;
+      for (int it = it0; it < it1; ++it) {
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        if (leader) {
+          const uint32_t a_addr = smem_u32(smem + s * stage_bytes);
+          const uint64_t ad0 = make_smem_desc(a_addr, 16, 1024, 0);
+          const uint64_t bd0 = make_smem_desc(a_addr + 16384, 16, 1024, 0);
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_tf32(tmem_base, desc_advance(ad0, k * 32), desc_advance(bd0, k * 32), idesc, (it > it0 || k > 0) ? 1u : 0u);
-        umma_commit(&empty_bar[s]);
+          for (int k = 0; k < 4; ++k)
+            umma_tf32(d_tmem, desc_advance(ad0, k * 32), desc_advance(bd0, k * 32), idesc, (it > it0 || k > 0) ? 1u : 0u);
+          umma_commit(&empty_bar[s]);
+        }
+        __syncwarp();
+        if (++s == a.stages) { s = 0; ph ^= 1; }
       }
+      if (leader) umma_commit(&tmem_full_bar[acc]);
       __syncwarp();
-      if (++s == a.stages) { s = 0; ph ^= 1; }
     }
-    if (leader) umma_commit(&tmem_full_bar);
-    __syncwarp();
   } else {
     // ---- epilogue: warp w owns TMEM lanes 32*(w%4)..+31, thread <-> one output pixel
     const int q = warp & 3;
@@ -159,62 +168,76 @@ __global__ void __launch_bounds__(192, 2) igemm_fwd_kernel(const __grid_constant
     const int lh = r % a.bh; r /= a.bh;
     const int ld = r % a.bd;
     const int ln = r / a.bd;
-    const int ow = (x0 + lw) * a.os_w + a.phase_ooff[phase][2];
-    const int oh = (y0 + lh) * a.os_h + a.phase_ooff[phase][1];
-    const int od = (d0 + ld) * a.os_d + a.phase_ooff[phase][0];
-    const int on = s0 + ln;
-    const bool rvalid = (ow < a.out_w) && (oh < a.out_h) && (od < a.out_d) && (on < a.out_n);
-    const long long ooff = on * a.so_n + od * a.so_d + oh * a.so_h + ow * a.so_w;
-    float* orow = a.out + ooff;
     const bool add_bias = (a.bias != nullptr) && (split == 0);
-    mbar_wait(&tmem_full_bar, 0);
-    tc_fence_after();
-    for (int c0 = 0; c0 < a.bn_tile; c0 += 16) {
-      float v[16];
-      __syncwarp();
-      tmem_ld16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c0, v);
-      const int col0 = n0 + c0;
-      if (rvalid && col0 < a.out_c) {
-        if (add_bias) {
+    int ti = 0;
+    for (int mtile = blockIdx.x; mtile < num_mtiles; mtile += gridDim.x, ++ti) {
+      int mt = mtile;
+      const int tw = mt % a.tiles_w; mt /= a.tiles_w;
+      const int th = mt % a.tiles_h; mt /= a.tiles_h;
+      const int td = mt % a.tiles_d;
+      const int tn = mt / a.tiles_d;
+      const int ow = (tw * a.bw + lw) * a.os_w + a.phase_ooff[phase][2];
+      const int oh = (th * a.bh + lh) * a.os_h + a.phase_ooff[phase][1];
+      const int od = (td * a.bd + ld) * a.os_d + a.phase_ooff[phase][0];
+      const int on = tn * a.bn + ln;
+      const bool rvalid = (ow < a.out_w) && (oh < a.out_h) && (od < a.out_d) && (on < a.out_n);
+      const long long ooff = on * a.so_n + od * a.so_d + oh * a.so_h + ow * a.so_w;
+      float* orow = a.out + ooff;
+      const int acc = ti & 1, use = ti >> 1;
+      mbar_wait(&tmem_full_bar[acc], use & 1);
+      tc_fence_after();
+      const uint32_t t_acc = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * a.bn_tile;
+      for (int c0 = 0; c0 < a.bn_tile; c0 += 16) {
+        float v[16];
+        __syncwarp();
+        tmem_ld16(t_acc + c0, v);
+        const int col0 = n0 + c0;
+        if (rvalid && col0 < a.out_c) {
+          if (add_bias) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) if (col0 + j < a.out_c) v[j] += __ldg(a.bias + col0 + j);
-        }
-        if (a.splits > 1) {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) if (col0 + j < a.out_c) atomicAdd(orow + col0 + j, v[j]);
-        } else {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = apply_act(v[j], a.act, a.alpha);
-          if (a.aux_y != nullptr) {   // fused backward of the previous layer's activation: (v + add) * act'(y)
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              if (col0 + j < a.out_c) {
-                const float yv = __ldg(a.aux_y + ooff + col0 + j);
-                float t = v[j];
-                if (a.aux_add != nullptr) t += __ldg(a.aux_add + ooff + col0 + j);
-                if (a.aux_act == VP_ACT_LRELU) t = yv > 0.f ? t : a.alpha * t;
-                else if (a.aux_act == VP_ACT_RELU) t = yv > 0.f ? t : 0.f;
-                else if (a.aux_act == VP_ACT_SIGMOID) t *= yv * (1.f - yv);
-                else if (a.aux_act == VP_ACT_TANH) t *= (1.f - yv * yv);
-                v[j] = t;
-              }
-            }
+            for (int j = 0; j < 16; ++j) if (col0 + j < a.out_c) v[j] += __ldg(a.bias + col0 + j);
           }
-          if (col0 + 16 <= a.out_c) {
-            float4* o4 = reinterpret_cast<float4*>(orow + col0);
+          if (a.splits > 1) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              float4 o = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-              if (a.accumulate) { const float4 e = o4[j]; o.x += e.x; o.y += e.y; o.z += e.z; o.w += e.w; }
-              o4[j] = o;
-            }
+            for (int j = 0; j < 16; ++j) if (col0 + j < a.out_c) atomicAdd(orow + col0 + j, v[j]);
           } else {
 #pragma unroll
-            for (int j = 0; j < 16; ++j)
-              if (col0 + j < a.out_c) orow[col0 + j] = a.accumulate ? orow[col0 + j] + v[j] : v[j];
+            for (int j = 0; j < 16; ++j) v[j] = apply_act(v[j], a.act, a.alpha);
+            if (a.aux_y != nullptr) {   // fused backward of the previous layer's activation: (v + add) * act'(y)
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                if (col0 + j < a.out_c) {
+                  const float yv = __ldg(a.aux_y + ooff + col0 + j);
+                  float t = v[j];
+                  if (a.aux_add != nullptr) t += __ldg(a.aux_add + ooff + col0 + j);
+                  if (a.aux_act == VP_ACT_LRELU) t = yv > 0.f ? t : a.alpha * t;
+                  else if (a.aux_act == VP_ACT_RELU) t = yv > 0.f ? t : 0.f;
+                  else if (a.aux_act == VP_ACT_SIGMOID) t *= yv * (1.f - yv);
+                  else if (a.aux_act == VP_ACT_TANH) t *= (1.f - yv * yv);
+                  v[j] = t;
+                }
+              }
+            }
+            if (col0 + 16 <= a.out_c) {
+              float4* o4 = reinterpret_cast<float4*>(orow + col0);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                float4 o = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                if (a.accumulate) { const float4 e = o4[j]; o.x += e.x; o.y += e.y; o.z += e.z; o.w += e.w; }
+                o4[j] = o;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j)
+                if (col0 + j < a.out_c) orow[col0 + j] = a.accumulate ? orow[col0 + j] + v[j] : v[j];
+            }
           }
         }
       }
+      // this warp is done reading the accumulator: hand it back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
     }
   }
   tc_fence_before();
@@ -513,7 +536,7 @@ static int conv_igemm_impl(const vp_tensor* in, const vp_conv_geom* g, const flo
   }
   if (const char* e = getenv("VP_FWD_BN")) { const int v = atoi(e); if (v >= 16 && v <= 256 && v % 16 == 0 && n_pad % v == 0) A.bn_tile = v; }
   if (A.bn_tile == 0) return set_error("vp_conv_igemm: unsupported n_pad %d", n_pad);
-  A.tmem_cols = next_pow2_cols(A.bn_tile);
+  A.tmem_cols = next_pow2_cols(2 * A.bn_tile);   // two accumulators (double-buffered epilogue)
   int min_iters = 1 << 30;
   for (int p = 0; p < A.num_phases; ++p) min_iters = std::min(min_iters, (A.phase_begin[p + 1] - A.phase_begin[p]) * kc);
   if (min_iters < 1) return set_error("vp_conv_igemm: a phase has no taps");
@@ -565,7 +588,13 @@ static int conv_igemm_impl(const vp_tensor* in, const vp_conv_geom* g, const flo
       return set_error("cudaFuncSetAttribute(igemm_fwd_kernel) failed: %s", cudaGetErrorString(cudaGetLastError()));
     attr_set = true;
   }
-  dim3 grid(A.tiles_w * A.tiles_h * A.tiles_d * A.tiles_n, n_pad / A.bn_tile, A.num_phases * A.splits);
+  // persistent over the pixel tiles: at most ~2 CTAs per SM in total; each CTA strides through the M tiles
+  const int m_tiles = A.tiles_w * A.tiles_h * A.tiles_d * A.tiles_n;
+  const int other = (n_pad / A.bn_tile) * A.num_phases * A.splits;
+  const int resident = (A.stages == 3 ? 2 : 1) * 148;
+  int gx = std::min(m_tiles, std::max(1, resident / other));
+  if (const char* e = getenv("VP_FWD_NONPERSISTENT")) { if (atoi(e)) gx = m_tiles; }
+  dim3 grid(gx, n_pad / A.bn_tile, A.num_phases * A.splits);
   igemm_fwd_kernel<<<grid, 192, smem, static_cast<cudaStream_t>(stream)>>>(A);
   count_launch(1);
   cudaError_t e = cudaGetLastError();
