@@ -48,7 +48,7 @@ struct SrcList {  // up to 4 gradient sources that are summed (each a channel sl
 // instance norm (+act) backward.  x: pre-norm input (dense, stride xs); dy: sum of `srcs`.
 // dx = r*(dxh - mean(dxh) - xh*mean(dxh*xh)),  dxh = dyp*gamma,  dyp = dy*act'(gamma*xh+beta)
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) inorm_act_bwd_kernel(const float* __restrict__ x, int xs, SrcList srcs,
+__global__ void __launch_bounds__(512) inorm_act_bwd_kernel(const float* __restrict__ x, int xs, SrcList srcs,
                                                             float* __restrict__ dx, int dxs, int P, int C,
                                                             const float* __restrict__ gamma,
                                                             const float* __restrict__ beta,
@@ -116,7 +116,7 @@ __global__ void __launch_bounds__(256) inorm_act_bwd_kernel(const float* __restr
 // ------------------------------------------------------------------------------------------------
 // ConvLSTM gates backward (see lstm_gates_fwd_kernel).  One CTA per (sample, 4 state channels).
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) lstm_gates_bwd_kernel(
+__global__ void __launch_bounds__(512) lstm_gates_bwd_kernel(
     const float* __restrict__ pre, int P, int F, const float* __restrict__ c_prev, const float* __restrict__ g1,
     const float* __restrict__ b1, const float* __restrict__ g2, const float* __restrict__ b2,
     const float* __restrict__ stats1, const float* __restrict__ stats2, float forget_bias, SrcList dh_srcs,
@@ -654,7 +654,7 @@ extern "C" int vp_inorm_act_bwd(const float* x, int x_cstride, const float* cons
     cudaFuncSetAttribute(inorm_act_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 4096 * 16);
     attr_set = true;
   }
-  inorm_act_bwd_kernel<<<grid, 256, staged ? static_cast<size_t>(positions) * 32 : 0, as_stream(stream)>>>(
+  inorm_act_bwd_kernel<<<grid, positions >= 2048 ? 512 : 256, staged ? static_cast<size_t>(positions) * 32 : 0, as_stream(stream)>>>(
       x, x_cstride, make_srcs(dy, dy_cstride, num_dy), dx, dx_cstride, positions, c, gamma, beta, stats, act, alpha, dgamma, dbeta,
       staged);
   return check_launch("inorm_act_bwd_kernel");
@@ -674,7 +674,7 @@ extern "C" int vp_lstm_gates_bwd(const float* pre, int n, int positions, int fil
     attr_set = true;
   }
   dim3 grid(filters / 4, n);
-  lstm_gates_bwd_kernel<<<grid, 256, smem, as_stream(stream)>>>(pre, positions, filters, c_prev, gamma1, beta1, gamma2, beta2,
+  lstm_gates_bwd_kernel<<<grid, positions >= 512 ? 512 : 256, smem, as_stream(stream)>>>(pre, positions, filters, c_prev, gamma1, beta1, gamma2, beta2,
                                                                stats1, stats2, forget_bias, make_srcs(dh, dh_cstride, num_dh),
                                                                dc_next, dpre, dc_prev, dgamma1, dbeta1, dgamma2, dbeta2);
   return check_launch("lstm_gates_bwd_kernel");

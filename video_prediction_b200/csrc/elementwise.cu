@@ -48,7 +48,7 @@ __device__ __forceinline__ void block_sum(float* vals, float* scratch) {
 // One CTA per (sample, group of 4 channels); three passes over a plane that lives in L2.
 // ------------------------------------------------------------------------------------------------
 // The (sample, 4-channel) plane is staged once in shared memory (16 B per position): one HBM/L2 read, one write.
-__global__ void __launch_bounds__(256) inorm_act_kernel(const float* __restrict__ x, int xs, float* __restrict__ y,
+__global__ void __launch_bounds__(512) inorm_act_kernel(const float* __restrict__ x, int xs, float* __restrict__ y,
                                                         int ys, int P, int C, const float* __restrict__ gamma,
                                                         const float* __restrict__ beta, float eps, int act,
                                                         float alpha, float* __restrict__ stats, int staged) {
@@ -102,7 +102,7 @@ __global__ void __launch_bounds__(256) inorm_act_kernel(const float* __restrict_
 constexpr int kGatesMaxP = 1024;
 struct GateDst { float* ptr[3]; int stride[3]; int count; };
 
-__global__ void __launch_bounds__(256) lstm_gates_fwd_kernel(const float* __restrict__ pre, int P, int F,
+__global__ void __launch_bounds__(512) lstm_gates_fwd_kernel(const float* __restrict__ pre, int P, int F,
                                                              const float* __restrict__ c_prev,
                                                              const float* __restrict__ g1, const float* __restrict__ b1,
                                                              const float* __restrict__ g2, const float* __restrict__ b2,
@@ -415,7 +415,7 @@ extern "C" int vp_inorm_act(const float* x, int x_cstride, float* y, int y_cstri
     cudaFuncSetAttribute(inorm_act_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4096 * 16);
     attr_set = true;
   }
-  inorm_act_kernel<<<grid, 256, smem, as_stream(stream)>>>(x, x_cstride, y, y_cstride, positions, c, gamma, beta, eps, act,
+  inorm_act_kernel<<<grid, positions >= 2048 ? 512 : 256, smem, as_stream(stream)>>>(x, x_cstride, y, y_cstride, positions, c, gamma, beta, eps, act,
                                                            alpha, stats, staged);
   return check_launch("inorm_act_kernel");
 }
@@ -437,7 +437,7 @@ extern "C" int vp_lstm_gates_fwd(const float* pre, int n, int positions, int fil
     attr_set = true;
   }
   dim3 grid(filters / 4, n);
-  lstm_gates_fwd_kernel<<<grid, 256, smem, as_stream(stream)>>>(pre, positions, filters, c_prev, gamma1, beta1, gamma2, beta2,
+  lstm_gates_fwd_kernel<<<grid, positions >= 512 ? 512 : 256, smem, as_stream(stream)>>>(pre, positions, filters, c_prev, gamma1, beta1, gamma2, beta2,
                                                                forget_bias, eps, c_new, d, stats1, stats2);
   return check_launch("lstm_gates_fwd_kernel");
 }
