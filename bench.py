@@ -200,7 +200,8 @@ def run_ours(args):
     # ---------------- e2e: public API with host inputs (H2D + D2H inside the timed region)
     batches = [synthetic_batch(B, seed=1000 * rank + i) for i in range(4)]
     h2d = sum(v.numel() * 4 for v in batches[0].values())
-    for i in range(max(3, args.warmup)):
+    model.use_cuda_graph = not args.no_graph
+    for i in range(max(3, args.warmup) + 1):
         model.train_step(batches[i % 4], allreduce=allreduce)
         model.losses()
     torch.cuda.synchronize()
@@ -218,44 +219,23 @@ def run_ours(args):
     torch.cuda.synchronize()
     e2e_ms = max(e0.elapsed_time(e1), (time.time() - t0) * 1e3) / k_e2e
     d2h = model.loss_vals.numel() * 4
-    log('e2e %.2f ms/step; capturing CUDA graph' % e2e_ms)
+    log('e2e %.2f ms/step (cuda graph inside train_step: %s)' % (e2e_ms, model._graph is not None))
 
     # ---------------- value: HBM-resident inputs, whole step as one CUDA graph
-    use_graph = not args.no_graph
-    graph = None
+    graph = model._graph
     launches_per_step = None
     model.set_inputs(batches[0])
-    if use_graph:
-        try:
-            side = torch.cuda.Stream()
-            side.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(side):
-                model.train_step(allreduce=allreduce)         # warm-up on a side stream
-            torch.cuda.current_stream().wait_stream(side)
-            torch.cuda.synchronize()
-            graph = torch.cuda.CUDAGraph()
-            c0 = L.launch_count()
-            model.stage_step()
-            with torch.cuda.graph(graph):
-                model.train_step(allreduce=allreduce, staged=True)
-            model.global_step += 1
-            launches_per_step = L.launch_count() - c0
-        except Exception as ex:     # noqa: BLE001
-            sys.stderr.write('CUDA graph capture failed (%s); timing eager launches instead\n' % ex)
-            graph = None
-            torch.cuda.synchronize()
+    if graph is None:
+        model.use_cuda_graph = False
 
     def one_step():
-        if graph is not None:
-            model.stage_step()
-            graph.replay()
-            model.global_step += 1
-        else:
-            model.train_step(allreduce=allreduce)
-    if launches_per_step is None:
-        c0 = L.launch_count()
-        model.train_step(allreduce=allreduce)
-        launches_per_step = L.launch_count() - c0
+        model.train_step(allreduce=allreduce)       # inputs already resident; replays the captured graph
+    # launches per step: counted on one eager execution of the same device step
+    c0 = L.launch_count()
+    model.stage_step()
+    model._step_device(allreduce)
+    model.global_step += 1
+    launches_per_step = L.launch_count() - c0
     log('graph=%s launches/step=%s; warm-up' % (graph is not None, launches_per_step))
     for _ in range(max(3, args.warmup)):
         one_step()

@@ -134,6 +134,7 @@ class SAVPVideoPredictionModel(TrainMixin, VideoPredictionModel):
         self.grads = None
         self.built = False
         self.world_size = 1
+        self.use_cuda_graph = False      # train_step(): capture the device part of the step once, then replay it
         self._pending_params = None
         self.g_adam_t = self.d_adam_t = 0
         self.dnets = OrderedDict()

@@ -240,6 +240,7 @@ class TrainMixin(object):
                 if i > 0:
                     G['deact%d' % i] = torch.zeros_like(Bf['eact%d' % i])
         self.loss_vals = z(len(LOSS_SLOTS))
+        self._graph, self._eager_steps = None, 0
         self.step_scalars = z(4)      # [lr_t(D), lr_t(G), kl_scale, -]  refreshed from the host every step
         self._scal_host = torch.zeros(4, dtype=torch.float32).pin_memory()
         for c in self.convs:
@@ -511,7 +512,26 @@ class TrainMixin(object):
             self.set_inputs(inputs, noise, sampling)
         if not staged:
             self.stage_step(noise)
-        self._step_device(allreduce)
+        if self.use_cuda_graph and not staged and self._eager_steps >= 1:
+            # the device part of the step (~1.5 k launches, no host sync) is captured once and replayed
+            if self._graph is None:
+                try:
+                    torch.cuda.synchronize()
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g):
+                        self._step_device(allreduce)
+                    self._graph = g
+                except Exception as ex:      # noqa: BLE001  (e.g. a collective that cannot be captured): stay eager
+                    import sys
+                    sys.stderr.write('CUDA graph capture failed (%s); continuing with eager launches\n' % ex)
+                    self.use_cuda_graph, self._graph = False, None
+                    torch.cuda.synchronize()
+                    self._step_device(allreduce)
+            else:
+                self._graph.replay()
+        else:
+            self._step_device(allreduce)
+            self._eager_steps += 1
         if not staged:
             self.global_step += 1
 
