@@ -67,6 +67,14 @@ def test_kth_shape_single_channel_nz32(Model):
     assert err <= 1e-3, err
 
 
+def test_cfg4_shape_128x128_generator_matches_oracle(Model):
+    # BASELINE configs[3] shape: 128x128x3 (4 encoder / 4 decoder levels, savp_model.py:198-210), shortened sequence
+    model, ref, _ = _run_forward(Model, dict(context_frames=2, sequence_length=5, nz=8), 1, (128, 128, 3))
+    for k in ('gen_images', 'gen_images_enc'):
+        err = (model.outputs[k].cpu() - ref[k].permute(1, 0, 2, 3, 4)).abs().max().item()
+        assert err <= 1e-3, (k, err)
+
+
 def test_golden_vectors_small_config(Model):
     g = np.load(os.path.join(GOLD, 'oracle_small.npz'))
     hk = dict(context_frames=2, sequence_length=5, nz=4, ngf=8, nef=8, ndf=8, clip_length=3)
