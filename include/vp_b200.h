@@ -154,6 +154,13 @@ int vp_cdna_kernel_norm(const float* raw, float* out, int b, int kh, int kw, int
  * layers[(n*h*w+p)*layers_cstride + 4*l]. */
 int vp_cdna_apply(const float* image, const float* first_image, const float* kernels, float* layers,
                   int layers_cstride, int n, int h, int w, int kh, int kw, int nk, vp_stream_t stream);
+/* flow_ops.image_warp (flow_ops.py:4-79; transformation='flow', savp_model.py:955-965): backward bilinear warp with
+ * the neighbour indices clipped to the image; flow [n][h][w][2] = (x, y) displacement.  bwd: dim += (atomic, may be
+ * NULL), dflow overwritten (may be NULL). */
+int vp_image_warp_fwd(const float* im, int im_cstride, const float* flow, float* out, int out_cstride, int n, int h, int w,
+                      int c, vp_stream_t stream);
+int vp_image_warp_bwd(const float* im, int im_cstride, const float* flow, const float* dout, int dout_cstride, float* dim,
+                      int dim_cstride, float* dflow, int n, int h, int w, int c, vp_stream_t stream);
 /* masks = softmax(logits) (savp_model.py:634); gen_image = sum_l layer_l * mask_l (:645-646). */
 int vp_composite(const float* logits, int logits_cstride, const float* layers, int layers_cstride, float* masks,
                  int masks_cstride, float* gen_image, long long positions, int num_layers, vp_stream_t stream);

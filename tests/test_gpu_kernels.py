@@ -317,3 +317,23 @@ def test_halo_resident_flat_conv_matches_box_engine(L, B, H, Cin, Cout, split):
     L.conv_flat(L.tensor_view(xp, Cin), H, H, L.geom((1, 5, 5), (1, 1, 1), (0, 2, 2), False), wp, n_pad, kc, L.tensor_view(out, Cout),
                 None, L.ACT_NONE, 0.0, split, 0, 0)
     close(out, O.conv2d_tf(tf32(xs).double(), tf32(w).double(), padding='SAME'), 2e-3, 'flat conv')
+
+
+def test_image_warp_fwd_bwd(L):
+    N, H, W, C = 2, 9, 11, 3
+    im = torch.zeros(N, H, W, 4, device='cuda')
+    im[..., :C] = torch.rand(N, H, W, C, device='cuda')
+    flow = rnd(N, H, W, 2, seed=1) * 2.5 + 0.37          # non-integer displacements, some leaving the image
+    out = torch.zeros(N, H, W, 4, device='cuda')
+    L.image_warp_fwd(im, 4, flow, out, 4, N, H, W, C)
+    imd = im[..., :C].double().requires_grad_(True)
+    fd = flow.double().requires_grad_(True)
+    ref = O.image_warp(imd, fd)
+    close(out[..., :C], ref, 1e-5, 'image_warp fwd')
+    dout = torch.zeros(N, H, W, 4, device='cuda')
+    dout[..., :C] = rnd(N, H, W, C, seed=2)
+    g_im, g_fl = torch.autograd.grad(ref, (imd, fd), dout[..., :C].double())
+    dim, dfl = torch.zeros(N, H, W, 4, device='cuda'), torch.zeros(N, H, W, 2, device='cuda')
+    L.image_warp_bwd(im, 4, flow, dout, 4, dim, 4, dfl, N, H, W, C)
+    close(dim[..., :C], g_im, 2e-5, 'image_warp dim')
+    close(dfl, g_fl, 2e-5, 'image_warp dflow')

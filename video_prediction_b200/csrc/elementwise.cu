@@ -522,3 +522,77 @@ extern "C" int vp_composite(const float* logits, int logits_cstride, const float
                                                                            positions, num_layers);
   return check_launch("composite_kernel");
 }
+
+// ------------------------------------------------------------------------------------------------
+// flow_ops.image_warp (flow_ops.py:4-79): backward bilinear warp.  x = floor(flow_x), weights from the fractional
+// part, the four neighbour indices are clipped to the image (tf.clip_by_value, :53-56), flow[...,0] = x, [...,1] = y.
+// im / out: [N,H,W,cs] (C valid channels), flow: [N,H,W,2].  HBM-bound gather: one thread per (pixel, channel).
+// ------------------------------------------------------------------------------------------------
+namespace vp {
+__global__ void image_warp_fwd_kernel(const float* __restrict__ im, int ims, const float* __restrict__ flow,
+                                      float* __restrict__ out, int os, int N, int H, int W, int C) {
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long total = static_cast<long long>(N) * H * W * C;
+  if (idx >= total) return;
+  const int c = static_cast<int>(idx % C);
+  const long long p = idx / C;
+  const int x = static_cast<int>(p % W), y = static_cast<int>((p / W) % H);
+  const long long n = p / (static_cast<long long>(W) * H);
+  const float fx = flow[p * 2], fy = flow[p * 2 + 1];
+  const float flx = floorf(fx), fly = floorf(fy);
+  const float xw = fx - flx, yw = fy - fly;
+  const int x0 = min(max(x + static_cast<int>(flx), 0), W - 1), x1 = min(max(x + static_cast<int>(flx) + 1, 0), W - 1);
+  const int y0 = min(max(y + static_cast<int>(fly), 0), H - 1), y1 = min(max(y + static_cast<int>(fly) + 1, 0), H - 1);
+  const float* b = im + n * H * W * ims + c;
+  const float Ia = b[(static_cast<long long>(y0) * W + x0) * ims], Ib = b[(static_cast<long long>(y1) * W + x0) * ims];
+  const float Ic = b[(static_cast<long long>(y0) * W + x1) * ims], Id = b[(static_cast<long long>(y1) * W + x1) * ims];
+  out[p * os + c] = (1.f - xw) * (1.f - yw) * Ia + (1.f - xw) * yw * Ib + xw * (1.f - yw) * Ic + xw * yw * Id;
+}
+// dim (+= atomics, zero-filled by the caller) and dflow (overwritten; floor has zero gradient, so only the weights carry it)
+__global__ void image_warp_bwd_kernel(const float* __restrict__ im, int ims, const float* __restrict__ flow,
+                                      const float* __restrict__ dout, int dos, float* __restrict__ dim, int dis,
+                                      float* __restrict__ dflow, int N, int H, int W, int C) {
+  const long long p = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long total = static_cast<long long>(N) * H * W;
+  if (p >= total) return;
+  const int x = static_cast<int>(p % W), y = static_cast<int>((p / W) % H);
+  const long long n = p / (static_cast<long long>(W) * H);
+  const float fx = flow[p * 2], fy = flow[p * 2 + 1];
+  const float flx = floorf(fx), fly = floorf(fy);
+  const float xw = fx - flx, yw = fy - fly;
+  const int x0 = min(max(x + static_cast<int>(flx), 0), W - 1), x1 = min(max(x + static_cast<int>(flx) + 1, 0), W - 1);
+  const int y0 = min(max(y + static_cast<int>(fly), 0), H - 1), y1 = min(max(y + static_cast<int>(fly) + 1, 0), H - 1);
+  const long long base = n * H * W;
+  const long long ia = (base + static_cast<long long>(y0) * W + x0), ib = (base + static_cast<long long>(y1) * W + x0);
+  const long long ic = (base + static_cast<long long>(y0) * W + x1), id = (base + static_cast<long long>(y1) * W + x1);
+  float gx = 0.f, gy = 0.f;
+  for (int c = 0; c < C; ++c) {
+    const float d = dout[p * dos + c];
+    const float Ia = im[ia * ims + c], Ib = im[ib * ims + c], Ic = im[ic * ims + c], Id = im[id * ims + c];
+    gx += d * ((1.f - yw) * (Ic - Ia) + yw * (Id - Ib));
+    gy += d * ((1.f - xw) * (Ib - Ia) + xw * (Id - Ic));
+    if (dim) {
+      atomicAdd(dim + ia * dis + c, d * (1.f - xw) * (1.f - yw));
+      atomicAdd(dim + ib * dis + c, d * (1.f - xw) * yw);
+      atomicAdd(dim + ic * dis + c, d * xw * (1.f - yw));
+      atomicAdd(dim + id * dis + c, d * xw * yw);
+    }
+  }
+  if (dflow) { dflow[p * 2] = gx; dflow[p * 2 + 1] = gy; }
+}
+}  // namespace vp
+
+extern "C" int vp_image_warp_fwd(const float* im, int im_cstride, const float* flow, float* out, int out_cstride, int n, int h,
+                                 int w, int c, vp_stream_t stream) {
+  const long long total = static_cast<long long>(n) * h * w * c;
+  vp::image_warp_fwd_kernel<<<vp::grid_for(total, 256), 256, 0, vp::as_stream(stream)>>>(im, im_cstride, flow, out, out_cstride, n, h, w, c);
+  return vp::check_launch("image_warp_fwd_kernel");
+}
+
+extern "C" int vp_image_warp_bwd(const float* im, int im_cstride, const float* flow, const float* dout, int dout_cstride,
+                                 float* dim, int dim_cstride, float* dflow, int n, int h, int w, int c, vp_stream_t stream) {
+  const long long total = static_cast<long long>(n) * h * w;
+  vp::image_warp_bwd_kernel<<<vp::grid_for(total, 256), 256, 0, vp::as_stream(stream)>>>(im, im_cstride, flow, dout, dout_cstride, dim,
+                                                                                          dim_cstride, dflow, n, h, w, c);
+  return vp::check_launch("image_warp_bwd_kernel");
+}

@@ -28,6 +28,7 @@ namespace vp {
 constexpr int kMaxTaps = 128;
 constexpr int kMaxMaps = 8;
 constexpr int kStagesFwd = 4;
+constexpr int kMaxStagesFwd = 6;
 constexpr int kStagesWg = 3;
 constexpr int kWgPix = 64;  // pixels (GEMM-K) per wgrad pipeline stage
 
@@ -81,7 +82,7 @@ __device__ __forceinline__ float apply_act(float v, int act, float alpha) {
 __global__ void __launch_bounds__(192, 2) igemm_fwd_kernel(const __grid_constant__ IgemmArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  __shared__ uint64_t full_bar[kStagesFwd], empty_bar[kStagesFwd], tmem_full_bar[2], tmem_empty_bar[2];
+  __shared__ uint64_t full_bar[kMaxStagesFwd], empty_bar[kMaxStagesFwd], tmem_full_bar[2], tmem_empty_bar[2];
   __shared__ uint32_t tmem_base_smem;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -581,10 +582,11 @@ static int conv_igemm_impl(const vp_tensor* in, const vp_conv_geom* g, const flo
   // more than one CTA per SM's worth of work: 3 stages (<= 97 KB) so two CTAs share an SM and overlap prologue/epilogue
   // with the other's main loop; a single partial wave keeps the deeper 4-stage pipeline
   A.stages = (A.bn_tile <= 128 && n_ctas > 148) ? 3 : kStagesFwd;
+  if (const char* e = getenv("VP_FWD_STAGES")) { const int v = atoi(e); if (v >= 2 && v <= kMaxStagesFwd && static_cast<size_t>(v) * (16384 + A.bn_tile * 128) + 1024 <= 226 * 1024) A.stages = v; }
   const size_t smem = static_cast<size_t>(A.stages) * (16384 + A.bn_tile * 128) + 1024;
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(igemm_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kStagesFwd * (16384 + 256 * 128) + 1024) != cudaSuccess)
+    if (cudaFuncSetAttribute(igemm_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024) != cudaSuccess)
       return set_error("cudaFuncSetAttribute(igemm_fwd_kernel) failed: %s", cudaGetErrorString(cudaGetLastError()));
     attr_set = true;
   }

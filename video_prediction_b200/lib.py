@@ -331,3 +331,11 @@ def conv3d_c4_fwd(x, w, inv_scale, bias, out, n, d, h, wd, ci, alpha):
 
 def conv3d_c4_wgrad(x, dy, gw, n, d, h, wd, ci):
     check(lib().vp_conv3d_c4_wgrad(ptr(x), ptr(dy), ptr(gw), n, d, h, wd, ci, stream_ptr()))
+
+
+def image_warp_fwd(im, im_cs, flow, out, out_cs, n, h, w, c):
+    check(lib().vp_image_warp_fwd(ptr(im), im_cs, ptr(flow), ptr(out), out_cs, n, h, w, c, stream_ptr()))
+
+
+def image_warp_bwd(im, im_cs, flow, dout, dout_cs, dim, dim_cs, dflow, n, h, w, c):
+    check(lib().vp_image_warp_bwd(ptr(im), im_cs, ptr(flow), ptr(dout), dout_cs, ptr(dim), dim_cs, ptr(dflow), n, h, w, c, stream_ptr()))
