@@ -50,6 +50,8 @@ enum { VP_WKIND_PLAIN = 0, VP_WKIND_POOLED = 1, VP_WKIND_UPSAMPLED = 2 };
 enum { VP_WLAYOUT_FWD = 0, VP_WLAYOUT_DGRAD = 1 };
 
 const char* vp_last_error(void);
+/* debug: per-CTA globaltimer stamps of the last vp_conv_igemm launch made with VP_FWD_TRACE=1 (8 x u64 per CTA) */
+int vp_debug_read_trace(unsigned long long* host, int n_ctas);
 int vp_version(void);
 
 /* ---- tensor-core implicit-GEMM convolution (tcgen05 / TMEM / TMA) ------------------------------

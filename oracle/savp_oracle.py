@@ -242,13 +242,13 @@ def image_warp(im, flow):
     fx = fl[..., 0].long()
     fy = fl[..., 1].long()
     xw, yw = wgt[..., 0:1], wgt[..., 1:2]
-    gx = torch.arange(w).view(1, 1, w).expand(b, h, w)
-    gy = torch.arange(h).view(1, h, 1).expand(b, h, w)
+    gx = torch.arange(w, device=im.device).view(1, 1, w).expand(b, h, w)
+    gy = torch.arange(h, device=im.device).view(1, h, 1).expand(b, h, w)
     x0 = (gx + fx).clamp(0, w - 1)
     x1 = (gx + fx + 1).clamp(0, w - 1)
     y0 = (gy + fy).clamp(0, h - 1)
     y1 = (gy + fy + 1).clamp(0, h - 1)
-    bi = torch.arange(b).view(b, 1, 1).expand(b, h, w)
+    bi = torch.arange(b, device=im.device).view(b, 1, 1).expand(b, h, w)
     Ia, Ib, Ic, Id = im[bi, y0, x0], im[bi, y1, x0], im[bi, y0, x1], im[bi, y1, x1]
     return (1 - xw) * (1 - yw) * Ia + (1 - xw) * yw * Ib + xw * (1 - yw) * Ic + xw * yw * Id
 

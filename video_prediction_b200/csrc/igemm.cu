@@ -12,7 +12,7 @@
 // s_d*s_h*s_w "parity" sub-lattices of the input (one tensor map each); transposed convolutions
 // (upsample_conv2d forward, dgrad of strided convs) are split into output phases.
 //
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA
+// Warp roles (224 threads; wgrad 192): warp 0 (+ warp 6 in the forward kernel: weights) = TMA producer, warp 1 = TMEM allocator + single-thread MMA
 // issuer, warps 2..5 = epilogue (TMEM -> registers -> bias/activation -> global).
 #include <cstdio>
 #include <cstdlib>
@@ -60,9 +60,27 @@ struct alignas(64) IgemmArgs {
   // wgrad only
   int32_t rows_from_shifted, m_tiles, n_tiles, kpad;
   int32_t tap_group, num_taps, rows_valid, wg_stages, stages;
+  int32_t ksub;          // 32-channel k-chunks per pipeline stage (1 or 2): two chunks halve the per-MMA cost of the issue loops
+  int32_t dbg_trace;
+  int32_t dbg_skip;      // timing experiments only (VP_FWD_SKIP): 1 = no activation loads, 2 = no weight loads
   uint32_t wg_stage_bytes;
   Tap taps[kMaxTaps];
 };
+
+// Optional per-CTA timeline (VP_FWD_TRACE=1; read back with vp_debug_read_trace): 8 globaltimer stamps per CTA.
+__device__ unsigned long long g_trace[16 * 2048];
+__device__ __forceinline__ unsigned long long gtimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define VP_TRACE(slot)                                                                                       \
+  do {                                                                                                       \
+    if (DBG && a.dbg_trace) {                                                                                \
+      const int cta_ = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);                        \
+      if (cta_ < 2048) g_trace[cta_ * 16 + (slot)] = gtimer();                                                \
+    }                                                                                                        \
+  } while (0)
 
 __device__ __forceinline__ float apply_act(float v, int act, float alpha) {
   switch (act) {
@@ -79,14 +97,16 @@ __device__ __forceinline__ float apply_act(float v, int act, float alpha) {
 // m = blockIdx.x, blockIdx.x + gridDim.x, ... (persistent): the TMA ring keeps streaming across tiles and the two TMEM
 // accumulators alternate, so the epilogue of tile i overlaps the MMAs of tile i+1 and barriers / TMEM are set up once.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(192, 2) igemm_fwd_kernel(const __grid_constant__ IgemmArgs a) {
+template <int KSUB, bool DBG>
+__global__ void __launch_bounds__(224, KSUB == 1 ? 2 : 1) igemm_fwd_kernel(const __grid_constant__ IgemmArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   __shared__ uint64_t full_bar[kMaxStagesFwd], empty_bar[kMaxStagesFwd], tmem_full_bar[2], tmem_empty_bar[2];
   __shared__ uint32_t tmem_base_smem;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t stage_bytes = 16384u + static_cast<uint32_t>(a.bn_tile) * 128u;
+  const uint32_t sub_bytes = 16384u + static_cast<uint32_t>(a.bn_tile) * 128u;
+  const uint32_t stage_bytes = sub_bytes * static_cast<uint32_t>(KSUB);
   const int num_mtiles = a.tiles_w * a.tiles_h * a.tiles_d * a.tiles_n;
   const int n0 = blockIdx.y * a.bn_tile;
   const int phase = blockIdx.z / a.splits, split = blockIdx.z % a.splits;
@@ -95,9 +115,13 @@ __global__ void __launch_bounds__(192, 2) igemm_fwd_kernel(const __grid_constant
   const int it0 = static_cast<int>(static_cast<long long>(total) * split / a.splits);
   const int it1 = static_cast<int>(static_cast<long long>(total) * (split + 1) / a.splits);
   if (it1 <= it0) return;
+  if (threadIdx.x == 0) {
+    VP_TRACE(0);
+    if (DBG && a.dbg_trace) { unsigned smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid)); g_trace[(blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z)) % 2048 * 16 + 7] = smid; }
+  }
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < a.stages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    for (int i = 0; i < a.stages; ++i) { mbar_init(&full_bar[i], 2); mbar_init(&empty_bar[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full_bar[i], 1); mbar_init(&tmem_empty_bar[i], 4); }
     fence_barrier_init();
   }
@@ -107,60 +131,138 @@ __global__ void __launch_bounds__(192, 2) igemm_fwd_kernel(const __grid_constant
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
 
+  // ---- Issue loops.  Each runs in ONE elected thread and is a serial latency chain (~5 cycles per instruction), while
+  // a stage of four N<=128 MMAs covers only 256 tensor-pipe cycles: the loops are kept to a few dozen instructions
+  // (no divisions, byte offsets carried instead of indices, slow paths out of line, debug code compiled out), the
+  // activation and weight streams have their own issuers, and narrow tiles carry KSUB = 2 k-chunks per stage.
+  const uint32_t full0 = smem_u32(&full_bar[0]), empty0 = smem_u32(&empty_bar[0]);
+  const uint32_t ring_end = static_cast<uint32_t>(a.stages) * 8u;
   if (warp == 0) {
-    const uint32_t leader = elect_one_sync();
-    int s = 0, ph = 0;
-    for (int mtile = blockIdx.x; mtile < num_mtiles; mtile += gridDim.x) {
-      int mt = mtile;
-      const int tw = mt % a.tiles_w; mt /= a.tiles_w;
-      const int th = mt % a.tiles_h; mt /= a.tiles_h;
-      const int td = mt % a.tiles_d;
-      const int tn = mt / a.tiles_d;
-      const int x0 = tw * a.bw, y0 = th * a.bh, d0 = td * a.bd, s0 = tn * a.bn;
-      for (int it = it0; it < it1; ++it) {
-        mbar_wait(&empty_bar[s], ph ^ 1);
-        if (leader) {
-          const Tap tp = a.taps[tb + it / a.kc];
-          const int kci = it % a.kc;
-          uint8_t* As = smem + s * stage_bytes;
-          uint8_t* Bs = As + 16384;
-          mbar_expect_tx(&full_bar[s], stage_bytes);
-          tma_load_5d(As, &a.amap[tp.map], &full_bar[s], kci * 32, x0 + tp.cw, y0 + tp.ch, d0 + tp.cd, s0);
-          tma_load_2d(Bs, &a.bmap, &full_bar[s], kci * 32, tp.wslot * a.n_pad + n0);
-        }
-        __syncwarp();
-        if (++s == a.stages) { s = 0; ph ^= 1; }
-      }
-    }
-  } else if (warp == 1) {
-    // whole warp converged; one elected lane issues (cheap uniform-datapath descriptor updates, no waterfall)
-    const uint32_t idesc = make_idesc_tf32(128, a.bn_tile, 0, 0);
-    const uint32_t leader = elect_one_sync();
-    int s = 0, ph = 0, ti = 0;
-    for (int mtile = blockIdx.x; mtile < num_mtiles; mtile += gridDim.x, ++ti) {
-      const int acc = ti & 1, use = ti >> 1;
-      mbar_wait(&tmem_empty_bar[acc], (use & 1) ^ 1);   // epilogue has drained this accumulator (first use passes)
-      tc_fence_after();
-      const uint32_t d_tmem = tmem_base + acc * a.bn_tile;
-      for (int it = it0; it < it1; ++it) {
-        mbar_wait(&full_bar[s], ph);
-        tc_fence_after();
-        if (leader) {
-          const uint32_t a_addr = smem_u32(smem + s * stage_bytes);
-          const uint64_t ad0 = make_smem_desc(a_addr, 16, 1024, 0);
-          const uint64_t bd0 = make_smem_desc(a_addr + 16384, 16, 1024, 0);
+    // activation boxes: one 5-D TMA per k-chunk; the tap is a coordinate shift, padding is the OOB zero fill
+    if (elect_one_sync() && !(DBG && (a.dbg_skip & 8))) {
+      const bool load = !(DBG && (a.dbg_skip & 1));
+      const uint32_t smem0 = smem_u32(smem);
+      uint32_t s_off = 0, b_off = 0, ph = 0;
+      const int tap0 = it0 / a.kc, c00 = (it0 - tap0 * a.kc) * 32, c0_end = a.kc * 32;
+#pragma unroll 1
+      for (int mtile = blockIdx.x; mtile < num_mtiles; mtile += gridDim.x) {
+        int mt = mtile;
+        const int tw = mt % a.tiles_w; mt /= a.tiles_w;
+        const int th = mt % a.tiles_h; mt /= a.tiles_h;
+        const int td = mt % a.tiles_d;
+        const int tn = mt / a.tiles_d;
+        const int x0 = tw * a.bw, y0 = th * a.bh, d0 = td * a.bd, s0 = tn * a.bn;
+        int tap = tb + tap0, c0 = c00;
+        Tap tp = a.taps[tap];
+        int c1 = x0 + tp.cw, c2 = y0 + tp.ch, c3 = d0 + tp.cd;
+        const CUtensorMap* map = &a.amap[tp.map];
+#pragma unroll 1
+        for (int it = it0; it < it1; it += KSUB) {
+          mbar_wait_addr(empty0 + b_off, ph ^ 1);
+          const uint32_t fb = full0 + b_off;
+          const bool two = KSUB == 2 && it + 1 < it1;
+          if (load) mbar_expect_tx_addr(fb, two ? 32768u : 16384u);
+          else mbar_arrive_addr(fb);
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_tf32(d_tmem, desc_advance(ad0, k * 32), desc_advance(bd0, k * 32), idesc, (it > it0 || k > 0) ? 1u : 0u);
-          umma_commit(&empty_bar[s]);
+          for (int j = 0; j < KSUB; ++j) {
+            if (j == 0 || two) {
+              if (load) tma_load_5d_addr(smem0 + s_off + j * sub_bytes, map, fb, c0, c1, c2, c3, s0);
+              c0 += 32;
+              if (c0 == c0_end) {
+                c0 = 0; ++tap;
+                tp = a.taps[tap < te ? tap : tb];
+                c1 = x0 + tp.cw; c2 = y0 + tp.ch; c3 = d0 + tp.cd;
+                map = &a.amap[tp.map];
+              }
+            }
+          }
+          s_off += stage_bytes; b_off += 8;
+          if (b_off == ring_end) { s_off = 0; b_off = 0; ph ^= 1; }
         }
-        __syncwarp();
-        if (++s == a.stages) { s = 0; ph ^= 1; }
       }
-      if (leader) umma_commit(&tmem_full_bar[acc]);
-      __syncwarp();
     }
-  } else {
+    __syncwarp();
+  } else if (warp == 6) {
+    // weight tiles: one 2-D TMA per k-chunk (rows = tap slot * n_pad + n0)
+    if (elect_one_sync() && !(DBG && (a.dbg_skip & 8))) {
+      const bool load = !(DBG && (a.dbg_skip & 2));
+      const uint32_t smem0 = smem_u32(smem) + 16384u;
+      const uint32_t b_bytes = sub_bytes - 16384u;
+      uint32_t s_off = 0, b_off = 0, ph = 0;
+      const int tap0 = it0 / a.kc, c00 = (it0 - tap0 * a.kc) * 32, c0_end = a.kc * 32;
+#pragma unroll 1
+      for (int mtile = blockIdx.x; mtile < num_mtiles; mtile += gridDim.x) {
+        int tap = tb + tap0, c0 = c00;
+        int c1 = a.taps[tap].wslot * a.n_pad + n0;
+#pragma unroll 1
+        for (int it = it0; it < it1; it += KSUB) {
+          mbar_wait_addr(empty0 + b_off, ph ^ 1);
+          const uint32_t fb = full0 + b_off;
+          const bool two = KSUB == 2 && it + 1 < it1;
+          if (load) mbar_expect_tx_addr(fb, two ? 2 * b_bytes : b_bytes);
+          else mbar_arrive_addr(fb);
+#pragma unroll
+          for (int j = 0; j < KSUB; ++j) {
+            if (j == 0 || two) {
+              if (load) tma_load_2d_addr(smem0 + s_off + j * sub_bytes, &a.bmap, fb, c0, c1);
+              c0 += 32;
+              if (c0 == c0_end) { c0 = 0; ++tap; c1 = a.taps[tap < te ? tap : tb].wslot * a.n_pad + n0; }
+            }
+          }
+          s_off += stage_bytes; b_off += 8;
+          if (b_off == ring_end) { s_off = 0; b_off = 0; ph ^= 1; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (elect_one_sync()) {
+      const uint32_t idesc = make_idesc_tf32(128, a.bn_tile, 0, 0);
+      const uint64_t ad_base = make_smem_desc(smem_u32(smem), 16, 1024, 0);
+      const uint32_t stage_adv = stage_bytes >> 4, sub_adv = sub_bytes >> 4;
+      const bool ring = !(DBG && (a.dbg_skip & 8));
+      uint32_t b_off = 0, ph = 0;
+      int ti = 0;
+      uint64_t ad = ad_base;
+      long long trace_c0 = 0;
+#pragma unroll 1
+      for (int mtile = blockIdx.x; mtile < num_mtiles; mtile += gridDim.x, ++ti) {
+        const int acc = ti & 1, use = ti >> 1;
+        if (!(DBG && (a.dbg_skip & 4))) mbar_wait(&tmem_empty_bar[acc], (use & 1) ^ 1);   // epilogue drained this accumulator
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * a.bn_tile;
+        uint32_t accum = 0;
+#pragma unroll 1
+        for (int it = it0; it < it1; it += KSUB) {
+          if (ring) mbar_wait_addr(full0 + b_off, ph);
+          tc_fence_after();
+          if (DBG && it == it0 && ti == 0) { VP_TRACE(2); trace_c0 = clock64(); }
+          const uint64_t bd = ad + (16384u >> 4);
+          umma_tf32(d_tmem, ad, bd, idesc, accum);
+          umma_tf32(d_tmem, ad + 2, bd + 2, idesc, 1u);
+          umma_tf32(d_tmem, ad + 4, bd + 4, idesc, 1u);
+          umma_tf32(d_tmem, ad + 6, bd + 6, idesc, 1u);
+          if (KSUB == 2 && it + 1 < it1) {
+            const uint64_t ad2 = ad + sub_adv, bd2 = bd + sub_adv;
+            umma_tf32(d_tmem, ad2, bd2, idesc, 1u);
+            umma_tf32(d_tmem, ad2 + 2, bd2 + 2, idesc, 1u);
+            umma_tf32(d_tmem, ad2 + 4, bd2 + 4, idesc, 1u);
+            umma_tf32(d_tmem, ad2 + 6, bd2 + 6, idesc, 1u);
+          }
+          if (ring) umma_commit_addr(empty0 + b_off);
+          accum = 1u;
+          ad += stage_adv; b_off += 8;
+          if (b_off == ring_end) { b_off = 0; ph ^= 1; ad = ad_base; }
+        }
+        umma_commit(&tmem_full_bar[acc]);
+        if (DBG) {
+          VP_TRACE(3);
+          if (a.dbg_trace) g_trace[(blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z)) % 2048 * 16 + 1] = clock64() - trace_c0;
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp < 6) {
     // ---- epilogue: warp w owns TMEM lanes 32*(w%4)..+31, thread <-> one output pixel
     const int q = warp & 3;
     const int row = q * 32 + lane;
@@ -171,7 +273,7 @@ __global__ void __launch_bounds__(192, 2) igemm_fwd_kernel(const __grid_constant
     const int ln = r / a.bd;
     const bool add_bias = (a.bias != nullptr) && (split == 0);
     int ti = 0;
-    for (int mtile = blockIdx.x; mtile < num_mtiles; mtile += gridDim.x, ++ti) {
+    for (int mtile = blockIdx.x; mtile < num_mtiles && !(DBG && (a.dbg_skip & 4)); mtile += gridDim.x, ++ti) {
       int mt = mtile;
       const int tw = mt % a.tiles_w; mt /= a.tiles_w;
       const int th = mt % a.tiles_h; mt /= a.tiles_h;
@@ -187,6 +289,7 @@ __global__ void __launch_bounds__(192, 2) igemm_fwd_kernel(const __grid_constant
       const int acc = ti & 1, use = ti >> 1;
       mbar_wait(&tmem_full_bar[acc], use & 1);
       tc_fence_after();
+      if (threadIdx.x == 64) VP_TRACE(4);
       const uint32_t t_acc = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * a.bn_tile;
       for (int c0 = 0; c0 < a.bn_tile; c0 += 16) {
         float v[16];
@@ -239,11 +342,13 @@ __global__ void __launch_bounds__(192, 2) igemm_fwd_kernel(const __grid_constant
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+      if (threadIdx.x == 64) VP_TRACE(5);
     }
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, a.tmem_cols);
+  if (threadIdx.x == 0) VP_TRACE(6);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -579,25 +684,36 @@ static int conv_igemm_impl(const vp_tensor* in, const vp_conv_geom* g, const flo
     if (r != CUDA_SUCCESS) return set_error("cuTensorMapEncodeTiled(weights) failed with %d", static_cast<int>(r));
   }
   const long long n_ctas = static_cast<long long>(A.tiles_w) * A.tiles_h * A.tiles_d * A.tiles_n * (n_pad / A.bn_tile) * A.num_phases * A.splits;
-  // more than one CTA per SM's worth of work: 3 stages (<= 97 KB) so two CTAs share an SM and overlap prologue/epilogue
-  // with the other's main loop; a single partial wave keeps the deeper 4-stage pipeline
-  A.stages = (A.bn_tile <= 128 && n_ctas > 148) ? 3 : kStagesFwd;
-  if (const char* e = getenv("VP_FWD_STAGES")) { const int v = atoi(e); if (v >= 2 && v <= kMaxStagesFwd && static_cast<size_t>(v) * (16384 + A.bn_tile * 128) + 1024 <= 226 * 1024) A.stages = v; }
-  const size_t smem = static_cast<size_t>(A.stages) * (16384 + A.bn_tile * 128) + 1024;
+  // Pipeline shape.  The producer / MMA issue loops are single-thread latency chains (~5 cycles per instruction), and a
+  // stage of four N<=128 MMAs covers only <= 256 tensor-pipe cycles, so narrow tiles carry TWO k-chunks per stage
+  // (8 MMAs, 64 KB, 3 stages); wide tiles (N > 128) keep one chunk per stage and 4 stages.
+  A.ksub = (A.bn_tile <= 128 && min_iters / std::max(1, split_k) >= 2) ? 2 : 1;
+  A.stages = A.ksub == 2 ? 3 : kStagesFwd;
+  if (const char* e = getenv("VP_FWD_KSUB")) { const int v = atoi(e); if (v == 1 || v == 2) { A.ksub = v; A.stages = v == 2 ? 3 : ((A.bn_tile <= 128 && n_ctas > 148) ? 3 : kStagesFwd); } }
+  if (const char* e = getenv("VP_FWD_SKIP")) A.dbg_skip = atoi(e);
+  if (getenv("VP_FWD_TRACE")) A.dbg_trace = 1;
+  const size_t sub_bytes = 16384 + static_cast<size_t>(A.bn_tile) * 128;
+  if (const char* e = getenv("VP_FWD_STAGES")) { const int v = atoi(e); if (v >= 2 && v <= kMaxStagesFwd && static_cast<size_t>(v) * A.ksub * sub_bytes + 1024 <= 226 * 1024) A.stages = v; }
+  const size_t smem = static_cast<size_t>(A.stages) * A.ksub * sub_bytes + 1024;
+  typedef void (*FwdKernel)(const IgemmArgs);
+  static const FwdKernel kernels[4] = {igemm_fwd_kernel<1, false>, igemm_fwd_kernel<2, false>, igemm_fwd_kernel<1, true>,
+                                       igemm_fwd_kernel<2, true>};
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(igemm_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024) != cudaSuccess)
-      return set_error("cudaFuncSetAttribute(igemm_fwd_kernel) failed: %s", cudaGetErrorString(cudaGetLastError()));
+    for (FwdKernel k : kernels)
+      if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024) != cudaSuccess)
+        return set_error("cudaFuncSetAttribute(igemm_fwd_kernel) failed: %s", cudaGetErrorString(cudaGetLastError()));
     attr_set = true;
   }
+  const FwdKernel kernel = kernels[(A.ksub == 2 ? 1 : 0) + ((A.dbg_skip || A.dbg_trace) ? 2 : 0)];
   // persistent over the pixel tiles: at most ~2 CTAs per SM in total; each CTA strides through the M tiles
   const int m_tiles = A.tiles_w * A.tiles_h * A.tiles_d * A.tiles_n;
   const int other = (n_pad / A.bn_tile) * A.num_phases * A.splits;
-  const int resident = (A.stages == 3 ? 2 : 1) * 148;
+  const int resident = (smem <= 113 * 1024 ? 2 : 1) * 148;
   int gx = std::min(m_tiles, std::max(1, resident / other));
   if (const char* e = getenv("VP_FWD_NONPERSISTENT")) { if (atoi(e)) gx = m_tiles; }
   dim3 grid(gx, n_pad / A.bn_tile, A.num_phases * A.splits);
-  igemm_fwd_kernel<<<grid, 192, smem, static_cast<cudaStream_t>(stream)>>>(A);
+  kernel<<<grid, 224, smem, static_cast<cudaStream_t>(stream)>>>(A);
   count_launch(1);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error("igemm_fwd_kernel launch failed: %s", cudaGetErrorString(e));
@@ -672,5 +788,13 @@ extern "C" int vp_conv_wgrad(const vp_tensor* x, const vp_tensor* dy, const vp_c
   count_launch(1);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error("igemm_wgrad_kernel launch failed: %s", cudaGetErrorString(e));
+  return 0;
+}
+
+// Debug: copy the per-CTA timeline of the last traced forward launch (VP_FWD_TRACE=1) to host memory (n entries of 8).
+extern "C" int vp_debug_read_trace(unsigned long long* host, int n_ctas) {
+  if (n_ctas > 2048) n_ctas = 2048;
+  if (cudaMemcpyFromSymbol(host, vp::g_trace, static_cast<size_t>(n_ctas) * 16 * sizeof(unsigned long long)) != cudaSuccess)
+    return set_error("vp_debug_read_trace failed: %s", cudaGetErrorString(cudaGetLastError()));
   return 0;
 }
