@@ -61,7 +61,7 @@ struct alignas(64) IgemmArgs {
   int32_t rows_from_shifted, m_tiles, n_tiles, kpad;
   int32_t tap_group, num_taps, rows_valid, wg_stages, stages;
   int32_t ksub;          // 32-channel k-chunks per pipeline stage (1 or 2): two chunks halve the per-MMA cost of the issue loops
-  int32_t dbg_trace;
+  int32_t dbg_trace, dbg_poll;
   int32_t dbg_skip;      // timing experiments only (VP_FWD_SKIP): 1 = no activation loads, 2 = no weight loads
   uint32_t wg_stage_bytes;
   Tap taps[kMaxTaps];
@@ -135,13 +135,13 @@ __global__ void __launch_bounds__(224, KSUB == 1 ? 2 : 1) igemm_fwd_kernel(const
   // a stage of four N<=128 MMAs covers only 256 tensor-pipe cycles: the loops are kept to a few dozen instructions
   // (no divisions, byte offsets carried instead of indices, slow paths out of line, debug code compiled out), the
   // activation and weight streams have their own issuers, and narrow tiles carry KSUB = 2 k-chunks per stage.
-  const uint32_t full0 = smem_u32(&full_bar[0]), empty0 = smem_u32(&empty_bar[0]);
+  const uint32_t full0 = opaque_u32(smem_u32(&full_bar[0])), empty0 = opaque_u32(smem_u32(&empty_bar[0]));
   const uint32_t ring_end = static_cast<uint32_t>(a.stages) * 8u;
   if (warp == 0) {
     // activation boxes: one 5-D TMA per k-chunk; the tap is a coordinate shift, padding is the OOB zero fill
     if (elect_one_sync() && !(DBG && (a.dbg_skip & 8))) {
       const bool load = !(DBG && (a.dbg_skip & 1));
-      const uint32_t smem0 = smem_u32(smem);
+      const uint32_t smem0 = opaque_u32(smem_u32(smem));
       uint32_t s_off = 0, b_off = 0, ph = 0;
       const int tap0 = it0 / a.kc, c00 = (it0 - tap0 * a.kc) * 32, c0_end = a.kc * 32;
 #pragma unroll 1
@@ -158,7 +158,7 @@ __global__ void __launch_bounds__(224, KSUB == 1 ? 2 : 1) igemm_fwd_kernel(const
         const CUtensorMap* map = &a.amap[tp.map];
 #pragma unroll 1
         for (int it = it0; it < it1; it += KSUB) {
-          mbar_wait_addr(empty0 + b_off, ph ^ 1);
+          if (a.dbg_poll) mbar_poll_addr(empty0 + b_off, ph ^ 1); else mbar_wait_addr(empty0 + b_off, ph ^ 1);
           const uint32_t fb = full0 + b_off;
           const bool two = KSUB == 2 && it + 1 < it1;
           if (load) mbar_expect_tx_addr(fb, two ? 32768u : 16384u);
@@ -186,7 +186,7 @@ __global__ void __launch_bounds__(224, KSUB == 1 ? 2 : 1) igemm_fwd_kernel(const
     // weight tiles: one 2-D TMA per k-chunk (rows = tap slot * n_pad + n0)
     if (elect_one_sync() && !(DBG && (a.dbg_skip & 8))) {
       const bool load = !(DBG && (a.dbg_skip & 2));
-      const uint32_t smem0 = smem_u32(smem) + 16384u;
+      const uint32_t smem0 = opaque_u32(smem_u32(smem) + 16384u);
       const uint32_t b_bytes = sub_bytes - 16384u;
       uint32_t s_off = 0, b_off = 0, ph = 0;
       const int tap0 = it0 / a.kc, c00 = (it0 - tap0 * a.kc) * 32, c0_end = a.kc * 32;
@@ -196,7 +196,7 @@ __global__ void __launch_bounds__(224, KSUB == 1 ? 2 : 1) igemm_fwd_kernel(const
         int c1 = a.taps[tap].wslot * a.n_pad + n0;
 #pragma unroll 1
         for (int it = it0; it < it1; it += KSUB) {
-          mbar_wait_addr(empty0 + b_off, ph ^ 1);
+          if (a.dbg_poll) mbar_poll_addr(empty0 + b_off, ph ^ 1); else mbar_wait_addr(empty0 + b_off, ph ^ 1);
           const uint32_t fb = full0 + b_off;
           const bool two = KSUB == 2 && it + 1 < it1;
           if (load) mbar_expect_tx_addr(fb, two ? 2 * b_bytes : b_bytes);
@@ -234,7 +234,7 @@ __global__ void __launch_bounds__(224, KSUB == 1 ? 2 : 1) igemm_fwd_kernel(const
         uint32_t accum = 0;
 #pragma unroll 1
         for (int it = it0; it < it1; it += KSUB) {
-          if (ring) mbar_wait_addr(full0 + b_off, ph);
+          if (ring) { if (a.dbg_poll) mbar_poll_addr(full0 + b_off, ph); else mbar_wait_addr(full0 + b_off, ph); }
           tc_fence_after();
           if (DBG && it == it0 && ti == 0) { VP_TRACE(2); trace_c0 = clock64(); }
           const uint64_t bd = ad + (16384u >> 4);
@@ -692,6 +692,7 @@ static int conv_igemm_impl(const vp_tensor* in, const vp_conv_geom* g, const flo
   if (const char* e = getenv("VP_FWD_KSUB")) { const int v = atoi(e); if (v == 1 || v == 2) { A.ksub = v; A.stages = v == 2 ? 3 : ((A.bn_tile <= 128 && n_ctas > 148) ? 3 : kStagesFwd); } }
   if (const char* e = getenv("VP_FWD_SKIP")) A.dbg_skip = atoi(e);
   if (getenv("VP_FWD_TRACE")) A.dbg_trace = 1;
+  if (const char* e = getenv("VP_FWD_POLL")) A.dbg_poll = atoi(e);
   const size_t sub_bytes = 16384 + static_cast<size_t>(A.bn_tile) * 128;
   if (const char* e = getenv("VP_FWD_STAGES")) { const int v = atoi(e); if (v >= 2 && v <= kMaxStagesFwd && static_cast<size_t>(v) * A.ksub * sub_bytes + 1024 <= 226 * 1024) A.stages = v; }
   const size_t smem = static_cast<size_t>(A.stages) * A.ksub * sub_bytes + 1024;

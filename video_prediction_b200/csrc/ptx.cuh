@@ -61,15 +61,35 @@ __device__ __forceinline__ uint32_t mbar_try_wait_addr(uint32_t addr, uint32_t p
       : "memory");
   return ok;
 }
-// Slow path out of line: the issue loops stay short (their instruction count is what bounds the MMA rate).
-static __device__ __noinline__ void mbar_wait_slow(uint32_t addr, uint32_t parity) {
-  const long long t0 = clock64();
+// Bounded spin without a call or a clock read: the issue loops stay short and keep their uniform registers (their
+// instruction count is what bounds the MMA rate).  Each failed try_wait suspends for a hardware time slice, so 2^26
+// attempts are many seconds; a protocol bug then traps instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait_addr(uint32_t addr, uint32_t parity) {
+  int spins = 0;
   while (!mbar_try_wait_addr(addr, parity)) {
-    if (clock64() - t0 > 4000000000LL) { __trap(); }
+    if (++spins > (1 << 26)) { __trap(); }
   }
 }
-__device__ __forceinline__ void mbar_wait_addr(uint32_t addr, uint32_t parity) {
-  if (!mbar_try_wait_addr(addr, parity)) mbar_wait_slow(addr, parity);
+// Non-suspending poll (mbarrier.test_wait): the issue threads have nothing else to do and the ring of a 192 KB
+// pipeline is round-trip-latency bound, so they react to a phase flip within a few cycles instead of a wake-up.
+__device__ __forceinline__ void mbar_poll_addr(uint32_t addr, uint32_t parity) {
+  uint32_t ok;
+  int spins = 0;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (!ok && ++spins > (1 << 28)) { __trap(); }
+  } while (!ok);
+}
+// Make a value opaque to the optimiser so that it stays in its register instead of being rematerialised in a loop.
+__device__ __forceinline__ uint32_t opaque_u32(uint32_t v) {
+  asm volatile("mov.u32 %0, %0;" : "+r"(v));
+  return v;
 }
 __device__ __forceinline__ void mbar_expect_tx_addr(uint32_t addr, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(addr), "r"(bytes) : "memory");
