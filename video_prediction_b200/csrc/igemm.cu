@@ -61,6 +61,7 @@ struct alignas(64) IgemmArgs {
   int32_t rows_from_shifted, m_tiles, n_tiles, kpad;
   int32_t tap_group, num_taps, rows_valid, wg_stages, stages;
   int32_t ksub;          // 32-channel k-chunks per pipeline stage (1 or 2): two chunks halve the per-MMA cost of the issue loops
+  int32_t k_tail;        // MMAs (K = 8 channels each) that hold real channels in the LAST k-chunk of a tap (1..4)
   int32_t dbg_trace, dbg_poll;
   int32_t dbg_skip;      // timing experiments only (VP_FWD_SKIP): 1 = no activation loads, 2 = no weight loads
   uint32_t wg_stage_bytes;
@@ -221,6 +222,7 @@ __global__ void __launch_bounds__(224, KSUB == 1 ? 2 : 1) igemm_fwd_kernel(const
       const uint64_t ad_base = make_smem_desc(smem_u32(smem), 16, 1024, 0);
       const uint32_t stage_adv = stage_bytes >> 4, sub_adv = sub_bytes >> 4;
       const bool ring = !(DBG && (a.dbg_skip & 8));
+      const int kq_last = a.kc - 1;
       uint32_t b_off = 0, ph = 0;
       int ti = 0;
       uint64_t ad = ad_base;
@@ -232,22 +234,29 @@ __global__ void __launch_bounds__(224, KSUB == 1 ? 2 : 1) igemm_fwd_kernel(const
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * a.bn_tile;
         uint32_t accum = 0;
+        int kq = it0 % a.kc;
 #pragma unroll 1
         for (int it = it0; it < it1; it += KSUB) {
           if (ring) { if (a.dbg_poll) mbar_poll_addr(full0 + b_off, ph); else mbar_wait_addr(full0 + b_off, ph); }
           tc_fence_after();
           if (DBG && it == it0 && ti == 0) { VP_TRACE(2); trace_c0 = clock64(); }
+          // the last k-chunk of a tap may hold fewer than 32 real channels (e.g. 72 = 32 + 32 + 8): the zero-filled
+          // K = 8 slices are not multiplied at all
           const uint64_t bd = ad + (16384u >> 4);
+          const int nk = kq == kq_last ? a.k_tail : 4;
           umma_tf32(d_tmem, ad, bd, idesc, accum);
-          umma_tf32(d_tmem, ad + 2, bd + 2, idesc, 1u);
-          umma_tf32(d_tmem, ad + 4, bd + 4, idesc, 1u);
-          umma_tf32(d_tmem, ad + 6, bd + 6, idesc, 1u);
+          if (nk > 1) umma_tf32(d_tmem, ad + 2, bd + 2, idesc, 1u);
+          if (nk > 2) umma_tf32(d_tmem, ad + 4, bd + 4, idesc, 1u);
+          if (nk > 3) umma_tf32(d_tmem, ad + 6, bd + 6, idesc, 1u);
+          kq = kq == kq_last ? 0 : kq + 1;
           if (KSUB == 2 && it + 1 < it1) {
             const uint64_t ad2 = ad + sub_adv, bd2 = bd + sub_adv;
+            const int nk2 = kq == kq_last ? a.k_tail : 4;
             umma_tf32(d_tmem, ad2, bd2, idesc, 1u);
-            umma_tf32(d_tmem, ad2 + 2, bd2 + 2, idesc, 1u);
-            umma_tf32(d_tmem, ad2 + 4, bd2 + 4, idesc, 1u);
-            umma_tf32(d_tmem, ad2 + 6, bd2 + 6, idesc, 1u);
+            if (nk2 > 1) umma_tf32(d_tmem, ad2 + 2, bd2 + 2, idesc, 1u);
+            if (nk2 > 2) umma_tf32(d_tmem, ad2 + 4, bd2 + 4, idesc, 1u);
+            if (nk2 > 3) umma_tf32(d_tmem, ad2 + 6, bd2 + 6, idesc, 1u);
+            kq = kq == kq_last ? 0 : kq + 1;
           }
           if (ring) umma_commit_addr(empty0 + b_off);
           accum = 1u;
@@ -632,6 +641,8 @@ static int conv_igemm_impl(const vp_tensor* in, const vp_conv_geom* g, const flo
   const int lat[4] = {out->w, out->h, out->d, out->n};
   if (build_geometry(A, g, in, 128, lat)) return -1;
   A.kc = kc; A.n_pad = n_pad;
+  A.k_tail = std::min(4, std::max(1, ceil_div(in->c - (kc - 1) * 32, 8)));
+  if (getenv("VP_FWD_NOTAIL")) A.k_tail = 4;
   // N tiling: the whole N when it fits one UMMA (<= 256); 128-wide tiles for multiples of 128 (more CTAs for the
   // small-M ConvLSTM GEMMs); otherwise the fewest equal tiles that are multiples of 16 (n_pad = tiles * bn_tile).
   if (n_pad <= 256) A.bn_tile = n_pad;
@@ -674,7 +685,8 @@ static int conv_igemm_impl(const vp_tensor* in, const vp_conv_geom* g, const flo
     EncodeTiledFn enc = get_encode();
     if (!enc) return set_error("cuTensorMapEncodeTiled entry point not found");
     const int slots = g->kd * g->kh * g->kw;
-    cuuint64_t dims[2] = {static_cast<cuuint64_t>(kc) * 32, static_cast<cuuint64_t>(slots) * n_pad};
+    // logical width = the real channel count: the zero padding of the last k-chunk is OOB-filled, not fetched
+    cuuint64_t dims[2] = {static_cast<cuuint64_t>(std::min(kc * 32, (in->c + 3) / 4 * 4)), static_cast<cuuint64_t>(slots) * n_pad};
     cuuint64_t strides[1] = {static_cast<cuuint64_t>(kc) * 128};
     cuuint32_t box[2] = {32, static_cast<cuuint32_t>(A.bn_tile)};
     cuuint32_t es[2] = {1, 1};
