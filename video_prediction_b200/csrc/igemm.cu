@@ -61,6 +61,7 @@ struct alignas(64) IgemmArgs {
   int32_t rows_from_shifted, m_tiles, n_tiles, kpad;
   int32_t tap_group, num_taps, rows_valid, wg_stages, stages;
   int32_t ksub;          // 32-channel k-chunks per pipeline stage (1 or 2): two chunks halve the per-MMA cost of the issue loops
+  int32_t halo_w, halo_sub, row_kw, row_pw;   // wgrad row mode: halo box width (pixels), padded bytes of one halo sub-tile, kw, pw
   int32_t k_tail;        // MMAs (K = 8 channels each) that hold real channels in the LAST k-chunk of a tap (1..4)
   int32_t dbg_trace, dbg_poll;
   int32_t dbg_skip;      // timing experiments only (VP_FWD_SKIP): 1 = no activation loads, 2 = no weight loads
@@ -474,7 +475,144 @@ __global__ void __launch_bounds__(192, 1) igemm_wgrad_kernel(const __grid_consta
         tmem_ld16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + t * ncols + cc, v);
         if (rvalid) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) atomicAdd(orow + cc + j, v[j]);
+          for (int j = 0; j < 16; j += 4) red_add_v4(orow + cc + j, v[j], v[j + 1], v[j + 2], v[j + 3]);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, a.tmem_cols);
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// wgrad, ROW MODE (stride-1 convolutions: the ConvLSTM gates).  One CTA = (128 dy-channels x up-to-96/128
+// x-channels) x ONE KERNEL ROW (all kw taps) x a range of pixel boxes.  Per 64-pixel box the CTA loads dy once and ONE
+// halo tile of x (bw + kw - 1 pixels per line, left/right padding by TMA OOB fill); the kw taps of the row read the
+// same halo tile through descriptor start addresses shifted by s pixels (s * 128 B inside the 128B-swizzled MN-major
+// tile).  L2 -> SM traffic per MMA drops ~3.3x against the tap-group kernel and the stage needs 7 TMA loads for 40 MMAs.
+// ------------------------------------------------------------------------------------------------
+template <int LINES>   // lines of bw = 64 / LINES pixels per 64-pixel box
+__global__ void __launch_bounds__(192, 1) igemm_wgrad_row_kernel(const __grid_constant__ IgemmArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ uint64_t full_bar[kWgMaxStages], empty_bar[kWgMaxStages], tmem_full_bar;
+  __shared__ uint32_t tmem_base_smem;
+  constexpr uint32_t kSub = kWgPix * 128;  // bytes of one 32-channel dy sub-tile
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int mtile = blockIdx.x % a.m_tiles, ntile = blockIdx.x / a.m_tiles;
+  const int m0 = mtile * 128;
+  const int nb_tile = a.tap_group;                               // 32-channel x groups per N tile (<= 512 / (32 kw))
+  const int c0 = ntile * nb_tile * 32;
+  const int nb = min(nb_tile, a.kc - ntile * nb_tile);
+  const int na = min(4, (a.rows_valid - m0 + 31) / 32);
+  const int row = blockIdx.y;                                    // kernel row (rd * kh + rh)
+  const int ncols = min(32 * nb, (a.out_c - c0 + 15) / 16 * 16);  // exact N (multiple of 16): no MMA columns for channel padding
+  const int stages = a.wg_stages;
+  const uint32_t stage_bytes = a.wg_stage_bytes;
+  const int total = a.tiles_w * a.tiles_h * a.tiles_d * a.tiles_n;
+  const int it0 = static_cast<int>(static_cast<long long>(total) * blockIdx.z / a.splits);
+  const int it1 = static_cast<int>(static_cast<long long>(total) * (blockIdx.z + 1) / a.splits);
+  if (it1 <= it0 || na <= 0) return;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < stages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    mbar_init(&tmem_full_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(&tmem_base_smem, a.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+  const uint32_t full0 = opaque_u32(smem_u32(&full_bar[0])), empty0 = opaque_u32(smem_u32(&empty_bar[0]));
+  const uint32_t ring_end = static_cast<uint32_t>(stages) * 8u;
+  const uint32_t smem0 = opaque_u32(smem_u32(smem));
+  const uint32_t halo_off = static_cast<uint32_t>(na) * kSub;   // x halo sub-tiles follow the dy sub-tiles
+
+  if (warp == 0) {
+    if (elect_one_sync()) {
+      const Tap tp = a.taps[row * a.row_kw];                    // first tap of the row: its (cd, ch) are the row's shift
+      const uint32_t tx = static_cast<uint32_t>(na) * kSub + static_cast<uint32_t>(nb) * (static_cast<uint32_t>(a.halo_w) * (kWgPix / a.bw) * 128u);
+      int mt = it0;
+      int tw = mt % a.tiles_w; mt /= a.tiles_w;
+      int th = mt % a.tiles_h; mt /= a.tiles_h;
+      int td = mt % a.tiles_d;
+      int tn = mt / a.tiles_d;
+      uint32_t s_off = 0, b_off = 0, ph = 0;
+#pragma unroll 1
+      for (int it = it0; it < it1; ++it) {
+        const int x0 = tw * a.bw, y0 = th * a.bh, d0 = td * a.bd, s0 = tn * a.bn;
+        mbar_wait_addr(empty0 + b_off, ph ^ 1);
+        const uint32_t fb = full0 + b_off, st = smem0 + s_off;
+        mbar_expect_tx_addr(fb, tx);
+        for (int i = 0; i < na; ++i) tma_load_5d_addr(st + i * kSub, &a.bmap, fb, m0 + 32 * i, x0, y0, d0, s0);
+        for (int i = 0; i < nb; ++i)
+          tma_load_5d_addr(st + halo_off + i * a.halo_sub, &a.amap[1], fb, c0 + 32 * i, x0 - a.row_pw, y0 + tp.ch, d0 + tp.cd, s0);
+        if (++tw == a.tiles_w) { tw = 0; if (++th == a.tiles_h) { th = 0; if (++td == a.tiles_d) { td = 0; ++tn; } } }
+        s_off += stage_bytes; b_off += 8;
+        if (b_off == ring_end) { s_off = 0; b_off = 0; ph ^= 1; }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (elect_one_sync()) {
+      const uint32_t idesc = make_idesc_tf32(128, ncols, 1, 1);
+      // MN-major tf32 (32-channel x 4-pixel atoms, 32-byte-granular 128B swizzle): LBO = stride between 32-channel
+      // groups, SBO = 512 (4 pixels).  The swizzle is keyed on the absolute shared-memory address, so a start address
+      // shifted by whole pixels (128 B) addresses the shifted window of the same tile.
+      const uint64_t ad_base = make_smem_desc(smem0, kSub, 512, 0, 1);
+      const uint64_t bd_base = make_smem_desc(smem0 + halo_off, static_cast<uint32_t>(a.halo_sub), 512, 0, 1);
+      const uint32_t stage_adv = stage_bytes >> 4;
+      constexpr int J = 8 / LINES;                               // K = 8 MMAs per line
+      const uint32_t b_line = static_cast<uint32_t>(a.halo_w) * 128u >> 4;
+      uint32_t b_off = 0, ph = 0, adv = 0, first = 1;
+      // N <= 128 MMAs last <= 64 cycles and the issuing thread retires one instruction every ~5 cycles: the 8 MMAs of a
+      // tap are fully unrolled, the dy descriptors (i * 1024 B) are shared by the kw taps of the stage.
+#pragma unroll 1
+      for (int it = it0; it < it1; ++it) {
+        mbar_wait_addr(full0 + b_off, ph);
+        tc_fence_after();
+        const uint64_t ad_s = ad_base + adv;
+        uint64_t bd_s = bd_base + adv;
+        const uint32_t accum0 = first ? 0u : 1u;
+#pragma unroll 1
+        for (int s = 0; s < a.row_kw; ++s, bd_s += 8) {          // next tap: + 1 pixel = 128 B = 8 descriptor units
+          const uint32_t d_tmem = tmem_base + s * ncols;
+#pragma unroll
+          for (int l = 0; l < LINES; ++l) {
+            const uint64_t bd_l = bd_s + l * b_line;
+#pragma unroll
+            for (int j = 0; j < J; ++j)
+              umma_tf32(d_tmem, ad_s + (l * J + j) * 64, bd_l + j * 64, idesc, (l == 0 && j == 0) ? accum0 : 1u);
+          }
+        }
+        umma_commit_addr(empty0 + b_off);
+        first = 0;
+        adv += stage_adv; b_off += 8;
+        if (b_off == ring_end) { b_off = 0; ph ^= 1; adv = 0; }
+      }
+      umma_commit(&tmem_full_bar);
+    }
+    __syncwarp();
+  } else {
+    const int q = warp & 3;
+    const int rowi = m0 + q * 32 + lane;
+    const bool rvalid = rowi < a.n_pad && rowi < a.rows_valid;
+    mbar_wait(&tmem_full_bar, 0);
+    tc_fence_after();
+    for (int s = 0; s < a.row_kw; ++s) {
+      const Tap tp = a.taps[row * a.row_kw + s];
+      float* orow = a.out + (static_cast<long long>(tp.wslot) * a.n_pad + rowi) * a.kpad + c0;
+      for (int cc = 0; cc < ncols; cc += 16) {
+        float v[16];
+        __syncwarp();
+        tmem_ld16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + s * ncols + cc, v);
+        if (rvalid) {
+#pragma unroll
+          for (int j = 0; j < 16; j += 4) red_add_v4(orow + cc + j, v[j], v[j + 1], v[j + 2], v[j + 3]);
         }
       }
     }
@@ -771,6 +909,59 @@ extern "C" int vp_conv_wgrad(const vp_tensor* x, const vp_tensor* dy, const vp_c
   A.m_tiles = ceil_div(std::min(n_pad, ceil_div(dy->c, 32) * 32), 128);
   A.n_tiles = ceil_div(kc, 4);
   A.num_taps = A.phase_begin[1];
+  // Row mode: stride-1, non-transposed convolutions with a box line that is a whole number of K = 8 MMAs.
+  {
+    const bool unit = g->sd == 1 && g->sh == 1 && g->sw == 1 && !g->transposed;
+    const char* env = getenv("VP_WGRAD_ROW");
+    const bool enabled = !(env && atoi(env) == 0);
+    if (enabled && unit && g->kw >= 4 && g->kw <= 8 && A.bw % 8 == 0 && g->kw * 32 <= 512) {
+      const int halo_w = A.bw + g->kw - 1;
+      const int lines = kWgPix / A.bw;
+      const int hbox[4] = {halo_w, A.bh, A.bd, A.bn};
+      if (halo_w <= 256 && make_act_map(&A.amap[1], x, 0, 0, 0, 1, 1, 1, hbox, true) == 0) {
+        A.halo_w = halo_w; A.row_kw = g->kw; A.row_pw = g->pw;
+        A.halo_sub = (halo_w * lines * 128 + 1023) / 1024 * 1024;
+        const int nb_max = std::min(std::min(4, kc), 512 / (32 * g->kw));
+        A.n_tiles = ceil_div(kc, nb_max);
+        const int nb_tile = ceil_div(kc, A.n_tiles);  // balanced N tiles (kc = 4 -> 2 + 2, kc = 5 -> 3 + 2)
+        A.tap_group = nb_tile;                       // reused: 32-channel x groups per N tile
+        A.out_c = x->c;
+        A.tmem_cols = next_pow2_cols(g->kw * 32 * nb_tile);
+        const int na_max = std::min(4, ceil_div(dy->c, 32));
+        A.wg_stage_bytes = static_cast<uint32_t>(na_max) * kWgPix * 128 + static_cast<uint32_t>(nb_tile) * A.halo_sub;
+        A.wg_stages = std::max(2, std::min(kWgMaxStages, static_cast<int>((198u * 1024u) / A.wg_stage_bytes)));
+        const int groups = g->kd * g->kh;
+        const int total = A.tiles_w * A.tiles_h * A.tiles_d * A.tiles_n;
+        const int ctas = A.m_tiles * A.n_tiles * groups;
+        int sk = split_k;
+        if (sk <= 0) sk = ceil_div(2 * 148, ctas);
+        A.splits = std::max(1, std::min(sk, std::max(1, total / 4)));
+        A.out = dwpacked;
+        static bool row_attr_set = false;
+        const size_t smem_max = 227 * 1024 - 2048;
+        typedef void (*RowKernel)(const IgemmArgs);
+        static const RowKernel row_kernels[4] = {igemm_wgrad_row_kernel<1>, igemm_wgrad_row_kernel<2>, igemm_wgrad_row_kernel<4>,
+                                                 igemm_wgrad_row_kernel<8>};
+        if (!row_attr_set) {
+          for (RowKernel k : row_kernels)
+            if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_max)) != cudaSuccess)
+              return set_error("cudaFuncSetAttribute(igemm_wgrad_row_kernel) failed: %s", cudaGetErrorString(cudaGetLastError()));
+          row_attr_set = true;
+        }
+        const RowKernel row_kernel = row_kernels[lines == 1 ? 0 : lines == 2 ? 1 : lines == 4 ? 2 : 3];
+        // + 24 KB: M = 128 always reads four dy groups; groups beyond `na` alias the following bytes (rows never stored)
+        const size_t smem = static_cast<size_t>(A.wg_stages) * A.wg_stage_bytes + 3 * kWgPix * 128 + 2048;
+        if (smem <= smem_max) {
+          dim3 grid(A.m_tiles * A.n_tiles, groups, A.splits);
+          row_kernel<<<grid, 192, smem, static_cast<cudaStream_t>(stream)>>>(A);
+          count_launch(1);
+          cudaError_t e = cudaGetLastError();
+          if (e != cudaSuccess) return set_error("igemm_wgrad_row_kernel launch failed: %s", cudaGetErrorString(e));
+          return 0;
+        }
+      }
+    }
+  }
   // tap group: bounded by TMEM columns (one accumulator per tap) and by the per-stage shared-memory budget
   const int nb_max = std::min(4, kc), na_max = std::min(4, ceil_div(dy->c, 32));
   const int n_shared = A.rows_from_shifted ? nb_max : na_max, n_per = A.rows_from_shifted ? na_max : nb_max;
