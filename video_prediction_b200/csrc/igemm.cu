@@ -405,60 +405,73 @@ __global__ void __launch_bounds__(192, 1) igemm_wgrad_kernel(const __grid_consta
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
 
+  // Issue loops: one elected thread each, no divisions, byte offsets carried instead of indices (see igemm_fwd_kernel).
+  const uint32_t full0 = opaque_u32(smem_u32(&full_bar[0])), empty0 = opaque_u32(smem_u32(&empty_bar[0]));
+  const uint32_t ring_end = static_cast<uint32_t>(stages) * 8u;
+  const uint32_t smem0 = opaque_u32(smem_u32(smem));
   if (warp == 0) {
-    const uint32_t leader = elect_one_sync();
-    int s = 0, ph = 0;
-    for (int it = it0; it < it1; ++it) {
-      mbar_wait(&empty_bar[s], ph ^ 1);
-      if (leader) {
-        int mt = it;
-        const int tw = mt % a.tiles_w; mt /= a.tiles_w;
-        const int th = mt % a.tiles_h; mt /= a.tiles_h;
-        const int td = mt % a.tiles_d;
-        const int tn = mt / a.tiles_d;
+    if (elect_one_sync()) {
+      const uint32_t tx = static_cast<uint32_t>(n_shared + nt * n_per) * kSub;
+      const int sh_c0 = a_shifted ? c0 : m0, pt_c0 = a_shifted ? m0 : c0;
+      int mt = it0;
+      int tw = mt % a.tiles_w; mt /= a.tiles_w;
+      int th = mt % a.tiles_h; mt /= a.tiles_h;
+      int td = mt % a.tiles_d;
+      int tn = mt / a.tiles_d;
+      uint32_t s_off = 0, b_off = 0, ph = 0;
+#pragma unroll 1
+      for (int it = it0; it < it1; ++it) {
         const int x0 = tw * a.bw, y0 = th * a.bh, d0 = td * a.bd, s0 = tn * a.bn;
-        uint8_t* st = smem + s * stage_bytes;
-        mbar_expect_tx(&full_bar[s], (n_shared + nt * n_per) * kSub);
+        mbar_wait_addr(empty0 + b_off, ph ^ 1);
+        const uint32_t fb = full0 + b_off;
+        uint32_t dst = smem0 + s_off;
+        mbar_expect_tx_addr(fb, tx);
         // shared (un-shifted) operand first, then one block per tap of the shifted operand
-        const int sh_c0 = a_shifted ? c0 : m0, pt_c0 = a_shifted ? m0 : c0;
-        for (int i = 0; i < n_shared; ++i) tma_load_5d(st + i * kSub, &a.bmap, &full_bar[s], sh_c0 + 32 * i, x0, y0, d0, s0);
+        for (int i = 0; i < n_shared; ++i, dst += kSub) tma_load_5d_addr(dst, &a.bmap, fb, sh_c0 + 32 * i, x0, y0, d0, s0);
+#pragma unroll 1
         for (int t = 0; t < nt; ++t) {
           const Tap tp = a.taps[t0 + t];
-          for (int i = 0; i < n_per; ++i)
-            tma_load_5d(st + (n_shared + t * n_per + i) * kSub, &a.amap[tp.map], &full_bar[s], pt_c0 + 32 * i, x0 + tp.cw,
-                        y0 + tp.ch, d0 + tp.cd, s0);
+          const CUtensorMap* map = &a.amap[tp.map];
+          const int cx = x0 + tp.cw, cy = y0 + tp.ch, cz = d0 + tp.cd;
+          for (int i = 0; i < n_per; ++i, dst += kSub) tma_load_5d_addr(dst, map, fb, pt_c0 + 32 * i, cx, cy, cz, s0);
         }
+        if (++tw == a.tiles_w) { tw = 0; if (++th == a.tiles_h) { th = 0; if (++td == a.tiles_d) { td = 0; ++tn; } } }
+        s_off += stage_bytes; b_off += 8;
+        if (b_off == ring_end) { s_off = 0; b_off = 0; ph ^= 1; }
       }
-      __syncwarp();
-      if (++s == stages) { s = 0; ph ^= 1; }
     }
+    __syncwarp();
   } else if (warp == 1) {
-    const uint32_t idesc = make_idesc_tf32(128, ncols, 1, 1);
-    const uint32_t leader = elect_one_sync();
-    int s = 0, ph = 0;
-    for (int it = it0; it < it1; ++it) {
-      mbar_wait(&full_bar[s], ph);
-      tc_fence_after();
-      if (leader) {
-        const uint32_t base = smem_u32(smem + s * stage_bytes);
-        for (int t = 0; t < nt; ++t) {
-          const uint32_t per = base + (n_shared + t * n_per) * kSub;
-          // MN-major tf32: 32-channel x 4-pixel atoms (512 B) with the 32-byte-granular 128B swizzle;
-          // LBO = stride between 32-channel groups, SBO = stride between 4-pixel groups.  M = 128 always reads
-          // four 32-channel groups; groups beyond `na` alias neighbouring data and only feed rows never stored.
-          const uint64_t ad0 = make_smem_desc(a_shifted ? per : base, kSub, 512, 0, 1);
-          const uint64_t bd0 = make_smem_desc(a_shifted ? base : per, kSub, 512, 0, 1);
+    if (elect_one_sync()) {
+      const uint32_t idesc = make_idesc_tf32(128, ncols, 1, 1);
+      // MN-major tf32: 32-channel x 4-pixel atoms (512 B) with the 32-byte-granular 128B swizzle;
+      // LBO = stride between 32-channel groups, SBO = stride between 4-pixel groups.  M = 128 always reads
+      // four 32-channel groups; groups beyond `na` alias neighbouring data and only feed rows never stored.
+      const uint64_t sh_base = make_smem_desc(smem0, kSub, 512, 0, 1);
+      const uint32_t per_adv = static_cast<uint32_t>(n_per) * kSub >> 4, sh_adv = static_cast<uint32_t>(n_shared) * kSub >> 4;
+      const uint32_t stage_adv = stage_bytes >> 4;
+      uint32_t b_off = 0, ph = 0, adv = 0, first = 1;
+#pragma unroll 1
+      for (int it = it0; it < it1; ++it) {
+        mbar_wait_addr(full0 + b_off, ph);
+        tc_fence_after();
+        const uint64_t shd = sh_base + adv;
+        uint64_t ptd = shd + sh_adv;
+        const uint32_t accum0 = first ? 0u : 1u;
+#pragma unroll 1
+        for (int t = 0; t < nt; ++t, ptd += per_adv) {
+          const uint64_t ad0 = a_shifted ? ptd : shd, bd0 = a_shifted ? shd : ptd;
+          const uint32_t d_tmem = tmem_base + t * ncols;
 #pragma unroll
-          for (int k = 0; k < kWgPix / 8; ++k)
-            umma_tf32(tmem_base + t * ncols, desc_advance(ad0, k * 1024), desc_advance(bd0, k * 1024), idesc,
-                      (it > it0 || k > 0) ? 1u : 0u);
+          for (int k = 0; k < kWgPix / 8; ++k) umma_tf32(d_tmem, ad0 + k * 64, bd0 + k * 64, idesc, k == 0 ? accum0 : 1u);
         }
-        umma_commit(&empty_bar[s]);
+        umma_commit_addr(empty0 + b_off);
+        first = 0;
+        adv += stage_adv; b_off += 8;
+        if (b_off == ring_end) { b_off = 0; ph ^= 1; adv = 0; }
       }
-      __syncwarp();
-      if (++s == stages) { s = 0; ph ^= 1; }
+      umma_commit(&tmem_full_bar);
     }
-    if (leader) umma_commit(&tmem_full_bar);
     __syncwarp();
   } else {
     const int q = warp & 3;
@@ -914,7 +927,9 @@ extern "C" int vp_conv_wgrad(const vp_tensor* x, const vp_tensor* dy, const vp_c
     const bool unit = g->sd == 1 && g->sh == 1 && g->sw == 1 && !g->transposed;
     const char* env = getenv("VP_WGRAD_ROW");
     const bool enabled = !(env && atoi(env) == 0);
-    if (enabled && unit && g->kw >= 4 && g->kw <= 8 && A.bw % 8 == 0 && g->kw * 32 <= 512) {
+    // (kc == 4 with kw = 5 would need two 64-column N tiles that re-read dy; the tap-group kernel is faster there)
+    const bool narrow_tiles = kc > 512 / (32 * g->kw) && kc % ceil_div(kc, 512 / (32 * g->kw)) == 0 && kc / ceil_div(kc, 512 / (32 * g->kw)) < 3;
+    if (enabled && unit && g->kw >= 4 && g->kw <= 8 && A.bw % 8 == 0 && g->kw * 32 <= 512 && !narrow_tiles) {
       const int halo_w = A.bw + g->kw - 1;
       const int lines = kWgPix / A.bw;
       const int hbox[4] = {halo_w, A.bh, A.bd, A.bn};
