@@ -541,6 +541,29 @@ class TrainMixin(object):
         if not staged:
             self.global_step += 1
 
+    def _run_concurrent(self, fns):
+        """Runs independent pieces of the step (the two discriminator towers) on forked streams: inside the captured CUDA
+        graph they become parallel branches, so the many sub-wave kernels of one tower fill the SMs the other leaves idle.
+        Every callable only touches its own tower's buffers, disjoint parameter/gradient ranges and its own loss slots."""
+        if len(fns) < 2 or os.environ.get('VP_CONCURRENT_D', '1') != '1':
+            for fn in fns:
+                fn()
+            return
+        main = torch.cuda.current_stream()
+        if not hasattr(self, '_side_streams'):
+            self._side_streams = []
+        while len(self._side_streams) < len(fns) - 1:
+            self._side_streams.append(torch.cuda.Stream(device=self.device))
+        side = self._side_streams[:len(fns) - 1]
+        for st in side:
+            st.wait_stream(main)
+        fns[0]()
+        for fn, st in zip(fns[1:], side):
+            with torch.cuda.stream(st):
+                fn()
+        for st in side:
+            main.wait_stream(st)
+
     def _step_device(self, allreduce=None):
         hp = self.hparams
         Bf, G, P = self.Bf, self.Gb, self.params
@@ -556,7 +579,7 @@ class TrainMixin(object):
             for net in self.dnets.values():     # UPDATE_OPS (ops.py:1046-1048): u' of the start-of-step weights
                 for lay in net['layers'] + [net['fc']]:
                     lay.u_next.copy_(lay.u_new)
-            for scope, net in self.dnets.items():
+            def d_step_tower(scope, net):
                 enc = scope.endswith('encoder/video')
                 w = hp.video_sn_vae_gan_weight if enc else hp.video_sn_gan_weight
                 self._d_gather(net, 'pre', net['ts'][('d_pre', 0)], net['ts'][('d_pre', 1)], 0 if enc else (B if hp.nz else 0))
@@ -565,6 +588,7 @@ class TrainMixin(object):
                 L.lsgan_loss(net['logits'][:B], 1.0, B, w, net['dlogits'][:B], slot)
                 L.lsgan_loss(net['logits'][B:], 0.0, B, w, net['dlogits'][B:], slot)
                 self._d_backward(net, 0, 2 * B, with_wgrad=True, to_clip=False)
+            self._run_concurrent([(lambda sc=sc, nt=nt: d_step_tower(sc, nt)) for sc, nt in self.dnets.items()])
             if allreduce is not None:
                 allreduce(self.d_grad)
             L.adam(self.d_flat, self.d_grad, self.d_m, self.d_v, self.d_flat.numel(), self.step_scalars[0:1], hp.beta1, hp.beta2,
@@ -587,7 +611,7 @@ class TrainMixin(object):
         if hp.kl_weight and hp.nz:
             L.kl_loss(Bf['zmu'], Bf['zlss'], S * B, hp.nz, self._slot('gen_kl_loss'))
         if has_d:
-            for scope, net in self.dnets.items():
+            def g_step_tower(scope, net):
                 enc = scope.endswith('encoder/video')
                 w = hp.video_sn_vae_gan_weight if enc else hp.video_sn_gan_weight
                 cd_w = hp.vae_gan_feature_cdist_weight if enc else hp.gan_feature_cdist_weight
@@ -610,7 +634,9 @@ class TrainMixin(object):
                         rows = int(np.prod(feat.shape[1:-1])) * B
                         L.cosine_distance(feat[B:], feat[:B], dcd[l], rows, co, cd_w, slot)
                 self._d_backward(net, B, 2 * B, with_wgrad=False, to_clip=True, dcd=dcd)
+                # the towers scatter into disjoint sample rows of dgen (posterior rows [0, B), prior rows [B, 2B))
                 L.scatter_clip(net['dclip'][B:], net['ts'][('d_post', 1)], G['dgen'], B, hp.clip_length, HW, NB, foff)
+            self._run_concurrent([(lambda sc=sc, nt=nt: g_step_tower(sc, nt)) for sc, nt in self.dnets.items()])
         # ---- BPTT
         for t in range(S - 1, -1, -1):
             self._gen_backward_step(t)
