@@ -231,6 +231,22 @@ def test_dense_and_small_lstm_fwd_bwd(L):
     close(dg, gg, 1e-5, 'lstm dgates'); close(dc0, gc, 1e-5, 'lstm dc')
 
 
+def test_wide_dense_tiled_kernels(L):
+    """The CDNA-kernel dense layer shapes (K >= 1024, J <= 128) take the tiled kernels; dW is called once over all time steps."""
+    for B, K, J in [(32, 2048, 100), (70, 1100, 36)]:
+        x, w, b, dy = rnd(B, K), rnd(K, J, seed=1, scale=0.05), rnd(J, seed=2), rnd(B, J, seed=3)
+        sig = torch.tensor([1.7], device='cuda')
+        y = torch.zeros(B, J, device='cuda')
+        L.dense_fwd(x, K, w, b, y, J, B, K, J, k_splits=32, inv_scale=sig)
+        xd, wd, bd = [t.double().requires_grad_(True) for t in (x, w, b)]
+        ref = xd @ (wd / 1.7) + bd
+        close(y, ref, 2e-5, 'wide dense fwd')
+        gx, gw, gb = torch.autograd.grad(ref, (xd, wd, bd), dy.double())
+        dx, dw, db = torch.zeros_like(x), torch.zeros_like(w), torch.zeros_like(b)
+        L.dense_bwd(x, K, w, dy, J, B, K, J, dx=dx, dx_stride=K, dw=dw, dbias=db, inv_scale=sig)
+        close(dx, gx, 2e-5, 'wide dense dx'); close(dw, gw, 2e-5, 'wide dense dw'); close(db, gb, 2e-5, 'wide dense db')
+
+
 def test_losses_and_adam(L):
     rows, C = 1000, 3
     pred, tgt = torch.rand(rows, 4, device='cuda'), torch.rand(rows, 4, device='cuda')

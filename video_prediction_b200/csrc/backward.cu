@@ -426,6 +426,87 @@ __global__ void dense_bwd_dw_kernel(const float* __restrict__ x, int xs, const f
   if (db && k == 0) db[j] += sb;
 }
 
+
+// Tiled versions for the wide CDNA-kernel dense layer (K = 8192 flattened lstm_h2 features -> J = 100, B = 2*batch rows):
+// dx: one CTA per 32 k; W tile and dy staged in shared memory (coalesced global reads, W read exactly once).
+// dW: one CTA per 32 k over ALL rows (the time-batched call passes B = (T-1)*NB rows); thread <-> (k, j mod 8).
+constexpr int kDenseJMax = 128;
+__global__ void __launch_bounds__(256) dense_bwd_dx_tiled_kernel(const float* __restrict__ dy, int dys, const float* __restrict__ W,
+                                                                 const float* __restrict__ inv_scale, float* __restrict__ dx, int dxs,
+                                                                 int B, int K, int J, int accumulate) {
+  extern __shared__ float dsm[];
+  float* Ws = dsm;                    // [32][J + 1]
+  float* dys_s = dsm + 32 * (J + 1);  // [B][J]
+  const int k0 = blockIdx.x * 32;
+  for (int i = threadIdx.x; i < 32 * J; i += blockDim.x) {
+    const int kk = i / J, j = i - kk * J;
+    Ws[kk * (J + 1) + j] = (k0 + kk < K) ? W[static_cast<long long>(k0 + kk) * J + j] : 0.f;
+  }
+  for (int i = threadIdx.x; i < B * J; i += blockDim.x) {
+    const int b = i / J, j = i - b * J;
+    dys_s[i] = dy[static_cast<long long>(b) * dys + j];
+  }
+  __syncthreads();
+  const float sc = inv_scale ? 1.f / __ldg(inv_scale) : 1.f;
+  for (int i = threadIdx.x; i < 32 * B; i += blockDim.x) {
+    const int kk = i & 31, b = i >> 5;
+    if (k0 + kk >= K) continue;
+    const float* wr = Ws + kk * (J + 1);
+    const float* dr = dys_s + b * J;
+    float s0 = 0.f, s1 = 0.f;
+    int j = 0;
+    for (; j + 1 < J; j += 2) { s0 += dr[j] * wr[j]; s1 += dr[j + 1] * wr[j + 1]; }
+    if (j < J) s0 += dr[j] * wr[j];
+    const float s = (s0 + s1) * sc;
+    float* o = dx + static_cast<long long>(b) * dxs + k0 + kk;
+    *o = accumulate ? *o + s : s;
+  }
+}
+
+__global__ void __launch_bounds__(256) dense_bwd_dw_tiled_kernel(const float* __restrict__ x, int xs, const float* __restrict__ dy,
+                                                                 int dys, const float* __restrict__ inv_scale,
+                                                                 float* __restrict__ dW, float* __restrict__ db, int B, int K, int J) {
+  __shared__ float xsm[32][33];
+  __shared__ float dsm2[32][kDenseJMax];
+  const int k0 = blockIdx.x * 32;
+  const int kk = threadIdx.x & 31, jg = threadIdx.x >> 5;   // 8 j-groups: j = jg + 8 i
+  float acc[kDenseJMax / 8];
+#pragma unroll
+  for (int i = 0; i < kDenseJMax / 8; ++i) acc[i] = 0.f;
+  float bsum = 0.f;                                          // CTA 0: thread t < J sums dy[:, t]
+  for (int i = threadIdx.x; i < 32 * kDenseJMax; i += blockDim.x) dsm2[i / kDenseJMax][i % kDenseJMax] = 0.f;   // columns >= J stay zero
+  __syncthreads();
+  for (int b0 = 0; b0 < B; b0 += 32) {
+    const int nb = min(32, B - b0);
+    for (int i = threadIdx.x; i < 32 * 32; i += blockDim.x) {
+      const int bb = i >> 5, k2 = i & 31;
+      xsm[bb][k2] = (bb < nb && k0 + k2 < K) ? x[static_cast<long long>(b0 + bb) * xs + k0 + k2] : 0.f;
+    }
+    for (int i = threadIdx.x; i < 32 * J; i += blockDim.x) {
+      const int bb = i / J, j = i - bb * J;
+      dsm2[bb][j] = bb < nb ? dy[static_cast<long long>(b0 + bb) * dys + j] : 0.f;
+    }
+    __syncthreads();
+    for (int bb = 0; bb < nb; ++bb) {
+      const float xv = xsm[bb][kk];
+#pragma unroll
+      for (int i = 0; i < kDenseJMax / 8; ++i) acc[i] += xv * dsm2[bb][jg + 8 * i];
+    }
+    if (db && blockIdx.x == 0 && threadIdx.x < J)
+      for (int bb = 0; bb < nb; ++bb) bsum += dsm2[bb][threadIdx.x];
+    __syncthreads();
+  }
+  const float sc = inv_scale ? 1.f / __ldg(inv_scale) : 1.f;
+  if (k0 + kk < K) {
+#pragma unroll
+    for (int i = 0; i < kDenseJMax / 8; ++i) {
+      const int j = jg + 8 * i;
+      if (j < J) dW[static_cast<long long>(k0 + kk) * J + j] += acc[i] * sc;
+    }
+  }
+  if (db && blockIdx.x == 0 && threadIdx.x < J) db[threadIdx.x] += bsum;
+}
+
 // dense LSTM cell backward (tf LSTMCell, gates i,j,f,o, forget bias)
 __global__ void lstm_cell_bwd_kernel(const float* __restrict__ gates, const float* __restrict__ c_prev,
                                      const float* __restrict__ c_new, const float* __restrict__ dh,
@@ -709,15 +790,28 @@ extern "C" int vp_cdna_kernel_norm_bwd(const float* raw, const float* out, const
 extern "C" int vp_dense_bwd(const float* x, int x_stride, const float* w, const float* inv_scale, const float* dy, int dy_stride,
                             float* dx, int dx_stride, int dx_accumulate, float* dw, float* dbias, int b, int k, int j,
                             vp_stream_t stream) {
+  const bool wide = k >= 1024 && j <= kDenseJMax;
   if (dx) {
-    dense_bwd_dx_kernel<<<grid_for(static_cast<long long>(b) * k, 256), 256, 0, as_stream(stream)>>>(dy, dy_stride, w, inv_scale, dx,
-                                                                                                   dx_stride, b, k, j, dx_accumulate);
-    if (check_launch("dense_bwd_dx_kernel")) return -1;
+    const size_t smem = (32 * static_cast<size_t>(j + 1) + static_cast<size_t>(b) * j) * sizeof(float);
+    if (wide && smem <= 48 * 1024) {
+      dense_bwd_dx_tiled_kernel<<<(k + 31) / 32, 256, smem, as_stream(stream)>>>(dy, dy_stride, w, inv_scale, dx, dx_stride, b, k, j,
+                                                                                 dx_accumulate);
+      if (check_launch("dense_bwd_dx_tiled_kernel")) return -1;
+    } else {
+      dense_bwd_dx_kernel<<<grid_for(static_cast<long long>(b) * k, 256), 256, 0, as_stream(stream)>>>(dy, dy_stride, w, inv_scale, dx,
+                                                                                                     dx_stride, b, k, j, dx_accumulate);
+      if (check_launch("dense_bwd_dx_kernel")) return -1;
+    }
   }
   if (dw) {
-    dense_bwd_dw_kernel<<<grid_for(static_cast<long long>(k) * j, 256), 256, 0, as_stream(stream)>>>(x, x_stride, dy, dy_stride,
-                                                                                                   inv_scale, dw, dbias, b, k, j);
-    if (check_launch("dense_bwd_dw_kernel")) return -1;
+    if (wide) {
+      dense_bwd_dw_tiled_kernel<<<(k + 31) / 32, 256, 0, as_stream(stream)>>>(x, x_stride, dy, dy_stride, inv_scale, dw, dbias, b, k, j);
+      if (check_launch("dense_bwd_dw_tiled_kernel")) return -1;
+    } else {
+      dense_bwd_dw_kernel<<<grid_for(static_cast<long long>(k) * j, 256), 256, 0, as_stream(stream)>>>(x, x_stride, dy, dy_stride,
+                                                                                                     inv_scale, dw, dbias, b, k, j);
+      if (check_launch("dense_bwd_dw_kernel")) return -1;
+    }
   }
   return 0;
 }

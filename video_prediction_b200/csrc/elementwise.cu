@@ -282,6 +282,43 @@ __global__ void __launch_bounds__(256) dense_fwd_kernel(const float* __restrict_
   }
 }
 
+
+// Tiled forward for the wide CDNA-kernel dense layer (K = 8192 -> J = 100, B <= 64 rows): one CTA per 64 k, W tile and
+// the x slab staged in shared memory, partial [B, J] products reduced into the zero-filled y with atomics.
+__global__ void __launch_bounds__(256) dense_fwd_tiled_kernel(const float* __restrict__ x, int xs, const float* __restrict__ W,
+                                                              const float* __restrict__ bias, const float* __restrict__ inv_scale,
+                                                              float* __restrict__ y, int ys, int B, int K, int J) {
+  extern __shared__ float fsm[];
+  float* Ws = fsm;              // [64][J]
+  float* xT = fsm + 64 * J;     // [64][B + 1]  (k-major so that lanes = consecutive rows b)
+  const int k0 = blockIdx.x * 64;
+  for (int i = threadIdx.x; i < 64 * J; i += blockDim.x) {
+    const int kk = i / J;
+    Ws[i] = (k0 + kk < K) ? W[static_cast<long long>(k0) * J + i] : 0.f;
+  }
+  for (int i = threadIdx.x; i < 64 * B; i += blockDim.x) {
+    const int b = i >> 6, kk = i & 63;
+    xT[kk * (B + 1) + b] = (k0 + kk < K) ? x[static_cast<long long>(b) * xs + k0 + kk] : 0.f;
+  }
+  __syncthreads();
+  const float sc = inv_scale ? 1.f / __ldg(inv_scale) : 1.f;
+  // outputs (b, j): lanes run over b, warps over j
+  for (int o = threadIdx.x; o < ((B + 31) / 32) * 32 * J; o += blockDim.x) {
+    const int bt = (B + 31) / 32 * 32;
+    const int b = o % bt, j = o / bt;
+    if (b >= B) continue;
+    float s0 = 0.f, s1 = 0.f;
+#pragma unroll 8
+    for (int kk = 0; kk < 64; kk += 2) {
+      s0 += xT[kk * (B + 1) + b] * Ws[kk * J + j];
+      s1 += xT[(kk + 1) * (B + 1) + b] * Ws[(kk + 1) * J + j];
+    }
+    float t = (s0 + s1) * sc;
+    if (bias && blockIdx.x == 0) t += bias[j];
+    atomicAdd(y + static_cast<long long>(b) * ys + j, t);
+  }
+}
+
 // dense LSTM cell on z (tf.nn.rnn_cell.LSTMCell, savp_model.py:354-362): gates [B,4U] (i,j,f,o)
 __global__ void lstm_cell_fwd_kernel(const float* __restrict__ gates, const float* __restrict__ c_prev,
                                      float* __restrict__ c_new, float* __restrict__ h_new, int B, int U,
@@ -478,6 +515,12 @@ extern "C" int vp_avgpool(const float* x, int x_cstride, float* y, int n, int po
 extern "C" int vp_dense_fwd(const float* x, int x_stride, const float* w, const float* bias, const float* inv_scale,
                             float* y, int y_stride, int b, int k, int j, int k_splits, vp_stream_t stream) {
   if (!x || !w || !y) return set_error("vp_dense_fwd: null pointer");
+  // wide layers called with k_splits > 1 (y zero-filled by the caller): tiled kernel
+  const size_t tsm = (64 * static_cast<size_t>(j) + 64 * static_cast<size_t>(b + 1)) * sizeof(float);
+  if (k_splits > 1 && k >= 1024 && j <= 128 && tsm <= 48 * 1024) {
+    dense_fwd_tiled_kernel<<<(k + 63) / 64, 256, tsm, as_stream(stream)>>>(x, x_stride, w, bias, inv_scale, y, y_stride, b, k, j);
+    return check_launch("dense_fwd_tiled_kernel");
+  }
   if (k_splits < 1) k_splits = 1;
   const int kchunk = (k + k_splits - 1) / k_splits;
   dim3 grid((b + 3) / 4, (k + kchunk - 1) / kchunk);

@@ -352,8 +352,9 @@ class TrainMixin(object):
         L.cdna_kernel_norm_bwd(Bf['kraw'][t], Bf['kern'][t], G['dkern'][t], G['dkraw'][t], NB, kh, kw, nk)
         K = Bf['small'].shape[-1]
         dn = sc + '/cdna_kernels/dense'
+        # dx only; dW / dbias of this layer are one GEMM over all time steps in _gen_backward_params
         L.dense_bwd(Bf['small'][t], K, P[dn + '/kernel'], G['dkraw'][t], kh * kw * nk, NB, K, kh * kw * nk, dx=G['dsmall'][t],
-                    dx_stride=K, dw=Gp[dn + '/kernel'], dbias=Gp[dn + '/bias'])
+                    dx_stride=K)
         # encoder/decoder stack in reverse
         n_enc = len(self.enc_specs)
         for li in range(nl - 1, -1, -1):
@@ -418,6 +419,11 @@ class TrainMixin(object):
         L.colsum(G['dsimg'].data_ptr(), 4, Gp[self.conv_simg.bname], 1, rows_top, C)
         self.conv_masks.wgrad(Bf['mk'], G['dmlog'], dy_c=self.nlayers)
         L.colsum(G['dmlog'].data_ptr(), 8, Gp[self.conv_masks.bname], 1, rows_top, self.nlayers)
+        # CDNA kernel dense layer: dW = sum over all time steps of small_t^T dkraw_t, one launch
+        Kd = Bf['small'].shape[-1]
+        dn = 'generator/rnn/savp_cell/cdna_kernels/dense'
+        nkk = self.kh * self.kw * self.nk
+        L.dense_bwd(Bf['small'], Kd, P[dn + '/kernel'], G['dkraw'], nkk, S * NB, Kd, nkk, dw=Gp[dn + '/kernel'], dbias=Gp[dn + '/bias'])
         if not self.Zc:
             return
         # tile_concat adjoint: sum the z-slot gradients of every concat buffer over space
@@ -570,15 +576,21 @@ class TrainMixin(object):
         B, NB, S, C = self.B, self.NB, self.S, self.C
         HW = self.H * self.W
         self.loss_vals.zero_()
-        self.generator_forward(collect=False)
         has_d = bool(self.dnets)
         world = float(self.world_size)
+
+        def d_prepare(net):
+            # spectral norm + weight packing of one tower (dozens of tiny dependent launches): independent of the generator
+            # forward, so it runs as a parallel graph branch underneath it
+            for lay in net['layers'] + [net['fc']]:
+                lay.sn_forward()
+                lay.pack()
+                lay.u_next.copy_(lay.u_new)     # UPDATE_OPS (ops.py:1046-1048): u' of the start-of-step weights
+
+        self._run_concurrent([lambda: self.generator_forward(collect=False)] +
+                             [(lambda nt=nt: d_prepare(nt)) for nt in self.dnets.values()])
         if has_d:
             self.d_grad.zero_()
-            self._d_sn_and_pack()
-            for net in self.dnets.values():     # UPDATE_OPS (ops.py:1046-1048): u' of the start-of-step weights
-                for lay in net['layers'] + [net['fc']]:
-                    lay.u_next.copy_(lay.u_new)
             def d_step_tower(scope, net):
                 enc = scope.endswith('encoder/video')
                 w = hp.video_sn_vae_gan_weight if enc else hp.video_sn_gan_weight
