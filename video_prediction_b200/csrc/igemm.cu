@@ -814,9 +814,17 @@ static int conv_igemm_impl(const vp_tensor* in, const vp_conv_geom* g, const flo
     // zero-filled output (only when the output view is dense so that it can be cleared here, and the epilogue is linear)
     split_k = 1;
     const bool dense = out->c == out->cstride;
-    if (dense && act == VP_ACT_NONE && !accumulate && !aux_y && base_ctas <= 96 && min_iters >= 24) {
-      split_k = static_cast<int>(std::min<long long>(3, (200 + base_ctas - 1) / base_ctas));   // measured: 3 splits on a 64-CTA grid 168 -> 237 TF/s
-      split_k = std::max(1, std::min(split_k, min_iters / 12));
+    if (dense && act == VP_ACT_NONE && !accumulate && !aux_y && base_ctas <= 148 && min_iters >= 24) {
+      // cost model: the persistent grid holds floor(148 / (N tiles * phases * splits)) CTAs per column of work, each CTA
+      // walks ceil(m_tiles / gx) pixel tiles of 1/splits of the K loop; every extra split costs atomics + a memset
+      const int m_tiles_all = A.tiles_w * A.tiles_h * A.tiles_d * A.tiles_n;
+      const int cols = (n_pad / A.bn_tile) * A.num_phases;
+      double best = 1e30;
+      for (int sp = 1; sp <= 4 && min_iters / sp >= 12; ++sp) {
+        const int gx = std::min(m_tiles_all, std::max(1, 148 / (cols * sp)));
+        const double cost = static_cast<double>(ceil_div(m_tiles_all, gx)) / sp + 0.06 * (sp - 1);
+        if (cost < best - 1e-9) { best = cost; split_k = sp; }
+      }
       if (split_k > 1) {
         const size_t bytes = static_cast<size_t>(out->n) * out->d * out->h * out->w * out->cstride * sizeof(float);
         if (cudaMemsetAsync(out->ptr, 0, bytes, static_cast<cudaStream_t>(stream)) != cudaSuccess)
@@ -949,7 +957,7 @@ extern "C" int vp_conv_wgrad(const vp_tensor* x, const vp_tensor* dy, const vp_c
         const int total = A.tiles_w * A.tiles_h * A.tiles_d * A.tiles_n;
         const int ctas = A.m_tiles * A.n_tiles * groups;
         int sk = split_k;
-        if (sk <= 0) sk = ceil_div(2 * 148, ctas);
+        if (sk <= 0) sk = std::max(1, (2 * 148) / ctas);   // at most two full waves of one-CTA-per-SM (never a third partial wave)
         A.splits = std::max(1, std::min(sk, std::max(1, total / 4)));
         A.out = dwpacked;
         static bool row_attr_set = false;
@@ -990,7 +998,7 @@ extern "C" int vp_conv_wgrad(const vp_tensor* x, const vp_tensor* dy, const vp_c
   A.wg_stages = std::max(2, std::min(kWgMaxStages, static_cast<int>((200u * 1024u) / A.wg_stage_bytes)));
   const int total = A.tiles_w * A.tiles_h * A.tiles_d * A.tiles_n;
   const int ctas = A.m_tiles * A.n_tiles * groups;
-  if (split_k <= 0) split_k = ceil_div(2 * 148, ctas);       // auto: about two waves of CTAs
+  if (split_k <= 0) split_k = std::max(1, (2 * 148) / ctas);  // auto: at most two full waves (never a third partial wave)
   A.splits = std::max(1, std::min(split_k, std::max(1, total / 4)));
   A.out = dwpacked;
   static bool attr_set = false;
