@@ -136,6 +136,27 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def ncu_traffic():
+    """DRAM traffic of the dominant kernel per launch (dram__bytes_read.sum + dram__bytes_write.sum) from the committed
+    `ncu --set full` capture of the lstm_h0 gate convolution (profiles/r01_ncu_full_final_summary.json), next to the
+    algorithmic bytes of that launch (input + packed weights read, gate pre-activations written)."""
+    out = dict(traffic=None)
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'profiles', 'r01_ncu_full_final_summary.json')
+    try:
+        with open(path) as f:
+            caps = json.load(f)['captures']['gate_r01b']
+        c = [x for x in caps if x.get('grid') == '148'][0]      # lstm_h0: 256 pixel tiles on a persistent grid of 148
+        out['traffic'] = (float(c['dram_bytes_read']) + float(c['dram_bytes_write'])) * 1e6
+        out['traffic_unit'] = 'bytes per launch (lstm_h0 gate conv, ncu --set full)'
+        out['traffic_algorithmic'] = 32 * 1024 * 72 * 4 + 25 * 128 * 96 * 4 + 32 * 1024 * 128 * 4
+        out['traffic_note'] = ('reads = input + weights once (no re-reads from HBM); the 16.8 MB of gate pre-activations stay in the '
+                               '126 MB L2 for the gate kernel that follows, so almost nothing is written back')
+        out['tensor_pipe_active_pct'] = float(c['tensor_pipe_active_pct_of_active'])
+    except Exception:       # noqa: BLE001  (profile summary absent: leave traffic null)
+        pass
+    return out
+
+
 def time_gate_kernels(model, iters=3):
     """CUDA-event timing of the five ConvLSTM gate convolutions (one launch per timestep buffer, cycling through all
     T-1 timesteps so consecutive launches touch different HBM lines; working set > L2)."""
@@ -274,7 +295,7 @@ def run_ours(args):
                     achieved=achieved, peak=peaks['bf16'], unit='TFLOP/s', frac=achieved / peaks['bf16'],
                     peak_source=peaks['src'] + ' cuBLAS bf16 (burst); tf32 MMA rate is half of bf16',
                     peak_tf32_equiv=peaks['bf16'] / 2, frac_of_tf32_peak=achieved / (peaks['bf16'] / 2),
-                    traffic=None, per_layer=per_layer)
+                    per_layer=per_layer, **ncu_traffic())
         cpu = None
         if world == 1 and not args.no_cpu:
             sb = 2
