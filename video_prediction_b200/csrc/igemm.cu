@@ -28,6 +28,7 @@ namespace vp {
 constexpr int kMaxTaps = 128;
 constexpr int kMaxMaps = 8;
 constexpr int kStagesFwd = 4;
+constexpr int kKsubMinIters = 48;  // k-iterations per CTA from which two k-chunks per stage pay off
 constexpr int kMaxStagesFwd = 6;
 constexpr int kStagesWg = 3;
 constexpr int kWgPix = 64;  // pixels (GEMM-K) per wgrad pipeline stage
@@ -858,8 +859,11 @@ static int conv_igemm_impl(const vp_tensor* in, const vp_conv_geom* g, const flo
   // Pipeline shape.  The producer / MMA issue loops are single-thread latency chains (~5 cycles per instruction), and a
   // stage of four N<=128 MMAs covers only <= 256 tensor-pipe cycles, so narrow tiles carry TWO k-chunks per stage
   // (8 MMAs, 64 KB, 3 stages); wide tiles (N > 128) keep one chunk per stage and 4 stages.
-  A.ksub = (A.bn_tile <= 128 && min_iters / std::max(1, split_k) >= 2) ? 2 : 1;
-  A.stages = A.ksub == 2 ? 3 : kStagesFwd;
+  // ... but short K loops (3x3 heads, pooled / upsampled encoder-decoder convs) are epilogue-bound: they keep one chunk per
+  // stage and 3 stages (<= 97 KB) so that TWO CTAs share an SM and eight epilogue warps drain the accumulators
+  const int iters_cta = min_iters / std::max(1, split_k);
+  A.ksub = (A.bn_tile <= 128 && iters_cta >= kKsubMinIters) ? 2 : 1;
+  A.stages = A.ksub == 2 ? 3 : ((A.bn_tile <= 128 && n_ctas > 148) ? 3 : kStagesFwd);
   if (const char* e = getenv("VP_FWD_KSUB")) { const int v = atoi(e); if (v == 1 || v == 2) { A.ksub = v; A.stages = v == 2 ? 3 : ((A.bn_tile <= 128 && n_ctas > 148) ? 3 : kStagesFwd); } }
   if (const char* e = getenv("VP_FWD_SKIP")) A.dbg_skip = atoi(e);
   if (getenv("VP_FWD_TRACE")) A.dbg_trace = 1;
