@@ -310,6 +310,7 @@ def run_ours(args):
         line = dict(metric='frames/sec SAVP 64x64 2+10 (training)', value=frames_per_step / ms * 1e3, unit='frames/s',
                     n_gpus=world, steps=args.steps, warmup=max(3, args.warmup), ms_per_step=ms, higher_is_better=True,
                     scaling='weak', vs_baseline=None, dtype='tf32 tensor-core convolutions, fp32 accumulate / state / optimizer',
+                    sequences_per_s=world * B / ms * 1e3,     # the reference's own `image/sec` print (train.py:331)
                     data='synthetic',
                     config=dict(workload='BASELINE configs[1]: SAVP (VAE+GAN) bair_action_free/ours_savp hparams, synthetic 64x64x3, '
                                          '2 context + 10 predicted, batch %d per GPU; full step = G fwd (2 unrolls) + 4 D towers + '
