@@ -73,6 +73,15 @@ def test_param_specs_match_oracle_names_and_shapes():
             assert tuple(shape) == tuple(ref[k].shape), k
 
 
+def test_loss_dict_split_matches_reference_attributes():
+    from video_prediction_b200.models.savp_train import TrainMixin
+    vals = {'gen_l1_loss': 2.0, 'gen_kl_loss': 0.5, 'gen_l2_loss': 0.0, 'discrim_video_sn_gan_loss': 0.25,
+            'discrim_video_sn_vae_gan_loss': 0.75}
+    g, d, gl, dl = TrainMixin.split_losses(vals)
+    assert list(g) == ['gen_l1_loss', 'gen_kl_loss'] and list(d) == ['discrim_video_sn_gan_loss', 'discrim_video_sn_vae_gan_loss']
+    assert gl == 2.5 and dl == 1.0
+
+
 def test_concat_spec_channel_maps():
     from video_prediction_b200.models.savp_model import ConcatSpec
     sp = ConcatSpec([('image', 3), ('first', 3), ('z', 8)])

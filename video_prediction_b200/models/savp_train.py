@@ -680,6 +680,17 @@ class TrainMixin(object):
         self._scal_host[2] = klw / float(self.S * self.B)
         self.step_scalars.copy_(self._scal_host, non_blocking=True)
 
+    @staticmethod
+    def split_losses(vals):
+        """name -> value dict of one step -> (g_losses, d_losses, g_loss, d_loss) as the reference exposes them
+        (base_model.py:461-465: the totals are the sums of the already-weighted terms)."""
+        g = OrderedDict((k, v) for k, v in vals.items() if k.startswith('gen_') and v != 0.0)
+        d = OrderedDict((k, v) for k, v in vals.items() if k.startswith('discrim_') and v != 0.0)
+        return g, d, float(sum(g.values())), float(sum(d.values()))
+
     def losses(self):
+        """Weighted loss terms of the last step (device -> host read); also refreshes g_losses / d_losses / g_loss / d_loss."""
         vals = self.loss_vals.detach().cpu().numpy()
-        return OrderedDict((k, float(v)) for k, v in zip(LOSS_SLOTS, vals))
+        out = OrderedDict((k, float(v)) for k, v in zip(LOSS_SLOTS, vals))
+        self.g_losses, self.d_losses, self.g_loss, self.d_loss = self.split_losses(out)
+        return out
