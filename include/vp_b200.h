@@ -210,9 +210,12 @@ int vp_sample_z_bwd(const float* mu, const float* lss, const float* eps, const f
 
 /* ---- losses (losses.py:6-67): out[0] += value; optional gradient = grad_scale * d value / d pred -------- */
 int vp_pixel_loss(const float* pred, int pred_cstride, const float* target, int target_cstride, float* dpred,
-                  int dpred_cstride, long long rows, int c, int mode /*0 = L1, 1 = L2*/, long long mean_count,
+                  int dpred_cstride, long long rows, int c, int mode /*bit 0: 0 = L1, 1 = L2; bit 1: dpred += instead of =*/, long long mean_count,
                   float grad_scale, float* out, vp_stream_t stream);
 int vp_lsgan_loss(const float* logits, float label, int n, float grad_scale, float* dlogits, float* out, vp_stream_t stream);
+/* losses.gan_loss (losses.py:29-54) for labels in {0,1}: kind 0 LSGAN, 1 GAN (sigmoid cross-entropy), 2 SNGAN (softplus) */
+int vp_gan_loss(const float* logits, float label, int n, float grad_scale, int kind, float* dlogits, float* out,
+                vp_stream_t stream);
 int vp_kl_loss(const float* mu, const float* lss, int rows, int nz, float* out, vp_stream_t stream);
 /* cosine_distance(a, b) over rows of c channels; da += grad (gradient w.r.t. a only) */
 int vp_cosine_distance(const float* a, const float* b, float* da, long long rows, int c, float grad_scale, float* out,

@@ -98,7 +98,65 @@ def _nhwc(x):
     return x.permute(0, 2, 3, 1)
 
 
-def conv2d_tf(x, kernel, strides=(1, 1), padding='SAME', bias=None):
+# ---- optional emulation of the CUDA path's tensor-core arithmetic --------------------------------
+# The sm_100a engine feeds fp32 operands to tcgen05.mma kind::tf32, which reads only the top 19 bits
+# of each operand (sign, 8 exponent, 10 mantissa bits) and accumulates in fp32.  With
+# `set_tf32_emulation('trunc')` every convolution of the oracle (forward AND its autograd backward:
+# dgrad sees tf32(dy) x tf32(W), wgrad sees tf32(x) x tf32(dy)) quantises its operands the same way, so a
+# difference between the CUDA path and this oracle that is NOT explained by operand rounding shows up
+# at fp32-summation-order level.  Default None = the reference's plain fp32 arithmetic.
+_TF32 = dict(mode=None, exempt=())
+
+
+def set_tf32_emulation(mode, exempt=()):
+    """mode: None | 'trunc' (drop the low 13 mantissa bits) | 'rna' (round to nearest, ties away).
+    exempt: iterable of substrings; a conv called with a `tag` containing one of them stays exact
+    (layers the CUDA path runs on fp32 CUDA cores)."""
+    assert mode in (None, 'trunc', 'rna')
+    _TF32['mode'] = mode
+    _TF32['exempt'] = tuple(exempt)
+
+
+def tf32_quantize(x, mode=None):
+    mode = mode or _TF32['mode']
+    if mode is None:
+        return x
+    x32 = x.detach().to(torch.float32).contiguous()
+    xi = x32.view(torch.int32)
+    if mode == 'rna':
+        xi = (xi + 0x1000) & ~0x1FFF
+    else:
+        xi = xi & ~0x1FFF
+    return xi.view(torch.float32).to(x.dtype)
+
+
+class _QuantConv(torch.autograd.Function):
+    """y = fn(q(x), q(w)); backward re-runs fn on the quantised operands with q(dy) as the cotangent."""
+
+    @staticmethod
+    def forward(ctx, x, w, fn):
+        ctx.fn = fn
+        ctx.save_for_backward(x, w)
+        return fn(tf32_quantize(x), tf32_quantize(w))
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w = ctx.saved_tensors
+        with torch.enable_grad():
+            xq = tf32_quantize(x).requires_grad_(True)
+            wq = tf32_quantize(w).requires_grad_(True)
+            y = ctx.fn(xq, wq)
+            dx, dw = torch.autograd.grad(y, (xq, wq), tf32_quantize(dy))
+        return dx, dw, None
+
+
+def _conv_op(fn, x, w, tag=''):
+    if _TF32['mode'] is None or tag.startswith('exact:') or any(e in tag for e in _TF32['exempt']):
+        return fn(x, w)
+    return _QuantConv.apply(x, w, fn)
+
+
+def conv2d_tf(x, kernel, strides=(1, 1), padding='SAME', bias=None, tag=''):
     """tf.nn.conv2d on NHWC input with HWIO filter (cross-correlation).  ops.py:494-550."""
     kh, kw = kernel.shape[:2]
     sh, sw = strides
@@ -111,17 +169,17 @@ def conv2d_tf(x, kernel, strides=(1, 1), padding='SAME', bias=None):
         xn = F.pad(xn, (kw - 1, kw - 1, kh - 1, kh - 1))
     elif padding != 'VALID':
         raise ValueError(padding)
-    y = F.conv2d(xn, kernel.permute(3, 2, 0, 1), stride=(sh, sw))
+    y = _conv_op(lambda a, k: F.conv2d(a, k.permute(3, 2, 0, 1), stride=(sh, sw)), xn, kernel, tag)
     y = _nhwc(y)
     if bias is not None:
         y = y + bias
     return y
 
 
-def conv3d_tf_valid(x, kernel, strides, bias=None):
+def conv3d_tf_valid(x, kernel, strides, bias=None, tag=''):
     """tf.nn.conv3d VALID on NDHWC input with [kt,kh,kw,Cin,Cout] filter.  ops.py:764-777."""
     xn = x.permute(0, 4, 1, 2, 3)
-    y = F.conv3d(xn, kernel.permute(4, 3, 0, 1, 2), stride=tuple(strides))
+    y = _conv_op(lambda a, k: F.conv3d(a, k.permute(4, 3, 0, 1, 2), stride=tuple(strides)), xn, kernel, tag)
     y = y.permute(0, 2, 3, 4, 1)
     if bias is not None:
         y = y + bias
@@ -179,7 +237,7 @@ def upsampled_kernel(kernel):
     kh, kw, ci, co = kernel.shape
     b2 = torch.tensor(bilinear_kernel_2x(), dtype=kernel.dtype, device=kernel.device)
     kt = kernel.permute(0, 1, 3, 2).reshape(kh, kw, 1, co * ci)       # kernel_reshaped
-    up = conv2d_tf(b2[None, :, :, None], kt, padding='FULL')           # [1,6,6,co*ci]
+    up = conv2d_tf(b2[None, :, :, None], kt, padding='FULL', tag='exact:weight-prep')   # [1,6,6,co*ci]
     return up.reshape(up.shape[1], up.shape[2], co, ci)
 
 
@@ -187,7 +245,7 @@ def upsample_conv2d(x, kernel, bias):
     """ops.py:643-719 with strides=(2,2): conv2d_transpose(x, kernel_up, stride 2, SAME)+bias.
     conv2d_transpose == gradient of the stride-2 SAME conv (k=6 on 2H -> pad 2/2)."""
     kup = upsampled_kernel(kernel)                                     # [6,6,co,ci]
-    y = F.conv_transpose2d(_nchw(x), kup.permute(3, 2, 0, 1), stride=2, padding=2)
+    y = _conv_op(lambda a, k: F.conv_transpose2d(a, k.permute(3, 2, 0, 1), stride=2, padding=2), _nchw(x), kup)
     return _nhwc(y) + bias
 
 
@@ -621,7 +679,7 @@ def video_sn_discriminator(V, scope, clips, ndf, u_out=None):
         if u_out is not None:
             u_out['%s/%s/conv3d/u' % (scope, name)] = u1.detach()
         xp = F.pad(x, (0, 0, 1, 1, 1, 1, 1, 1))                              # networks.py:76-81
-        x = lrelu(conv3d_tf_valid(xp, Wb, strides, b), 0.1)
+        x = lrelu(conv3d_tf_valid(xp, Wb, strides, b, tag='%s/%s' % (scope, name)), 0.1)
         feats.append(x)
     flat = x.reshape(x.shape[0], -1)
     W = V.get('%s/sn_fc4/dense/kernel' % scope, (flat.shape[1], 1))

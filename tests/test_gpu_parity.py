@@ -125,7 +125,7 @@ def test_savp_training_step_matches_oracle(Model):
     binp = {'images': inputs['images'].permute(1, 0, 2, 3, 4)}
     model.build_graph(binp)
     model.global_step = step
-    model.train_step(binp, noise)
+    model.train_step(binp, noise, sampling=False)
     torch.cuda.synchronize()
     lv = model.losses()
     ref_l = dict(res['g_losses'])

@@ -73,13 +73,71 @@ def test_param_specs_match_oracle_names_and_shapes():
             assert tuple(shape) == tuple(ref[k].shape), k
 
 
-def test_loss_dict_split_matches_reference_attributes():
-    from video_prediction_b200.models.savp_train import TrainMixin
-    vals = {'gen_l1_loss': 2.0, 'gen_kl_loss': 0.5, 'gen_l2_loss': 0.0, 'discrim_video_sn_gan_loss': 0.25,
-            'discrim_video_sn_vae_gan_loss': 0.75}
-    g, d, gl, dl = TrainMixin.split_losses(vals)
-    assert list(g) == ['gen_l1_loss', 'gen_kl_loss'] and list(d) == ['discrim_video_sn_gan_loss', 'discrim_video_sn_vae_gan_loss']
-    assert gl == 2.5 and dl == 1.0
+def test_loss_totals_are_weighted_sums_like_the_reference():
+    # base_model.py:461: total = accumulate_n(loss * weight); the per-term dicts stay unweighted.  Checked against the
+    # oracle's generator_losses / total_loss on the same (unweighted) values, with the annealed KL weight at step 75000.
+    from oracle import savp_oracle as O
+    from video_prediction_b200.models import SAVPVideoPredictionModel
+    hk = dict(context_frames=2, sequence_length=12, l1_weight=100.0, l2_weight=0.5, kl_weight=1.0, video_sn_gan_weight=0.1,
+              video_sn_vae_gan_weight=0.1, vae_gan_feature_cdist_weight=10.0)
+    m = SAVPVideoPredictionModel(mode='train', hparams_dict=hk)
+    vals = {'gen_l1_loss': 0.02, 'gen_l2_loss': 0.3, 'gen_kl_loss': 0.5, 'gen_video_sn_gan_loss': 0.9,
+            'gen_video_sn_vae_gan_loss': 0.8, 'gen_video_sn_vae_gan_feature_cdist_loss': 0.07,
+            'gen_video_sn_gan_feature_cdist_loss': 0.0, 'discrim_video_sn_gan_loss': 0.25, 'discrim_video_sn_vae_gan_loss': 0.75}
+    w = m.loss_weights(step=75000)
+    g, d, gl, dl = m.split_losses(vals, w)
+    assert 'gen_video_sn_gan_feature_cdist_loss' not in g          # weight 0 -> the reference never creates the term
+    assert g['gen_l1_loss'] == 0.02 and d['discrim_video_sn_gan_loss'] == 0.25
+    hp = O.make_hparams(**hk)
+    ref_g = 100.0 * 0.02 + 0.5 * 0.3 + O.kl_weight(hp, 75000) * 0.5 + 0.1 * 0.9 + 0.1 * 0.8 + 10.0 * 0.07
+    assert abs(gl - ref_g) < 1e-9 and abs(dl - (0.1 * 0.25 + 0.1 * 0.75)) < 1e-12
+    assert m.loss_weights(step=0)['gen_kl_loss'] == 0.0            # KL weight is annealed from 0 (base_model.py:312-315)
+
+
+def test_scheduled_sampling_schedule_and_mask():
+    # savp_model.py:309-334: inverse sigmoid k / (k + exp((step - start) / k)), 1.0 before start, all-False below 1e-3,
+    # nothing in test mode or with schedule 'none'; linear: 1 - (clip(step) - start) / (end - start)
+    import math
+    from video_prediction_b200.models import SAVPVideoPredictionModel
+    hk = dict(context_frames=2, sequence_length=12)
+    m = SAVPVideoPredictionModel(mode='train', hparams_dict=hk)
+    assert abs(m.schedule_sampling_prob(0) - 900.0 / 901.0) < 1e-12
+    assert abs(m.schedule_sampling_prob(9000) - 900.0 / (900.0 + math.exp(10.0))) < 1e-12
+    m.B, m.NB, m.S = 4, 8, 11
+    m.global_step = 0
+    mask = m.draw_scheduled_sampling()
+    assert tuple(mask.shape) == (9, 8) and mask.float().mean() > 0.9
+    m.global_step = 20000                                         # prob = 900 / (900 + e^22.2) < 1e-3 -> deterministic
+    assert m.draw_scheduled_sampling() is None
+    m.global_step = 0
+    a, m.rank = m.draw_scheduled_sampling(), 1
+    m.hparams.set_hparam('schedule_sampling_k', 1.0)              # prob(0) = 0.5: masks of different ranks must differ
+    m.rank = 0
+    r0 = m.draw_scheduled_sampling()
+    m.rank = 1
+    assert not torch.equal(r0, m.draw_scheduled_sampling())
+    t = SAVPVideoPredictionModel(mode='test', hparams_dict=hk)
+    assert t.schedule_sampling_prob(0) == 0.0
+    lin = SAVPVideoPredictionModel(mode='train', hparams_dict=dict(hk, schedule_sampling='linear', schedule_sampling_steps=(100, 300)))
+    assert lin.schedule_sampling_prob(0) == 1.0 and lin.schedule_sampling_prob(200) == 0.5 and lin.schedule_sampling_prob(999) == 0.0
+    none = SAVPVideoPredictionModel(mode='train', hparams_dict=dict(hk, schedule_sampling='none'))
+    assert none.schedule_sampling_prob(0) == 0.0
+
+
+def test_accepted_but_unbuilt_hparams_are_refused():
+    from video_prediction_b200.models import SAVPVideoPredictionModel
+    base = dict(context_frames=2, sequence_length=12)
+    for bad in (dict(joint_gan_optimization=True), dict(state_weight=1.0), dict(tv_weight=0.1), dict(z_l1_weight=1.0),
+                dict(use_same_discriminator=True), dict(dilation_rate=(2, 2)), dict(gan_feature_l2_weight=1.0),
+                dict(conv_rnn='gru'), dict(transformation='dna'), dict(learn_prior=True)):
+        m = SAVPVideoPredictionModel(mode='train', hparams_dict=dict(base, **bad))
+        with pytest.raises(NotImplementedError):
+            m._check_supported()
+    with pytest.raises(ValueError):
+        SAVPVideoPredictionModel(mode='train', hparams_dict=dict(base, gan_loss_type='WGAN'))._check_supported()
+    for ok in (dict(gan_loss_type='GAN'), dict(gan_loss_type='SNGAN'), dict(l1_weight=1.0, l2_weight=1.0),
+               dict(schedule_sampling='linear')):
+        SAVPVideoPredictionModel(mode='train', hparams_dict=dict(base, **ok))._check_supported()
 
 
 def test_concat_spec_channel_maps():

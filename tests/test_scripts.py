@@ -1,0 +1,102 @@
+"""The reference's command lines run through scripts/train.py / scripts/generate.py (CPU part: argument set, option
+resolution, side files; GPU part: three optimisation steps, a checkpoint, and sampling from it)."""
+import json
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, 'scripts'))
+
+REFERENCE_TRAIN_FLAGS = ['--input_dir', '--val_input_dir', '--logs_dir', '--output_dir', '--output_dir_postfix', '--checkpoint',
+                         '--resume', '--dataset', '--dataset_hparams', '--dataset_hparams_dict', '--model', '--model_hparams',
+                         '--model_hparams_dict', '--summary_freq', '--image_summary_freq', '--eval_summary_freq',
+                         '--accum_eval_summary_freq', '--progress_freq', '--save_freq', '--aggregate_nccl', '--gpu_mem_frac', '--seed']
+REFERENCE_GENERATE_FLAGS = ['--input_dir', '--results_dir', '--results_gif_dir', '--results_png_dir', '--output_gif_dir',
+                            '--output_png_dir', '--checkpoint', '--mode', '--dataset', '--dataset_hparams', '--model',
+                            '--model_hparams', '--batch_size', '--num_samples', '--num_epochs', '--num_stochastic_samples',
+                            '--gif_length', '--fps', '--gpu_mem_frac', '--seed']
+
+
+def test_train_and_generate_accept_the_reference_argument_set(tmp_path):
+    import train
+    import generate
+    flags = {a.option_strings[0]: a for a in train.build_parser()._actions if a.option_strings}
+    assert set(REFERENCE_TRAIN_FLAGS) <= set(flags)                          # /root/reference/scripts/train.py:30-61
+    assert flags['--summary_freq'].default == 1000 and flags['--save_freq'].default == 5000 and flags['--progress_freq'].default == 100
+    gflags = {a.option_strings[0]: a for a in generate.build_parser()._actions if a.option_strings}
+    assert set(REFERENCE_GENERATE_FLAGS) <= set(gflags)                      # /root/reference/scripts/generate.py:19-49
+    assert gflags['--batch_size'].default == 8 and gflags['--num_stochastic_samples'].default == 5 and gflags['--seed'].default == 7
+    # the README's training command line (bair_action_free / ours_savp), with the synthetic dataset
+    hp = tmp_path / 'model_hparams.json'
+    hp.write_text(json.dumps(dict(batch_size=16, lr=0.0002, beta1=0.5, l1_weight=100.0, kl_weight=1.0, video_sn_vae_gan_weight=0.1,
+                                  video_sn_gan_weight=0.1, vae_gan_feature_cdist_weight=10.0)))
+    args = train.build_parser().parse_args(['--input_dir', 'data/bair', '--dataset', 'synthetic', '--model', 'savp',
+                                            '--model_hparams_dict', str(hp), '--model_hparams', 'kernel_size=[5,5],lr=0.001',
+                                            '--logs_dir', str(tmp_path)])
+    d, m = train.resolve_options(args)
+    assert m['l1_weight'] == 100.0 and d == {}
+    assert args.output_dir == os.path.join(str(tmp_path), 'model.savp.kernel_size.5..5.lr.0.001')   # train.py:69-84
+    with pytest.raises(ValueError):
+        a = train.build_parser().parse_args(['--input_dir', 'x', '--resume', '--checkpoint', 'y'])
+        train.resolve_options(a)
+    with pytest.raises(ValueError):
+        generate.resolve_options(generate.build_parser().parse_args(['--input_dir', 'x']))     # dataset required w/o checkpoint
+
+
+def test_dataset_registry_and_synthetic_batches():
+    from video_prediction_b200 import datasets
+    with pytest.raises(ValueError, match='Invalid dataset'):
+        datasets.get_dataset_class('bogus')
+    with pytest.raises(NotImplementedError):
+        datasets.get_dataset_class('bair')
+    DS = datasets.get_dataset_class('synthetic')
+    ds = DS('ignored', mode='val', num_epochs=1, seed=3, hparams='sequence_length=6,action_dim=4,num_examples=8')
+    assert ds.hparams.long_sequence_length == 6 and ds.hparams.context_frames == 2
+    b = ds.make_batch(4)
+    assert b['images'].shape == (4, 6, 64, 64, 3) and b['images'].dtype == np.float32 and b['actions'].shape == (4, 5, 4)
+    assert 0.0 <= b['images'].min() and b['images'].max() <= 1.0
+    ds.make_batch(4)
+    with pytest.raises(StopIteration):
+        ds.make_batch(4)
+    with pytest.raises(ValueError):
+        DS('x', mode='bad')
+
+
+@pytest.mark.gpu
+def test_train_three_steps_checkpoint_resume_and_generate(tmp_path):
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip('no CUDA device')
+    import train
+    import generate
+    out = str(tmp_path / 'run')
+    common = ['--input_dir', 'none', '--dataset', 'synthetic', '--dataset_hparams', 'sequence_length=6,num_examples=8',
+              '--model', 'savp', '--output_dir', out, '--progress_freq', '1', '--save_freq', '3', '--seed', '1']
+    hp = 'batch_size=2,max_steps=3,clip_length=4,lr=0.0002,beta1=0.5,l1_weight=100.0,kl_weight=1.0,video_sn_vae_gan_weight=0.1,' \
+         'video_sn_gan_weight=0.1,vae_gan_feature_cdist_weight=10.0'
+    model = train.main(common + ['--model_hparams', hp])
+    assert model.global_step == 3 and model.g_loss is not None and np.isfinite(model.g_loss) and np.isfinite(model.d_loss)
+    assert set(model.g_losses) >= {'gen_l1_loss', 'gen_video_sn_gan_loss'} and 'gen_kl_loss' not in model.g_losses  # KL weight 0 at step 2
+    for f in ('options.json', 'dataset_hparams.json', 'model_hparams.json', 'checkpoint', 'model-3.npz'):
+        assert os.path.exists(os.path.join(out, f)), f
+    w = model.get_params()['generator/rnn/savp_cell/h0/conv_pool2d/kernel']
+    # resume: options / hparams come from the checkpoint directory, training continues at step 3
+    model2 = train.main(['--input_dir', 'none', '--output_dir', out, '--resume', '--model_hparams', 'max_steps=4',
+                         '--progress_freq', '1', '--save_freq', '0'])
+    assert model2.global_step == 4 and model2.g_adam_t == 4
+    assert model2.hparams.l1_weight == 100.0 and model2.hparams.clip_length == 4
+    # sampling from the checkpoint
+    n = generate.main(['--input_dir', 'none', '--checkpoint', out, '--results_dir', str(tmp_path / 'results'), '--batch_size', '2',
+                       '--num_samples', '2', '--num_stochastic_samples', '2', '--mode', 'test'])
+    assert n == 2
+    png_dir = str(tmp_path / 'results' / 'run')
+    pngs = [p for p in os.listdir(png_dir) if p.endswith('.png')]
+    assert len(pngs) == 2 * 2 * 4                                           # samples x stochastic samples x future frames
+    a = np.load(os.path.join(png_dir, 'gen_image_00000_00.npy'))
+    b = np.load(os.path.join(png_dir, 'gen_image_00000_01.npy'))
+    assert a.shape == (6, 64, 64, 3) and a.dtype == np.uint8
+    assert np.array_equal(a[:2], b[:2]) and not np.array_equal(a[2:], b[2:])    # same context, different noise draws
+    del w

@@ -617,13 +617,15 @@ __global__ void __launch_bounds__(256) pixel_loss_kernel(const float* __restrict
     const int c = static_cast<int>(idx % C);
     const long long r = idx / C;
     const float d = pred[r * ps + c] - target[r * ts + c];
-    if (mode == 0) {
+    float g;
+    if ((mode & 1) == 0) {
       s[0] += fabsf(d);
-      if (dpred) dpred[r * dps + c] = gscale * inv_count * (d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f));
+      g = gscale * inv_count * (d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f));
     } else {
       s[0] += d * d;
-      if (dpred) dpred[r * dps + c] = gscale * inv_count * 2.f * d;
+      g = gscale * inv_count * 2.f * d;
     }
+    if (dpred) dpred[r * dps + c] = (mode & 2) ? dpred[r * dps + c] + g : g;   // bit 1: accumulate (l1 and l2 together)
   }
   bsum<1>(s, scratch);
   if (threadIdx.x == 0) atomicAdd(out, s[0] * inv_count);
@@ -636,6 +638,29 @@ __global__ void lsgan_loss_kernel(const float* __restrict__ logits, float label,
     const float d = logits[i] - label;
     s += d * d;
     if (dlogits) dlogits[i] = gscale * 2.f * d / n;
+  }
+  __shared__ float scratch[32];
+  float v[1] = {s};
+  bsum<1>(v, scratch);
+  if (threadIdx.x == 0) atomicAdd(out, v[0] / n);
+}
+// losses.gan_loss for labels in {0, 1}: kind 0 = LSGAN mean (l - y)^2; kind 1 = GAN = mean sigmoid-cross-entropy(l, y);
+// kind 2 = SNGAN = mean softplus(l) (y = 0) / softplus(-l) (y = 1) -- numerically the same function as kind 1 for y in {0,1}.
+// dlogits = gscale * d value / d logits.
+__global__ void gan_loss_kernel(const float* __restrict__ logits, float label, int n, float gscale, int kind,
+                                float* __restrict__ dlogits, float* __restrict__ out) {
+  float s = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const float x = logits[i];
+    if (kind == 0) {
+      const float d = x - label;
+      s += d * d;
+      if (dlogits) dlogits[i] = gscale * 2.f * d / n;
+    } else {
+      // max(x, 0) - x*y + log(1 + exp(-|x|))   (tf.nn.sigmoid_cross_entropy_with_logits)
+      s += fmaxf(x, 0.f) - x * label + log1pf(expf(-fabsf(x)));
+      if (dlogits) dlogits[i] = gscale * (1.f / (1.f + expf(-x)) - label) / n;
+    }
   }
   __shared__ float scratch[32];
   float v[1] = {s};
@@ -875,6 +900,14 @@ extern "C" int vp_lsgan_loss(const float* logits, float label, int n, float grad
                              vp_stream_t stream) {
   lsgan_loss_kernel<<<1, 256, 0, as_stream(stream)>>>(logits, label, n, grad_scale, dlogits, out);
   return check_launch("lsgan_loss_kernel");
+}
+
+extern "C" int vp_gan_loss(const float* logits, float label, int n, float grad_scale, int kind, float* dlogits, float* out,
+                           vp_stream_t stream) {
+  if (kind < 0 || kind > 2) return set_error("vp_gan_loss: kind must be 0 (LSGAN), 1 (GAN) or 2 (SNGAN)");
+  if (label != 0.f && label != 1.f && kind != 0) return set_error("vp_gan_loss: GAN / SNGAN need a label in {0, 1}");
+  gan_loss_kernel<<<1, 256, 0, as_stream(stream)>>>(logits, label, n, grad_scale, kind, dlogits, out);
+  return check_launch("gan_loss_kernel");
 }
 
 extern "C" int vp_kl_loss(const float* mu, const float* lss, int rows, int nz, float* out, vp_stream_t stream) {

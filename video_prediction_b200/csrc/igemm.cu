@@ -788,7 +788,7 @@ static int conv_igemm_impl(const vp_tensor* in, const vp_conv_geom* g, const flo
   if (in->n != out->n) return set_error("vp_conv_igemm: batch mismatch");
   if (split_k > 1 && act != VP_ACT_NONE) return set_error("vp_conv_igemm: split_k needs act NONE");
   if (aux_y && split_k > 1) return set_error("vp_conv_igemm: the fused activation gradient needs split_k <= 1");
-  static IgemmArgs A;  // large POD; host-side scratch (calls are serialized by the Python GIL / caller)
+  static thread_local IgemmArgs A;  // large POD; per-thread host-side scratch (ctypes releases the GIL during calls)
   std::memset(&A, 0, sizeof(A));
   const int lat[4] = {out->w, out->h, out->d, out->n};
   if (build_geometry(A, g, in, 128, lat)) return -1;
@@ -915,7 +915,7 @@ extern "C" int vp_conv_wgrad(const vp_tensor* x, const vp_tensor* dy, const vp_c
   if (check_tensor(x, "vp_conv_wgrad(x)") || check_tensor(dy, "vp_conv_wgrad(dy)")) return -1;
   if (!g || !dwpacked) return set_error("vp_conv_wgrad: null argument");
   if (n_pad % 16 || dy->c > n_pad || kc * 32 < x->c) return set_error("vp_conv_wgrad: bad n_pad / kc");
-  static IgemmArgs A;
+  static thread_local IgemmArgs A;
   std::memset(&A, 0, sizeof(A));
   // conv:  dW[r] += sum_o dy[o]^T x[s*o+r-p]   (x shifted, lattice = dy)
   // tconv: dW[r] += sum_o dy[s*o+r-p]^T x[o]   (dy shifted, lattice = x); as a gather this is a

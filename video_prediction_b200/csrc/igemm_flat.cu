@@ -224,7 +224,7 @@ extern "C" int vp_conv_flat(const vp_tensor* in, int valid_h, int valid_w, const
   const int left = g->transposed ? (g->kw - 1 - g->pw) : g->pw, right = g->transposed ? g->pw : (g->kw - 1 - g->pw);
   if (Hp - valid_h < std::max(up, down) || P - valid_w < std::max(left, right))
     return set_error("vp_conv_flat: padding gap smaller than the filter reach");
-  static FlatArgs A;
+  static thread_local FlatArgs A;
   std::memset(&A, 0, sizeof(A));
   A.q_total = in->n * Hp * P; A.Hp = Hp; A.P = P; A.H = valid_h; A.W = valid_w;
   A.kc = kc; A.n_pad = n_pad;

@@ -40,7 +40,7 @@ def lib():
     global _LIB
     if _LIB is None:
         path = _build.LIB_PATH
-        if not os.path.exists(path):
+        if _build.needs_build():       # missing, or older than any source under csrc/ / the header
             path = _build.build()
         _LIB = C.CDLL(path)
         _LIB.vp_last_error.restype = C.c_char_p
@@ -285,6 +285,13 @@ def pixel_loss(pred_addr, pred_cs, target_addr, target_cs, dpred_addr, dpred_cs,
 
 def lsgan_loss(logits, label, n, grad_scale, dlogits, out):
     check(lib().vp_lsgan_loss(ptr(logits), _f(label), n, _f(grad_scale), ptr(dlogits), ptr(out), stream_ptr()))
+
+
+GAN_KINDS = {'LSGAN': 0, 'GAN': 1, 'SNGAN': 2}
+
+
+def gan_loss(logits, label, n, grad_scale, kind, dlogits, out):
+    check(lib().vp_gan_loss(ptr(logits), _f(label), n, _f(grad_scale), GAN_KINDS[kind], ptr(dlogits), ptr(out), stream_ptr()))
 
 
 def kl_loss(mu, lss, rows, nz, out):

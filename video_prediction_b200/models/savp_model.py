@@ -20,6 +20,7 @@ from collections import OrderedDict
 import numpy as np
 import torch
 
+from .. import dp
 from .. import lib as L
 from .base_model import VideoPredictionModel
 from .savp_train import TrainMixin
@@ -134,6 +135,8 @@ class SAVPVideoPredictionModel(TrainMixin, VideoPredictionModel):
         self.grads = None
         self.built = False
         self.world_size = 1
+        self.rank = 0
+        self.random_seed = 0
         self.use_cuda_graph = False      # train_step(): capture the device part of the step once, then replay it
         self._pending_params = None
         self.g_adam_t = self.d_adam_t = 0
@@ -166,11 +169,16 @@ class SAVPVideoPredictionModel(TrainMixin, VideoPredictionModel):
         return super(SAVPVideoPredictionModel, self).parse_hparams(hparams_dict, hparams)
 
     def _check_supported(self):
+        """Every hparam the reference acts on is either implemented here or refused: nothing is accepted and ignored."""
         hp = self.hparams
         if hp.where_add not in ('input', 'all', 'middle'):
             raise ValueError('Invalid where_add %s' % hp.where_add)  # savp_model.py:176-177
+        if hp.schedule_sampling not in ('none', 'inverse_sigmoid', 'linear'):
+            raise NotImplementedError('schedule_sampling=%r' % (hp.schedule_sampling,))     # savp_model.py:332-333
+        if hp.gan_loss_type not in ('LSGAN', 'GAN', 'SNGAN'):
+            raise ValueError('Unknown GAN loss type %s' % hp.gan_loss_type)                 # losses.py:52-53
         unsupported = []
-        for key, want in (('where_add', 'all'), ('use_tile_concat', True), ('transformation', 'cdna'),
+        for key, want in (('where_add', 'all'), ('use_tile_concat', True),
                           ('conv_rnn', 'lstm'), ('rnn', 'lstm'), ('conv_rnn_norm_layer', 'instance'),
                           ('norm_layer', 'instance'), ('downsample_layer', 'conv_pool2d'),
                           ('upsample_layer', 'upsample_conv2d'), ('activation_layer', 'relu'), ('last_frames', 1),
@@ -179,9 +187,23 @@ class SAVPVideoPredictionModel(TrainMixin, VideoPredictionModel):
                           ('context_images_background', False), ('generate_scratch_image', True),
                           ('dependent_mask', True), ('use_e_rnn', False), ('learn_prior', False),
                           ('learn_initial_state', False), ('ablation_conv_rnn_norm', False), ('ablation_rnn', False),
-                          ('use_rnn_z', True)):
+                          ('use_rnn_z', True), ('joint_gan_optimization', False), ('use_same_discriminator', False),
+                          ('repeat', 1)):
             if getattr(hp, key) != want:
                 unsupported.append('%s=%r' % (key, getattr(hp, key)))
+        if hp.transformation not in ('cdna',):
+            unsupported.append('transformation=%r' % (hp.transformation,))
+        if tuple(hp.dilation_rate) != (1, 1):
+            unsupported.append('dilation_rate=%r' % (hp.dilation_rate,))
+        if self.mode == 'train':
+            # loss terms of base_model.py:733-852 that are not built: refuse instead of silently dropping them
+            for key in ('vgg_cdist_weight', 'feature_l2_weight', 'ae_l2_weight', 'state_weight', 'tv_weight', 'z_l1_weight',
+                        'images_sn_gan_weight', 'images_sn_vae_gan_weight', 'gan_feature_l2_weight',
+                        'vae_gan_feature_l2_weight'):
+                if getattr(hp, key):
+                    unsupported.append('%s=%r' % (key, getattr(hp, key)))
+            if hp.kl_weight and hp.kl_anneal not in ('none', 'sigmoid', 'linear'):
+                unsupported.append('kl_anneal=%r' % (hp.kl_anneal,))
         if unsupported:
             raise NotImplementedError('hparams outside the B200 hot path (SURVEY.md 8f): ' + ', '.join(unsupported))
 
@@ -292,6 +314,18 @@ class SAVPVideoPredictionModel(TrainMixin, VideoPredictionModel):
         L.lib()  # fail loudly if the CUDA library is missing
         self._check_supported()
         hp = self.hparams
+        # data parallelism (base_model.py:517-646): one process per GPU.  torchrun's env gives rank / world; with the
+        # reference's `num_gpus` > 1 the batch in `inputs` is the GLOBAL batch and every rank takes its shard
+        # (tf.split of the global batch, :523-527); with num_gpus <= 1 under torchrun each rank feeds its own batch.
+        self.rank, _local, self.world_size = dp.init_from_env()
+        if self.num_gpus and self.num_gpus > 1:
+            if self.world_size != self.num_gpus:
+                raise ValueError('num_gpus=%d needs %d processes (torchrun --nproc-per-node), found WORLD_SIZE=%d'
+                                 % (self.num_gpus, self.num_gpus, self.world_size))
+            self._shard = dp.shard_batch(int(inputs['images'].shape[0]), self.rank, self.world_size)
+            inputs = {k: v[self._shard] for k, v in inputs.items()}
+        else:
+            self._shard = None
         self.device = torch.device('cuda', torch.cuda.current_device())
         imgs = inputs['images']
         B, T, H, W, C = [int(s) for s in imgs.shape]
@@ -317,6 +351,9 @@ class SAVPVideoPredictionModel(TrainMixin, VideoPredictionModel):
         if self._pending_params is not None:
             self._apply_params(self._pending_params)
             self._pending_params = None
+        if self.world_size > 1:     # replicas start from rank 0's variables (post_init_ops, base_model.py:640-646)
+            dp.broadcast_state([self.g_flat, self.d_flat] + [v for k, v in self.params.items() if k.endswith('/u')])
+        self._allreduce = dp.make_allreduce()
         self._build_generator()
         if self.mode == 'train':
             self._build_discriminator()
@@ -391,6 +428,81 @@ class SAVPVideoPredictionModel(TrainMixin, VideoPredictionModel):
         self._apply_params(values)
         if self.built:
             self._pack_all()
+
+    # ------------------------------------------------------------------ checkpoints (base_model.py:229-246, train.py:242, 349)
+    def saveable_state(self):
+        """What tf.train.Saver(model.saveable_variables) stores: global_step + every variable (reference names) + both
+        optimizers' slots."""
+        st = OrderedDict(global_step=np.int64(self.global_step))
+        for k, v in self.params.items():
+            st['var/' + k] = v.detach().cpu().numpy()
+        if self.mode == 'train':
+            for nm in ('g_m', 'g_v', 'd_m', 'd_v'):
+                st['adam/' + nm] = getattr(self, nm).detach().cpu().numpy()
+            st['adam/t'] = np.array([self.g_adam_t, self.d_adam_t], np.int64)
+        return st
+
+    def save(self, output_dir, prefix='model'):
+        """Writes `<output_dir>/<prefix>-<global_step>.npz` (+ a `checkpoint` text file naming the latest, as tf.train.Saver
+        does), keeping the two most recent (train.py:231 max_to_keep=2).  Returns the path."""
+        import os
+        os.makedirs(output_dir, exist_ok=True)
+        path = os.path.join(output_dir, '%s-%d.npz' % (prefix, self.global_step))
+        np.savez(path, **self.saveable_state())
+        with open(os.path.join(output_dir, 'checkpoint'), 'w') as f:
+            f.write('model_checkpoint_path: "%s"\n' % os.path.basename(path))
+        old = sorted((p for p in os.listdir(output_dir) if p.startswith(prefix + '-') and p.endswith('.npz')),
+                     key=lambda p: int(p[len(prefix) + 1:-4]))
+        for p in old[:-2]:
+            os.remove(os.path.join(output_dir, p))
+        return path
+
+    @staticmethod
+    def latest_checkpoint(checkpoint):
+        """A checkpoint name, or a directory holding a `checkpoint` file (tf.train.latest_checkpoint)."""
+        import os
+        if checkpoint and os.path.isdir(checkpoint):
+            idx = os.path.join(checkpoint, 'checkpoint')
+            if not os.path.exists(idx):
+                return None
+            with open(idx) as f:
+                name = f.readline().split('"')[1]
+            return os.path.join(checkpoint, name)
+        return checkpoint
+
+    def restore(self, sess=None, checkpoints=None, restore_to_checkpoint_mapping=None):
+        """base_model.py:229-246.  `sess` is accepted for call compatibility and ignored.  Restores every variable present
+        in both the model and the checkpoint(s) (tf_utils.get_checkpoint_restore_saver: variables missing from the
+        checkpoint are reported and skipped), global_step unless several checkpoints are given, and Adam slots."""
+        import os
+        import sys
+        if not checkpoints:
+            return
+        if not isinstance(checkpoints, (list, tuple)):
+            checkpoints = [checkpoints]
+        skip_global_step = len(checkpoints) > 1
+        for ck in checkpoints:
+            path = self.latest_checkpoint(ck)
+            if path is None or not os.path.exists(path):
+                raise FileNotFoundError('no checkpoint found at %s' % ck)
+            data = np.load(path)
+            names = {k[4:]: k for k in data.files if k.startswith('var/')}
+            if restore_to_checkpoint_mapping is not None:
+                names = {k: names[restore_to_checkpoint_mapping(k, names)] for k in self.params
+                         if restore_to_checkpoint_mapping(k, names) in names}
+            vals = {k: data[f] for k, f in names.items() if k in self.params}
+            missing = [k for k in self.params if k not in vals]
+            if missing:
+                sys.stderr.write('restore: %d variables are not in %s (kept): %s ...\n' % (len(missing), path, missing[:3]))
+            self.set_params(vals)
+            if not skip_global_step and 'global_step' in data.files:
+                self.global_step = int(data['global_step'])
+            if self.mode == 'train' and 'adam/t' in data.files:
+                for nm in ('g_m', 'g_v', 'd_m', 'd_v'):
+                    buf = getattr(self, nm)
+                    if ('adam/' + nm) in data.files and data['adam/' + nm].shape == tuple(buf.shape):
+                        buf.copy_(torch.from_numpy(data['adam/' + nm]).to(self.device))
+                self.g_adam_t, self.d_adam_t = [int(v) for v in data['adam/t']]
 
     def get_params(self):
         return OrderedDict((k, v.detach().cpu().numpy()) for k, v in self.params.items())
@@ -543,11 +655,14 @@ class SAVPVideoPredictionModel(TrainMixin, VideoPredictionModel):
     def set_inputs(self, inputs, noise=None, sampling=None):
         """Stages a batch: images [B,T,H,W,C] -> time-major, colour-padded, duplicated for the two
         unrolls.  noise: dict eps [T-1,B,nz], z_prior [T-context,B,nz] (time-major, as the oracle);
-        sampling: optional bool [T-1-context, B] scheduled-sampling mask (savp_model.py:309-334)."""
+        sampling: bool [T-1-context, B] (or [.., 2B]: posterior | prior unroll) scheduled-sampling mask; None = drawn from
+        the schedule (savp_model.py:309-334: Bernoulli(p(global_step)) in train mode, all False otherwise); False = all False."""
         hp = self.hparams
         Bf = self.Bf
         dev = self.device
         B, T, S, C = self.B, self.T, self.S, self.C
+        if getattr(self, '_shard', None) is not None and int(inputs['images'].shape[0]) != B:
+            inputs = {k: v[self._shard] for k, v in inputs.items()}
         imgs = torch.as_tensor(inputs['images']).to(dev, torch.float32)[:, :T]
         x = imgs.permute(1, 0, 2, 3, 4)
         Bf['x'].zero_()
@@ -561,21 +676,89 @@ class SAVPVideoPredictionModel(TrainMixin, VideoPredictionModel):
             if self.NB > B:
                 Bf['zvec'][:, B:, :self.A] = act
         sel = torch.ones(S, self.NB, dtype=torch.int32)
-        if sampling is not None:
-            sm = torch.as_tensor(sampling).to(torch.int32).reshape(S - hp.context_frames, B)
-            sel[hp.context_frames:, :B] = sm
-            if self.NB > B:
-                sel[hp.context_frames:, B:] = sm
+        n_free = S - hp.context_frames
+        if sampling is None:
+            sampling = self.draw_scheduled_sampling()
+        elif sampling is False:       # explicit "never feed ground truth after the context frames"
+            sampling = None
+        if sampling is not None and n_free > 0:
+            sm = torch.as_tensor(sampling).to(torch.int32)
+            if sm.numel() == n_free * B:          # one mask for both unrolls (what the oracle takes)
+                sm = sm.reshape(n_free, B)
+                sm = torch.cat([sm, sm], dim=1) if self.NB > B else sm
+            sel[hp.context_frames:] = sm.reshape(n_free, self.NB)
         else:
             sel[hp.context_frames:] = 0
         Bf['sel'].copy_(sel)
         if hp.nz:
             if noise is None:
-                g = torch.Generator(device='cpu').manual_seed(self.global_step + 1)
+                g = torch.Generator(device='cpu').manual_seed(self._seed('noise'))
                 noise = dict(eps=torch.randn(S, B, hp.nz, generator=g),
                              z_prior=torch.randn(T - hp.context_frames, B, hp.nz, generator=g))
             Bf['eps'].copy_(torch.as_tensor(noise['eps']).to(dev, torch.float32))
             Bf['zprior'].copy_(torch.as_tensor(noise['z_prior']).to(dev, torch.float32))
+
+    def redraw_step_randomness(self, noise=None, sampling=None):
+        """A step on resident inputs still draws fresh eps / z_prior and a fresh scheduled-sampling mask (tf.random_normal
+        / tf.multinomial are re-evaluated by every sess.run)."""
+        hp, Bf = self.hparams, self.Bf
+        n_free = self.S - hp.context_frames
+        if self.mode == 'train' and n_free > 0 and (sampling is not None or hp.schedule_sampling != 'none'):
+            if sampling is None:
+                sm = self.draw_scheduled_sampling()
+            else:
+                sm = None if sampling is False else torch.as_tensor(sampling).to(torch.int32)
+            sel = torch.ones(self.S, self.NB, dtype=torch.int32)
+            if sm is None:
+                sel[hp.context_frames:] = 0
+            else:
+                if sm.numel() == n_free * self.B and self.NB > self.B:
+                    sm = torch.cat([sm.reshape(n_free, self.B)] * 2, dim=1)
+                sel[hp.context_frames:] = sm.reshape(n_free, self.NB)
+            Bf['sel'].copy_(sel)
+        if hp.nz:
+            if noise is None or 'eps' not in noise:
+                g = torch.Generator(device='cpu').manual_seed(self._seed('noise'))
+                noise = dict(eps=torch.randn(self.S, self.B, hp.nz, generator=g),
+                             z_prior=torch.randn(self.T - hp.context_frames, self.B, hp.nz, generator=g))
+            Bf['eps'].copy_(torch.as_tensor(noise['eps']).to(self.device, torch.float32))
+            Bf['zprior'].copy_(torch.as_tensor(noise['z_prior']).to(self.device, torch.float32))
+
+    def _seed(self, what, extra=0):
+        """Host RNG seeds: distinct per purpose, step, data-parallel rank and `extra` (e.g. discriminator scope)."""
+        tag = {'noise': 1, 'sampling': 2, 'clips': 3}[what]
+        return (((self.random_seed * 1000003 + self.global_step) * 4099 + getattr(self, 'rank', 0)) * 131 + tag) * 8191 + extra
+
+    def schedule_sampling_prob(self, step=None):
+        """P(feed ground truth) after the context frames (savp_model.py:313-323), evaluated on the host for `step`."""
+        import math
+        hp = self.hparams
+        step = self.global_step if step is None else step
+        if hp.schedule_sampling == 'none' or self.mode != 'train':
+            return 0.0
+        if hp.schedule_sampling == 'inverse_sigmoid':
+            k, start = float(hp.schedule_sampling_k), hp.schedule_sampling_steps[0]
+            if step < start:
+                return 1.0
+            e = (step - start) / k
+            return k / (k + math.exp(e)) if e < 700 else 0.0
+        if hp.schedule_sampling == 'linear':
+            start, end = hp.schedule_sampling_steps
+            st = min(max(step, start), end)
+            return 1.0 - float(st - start) / float(end - start)
+        raise NotImplementedError
+
+    def draw_scheduled_sampling(self):
+        """ground_truth_sampling [T-1-context, NB] (savp_model.py:309-331): Bernoulli(prob(global_step)) per (frame,
+        sample), drawn independently for the two unrolls (each generator_given_z_fn builds its own SAVPCell, :689-696);
+        all False once prob < 0.001 (:327-330), in test mode and for schedule 'none'.  None = all False."""
+        hp = self.hparams
+        prob = self.schedule_sampling_prob()
+        n_free = self.S - hp.context_frames
+        if prob < 0.001 or n_free <= 0:
+            return None
+        g = torch.Generator(device='cpu').manual_seed(self._seed('sampling'))
+        return (torch.rand(n_free, self.NB, generator=g) < prob).to(torch.int32)
 
     # ------------------------------------------------------------------ forward
     def _posterior_forward(self):
@@ -766,6 +949,27 @@ class SAVPVideoPredictionModel(TrainMixin, VideoPredictionModel):
             self._gen_step(t)
         if collect:
             self._collect_outputs()
+
+    def predict(self, inputs, noise=None):
+        """sess.run(model.outputs['gen_images'], feed_dict=inputs) of generate.py:166-168: stages the batch, runs the
+        generator forward with a fresh noise draw and returns gen_images [B, T-1, H, W, C] as a numpy array."""
+        self.set_inputs(inputs, noise)
+        self.generator_forward()
+        return self.outputs['gen_images'].detach().cpu().numpy()
+
+    def outputs_time_major(self, key):
+        """One generator output straight from the device buffers, time-major as generator_fn returns it (no copy)."""
+        B, C, Bf = self.B, self.C, self.Bf
+        nz = bool(self.hparams.nz)
+        if key == 'gen_images':
+            return Bf['gen'][:, B:, ..., :C] if nz else Bf['gen'][..., :C]
+        if key == 'gen_images_enc':
+            return Bf['gen'][:, :B, ..., :C]
+        if key == 'zs_mu_enc':
+            return Bf['zmu']
+        if key == 'zs_log_sigma_sq_enc':
+            return Bf['zlss']
+        raise KeyError(key)
 
     def _collect_outputs(self):
         B, C = self.B, self.C

@@ -170,11 +170,6 @@ class TrainMixin(object):
         return specs
 
     # ------------------------------------------------------------------ build (training side)
-    def wgrad_splits(self, x):
-        """K-splits for the wgrad GEMM so that the grid covers the 148 SMs a few times."""
-        pix = int(np.prod(x.shape[:-1]))
-        return max(1, min(64, pix // (64 * 24)))
-
     def _build_discriminator(self):
         hp = self.hparams
         B, H, W, C = self.B, self.H, self.W, self.C
@@ -501,7 +496,7 @@ class TrainMixin(object):
                     if noise is not None and which in noise:
                         v = torch.as_tensor(noise[which][key]).to(torch.int32)
                     else:
-                        g = torch.Generator().manual_seed(1000003 * self.global_step + 17 * w + r + 1)
+                        g = torch.Generator().manual_seed(self._seed('clips', 8 * list(self.dnets).index(scope) + 2 * w + r))
                         v = torch.randint(0, hi, (self.B,), generator=g, dtype=torch.int32)
                     if 'ts' not in net:
                         net['ts'] = {(a, b): torch.zeros(self.B, dtype=torch.int32, device=self.device)
@@ -520,8 +515,12 @@ class TrainMixin(object):
         `allreduce(flat_grad)` (optional) is called on the flat discriminator / generator gradient buffers before
         their Adam steps (data parallel, tf_utils.py:450-480).  staged=True: `stage_step()` was already called and
         the caller advances `global_step` (used when the device part is captured into a CUDA graph)."""
+        if allreduce is None:
+            allreduce = getattr(self, '_allreduce', None)     # data parallel under torchrun (dp.make_allreduce)
         if inputs is not None:
             self.set_inputs(inputs, noise, sampling)
+        elif not staged:
+            self.redraw_step_randomness(noise, sampling)      # resident inputs: fresh eps / z_prior / sampling mask per step
         if not staged:
             self.stage_step(noise)
         if self.use_cuda_graph and not staged and self._eager_steps >= 1:
@@ -597,8 +596,8 @@ class TrainMixin(object):
                 self._d_gather(net, 'pre', net['ts'][('d_pre', 0)], net['ts'][('d_pre', 1)], 0 if enc else (B if hp.nz else 0))
                 self._d_forward(net, 0, 2 * B)
                 slot = self._slot('discrim_video_sn_vae_gan_loss' if enc else 'discrim_video_sn_gan_loss')
-                L.lsgan_loss(net['logits'][:B], 1.0, B, w, net['dlogits'][:B], slot)
-                L.lsgan_loss(net['logits'][B:], 0.0, B, w, net['dlogits'][B:], slot)
+                L.gan_loss(net['logits'][:B], 1.0, B, w, hp.gan_loss_type, net['dlogits'][:B], slot)
+                L.gan_loss(net['logits'][B:], 0.0, B, w, hp.gan_loss_type, net['dlogits'][B:], slot)
                 self._d_backward(net, 0, 2 * B, with_wgrad=True, to_clip=False)
             self._run_concurrent([(lambda sc=sc, nt=nt: d_step_tower(sc, nt)) for sc, nt in self.dnets.items()])
             if allreduce is not None:
@@ -615,11 +614,13 @@ class TrainMixin(object):
             r1 = NB
         cnt = S * (r1 - r0) * HW * C
         for t in range(S):
+            first = True
             for mode, wgt, nm in ((0, hp.l1_weight, 'gen_l1_loss'), (1, hp.l2_weight, 'gen_l2_loss')):
                 if wgt:
-                    # both write dgen; with l1 and l2 both enabled the second overwrites -> not supported together
+                    # the first enabled term writes dgen, a second one accumulates into it (mode bit 1)
                     L.pixel_loss(Bf['gen'][t, r0:r1].data_ptr(), 4, Bf['x'][t + 1, r0:r1].data_ptr(), 4, G['dgen'][t, r0:r1].data_ptr(), 4,
-                                 (r1 - r0) * HW, C, mode, cnt, wgt, self._slot(nm))
+                                 (r1 - r0) * HW, C, mode | (0 if first else 2), cnt, wgt, self._slot(nm))
+                    first = False
         if hp.kl_weight and hp.nz:
             L.kl_loss(Bf['zmu'], Bf['zlss'], S * B, hp.nz, self._slot('gen_kl_loss'))
         if has_d:
@@ -632,8 +633,8 @@ class TrainMixin(object):
                 self._d_gather(net, 'post', net['ts'][('d_post', 0)], net['ts'][('d_post', 1)], foff, rows_real=need_real)
                 self._d_forward(net, 0 if need_real else B, 2 * B)
                 if w:
-                    L.lsgan_loss(net['logits'][B:], 1.0, B, w, net['dlogits'][B:],
-                                 self._slot('gen_video_sn_vae_gan_loss' if enc else 'gen_video_sn_gan_loss'))
+                    L.gan_loss(net['logits'][B:], 1.0, B, w, hp.gan_loss_type, net['dlogits'][B:],
+                               self._slot('gen_video_sn_vae_gan_loss' if enc else 'gen_video_sn_gan_loss'))
                 else:
                     net['dlogits'][B:].zero_()
                 dcd = None
@@ -667,6 +668,7 @@ class TrainMixin(object):
         import math
         hp = self.hparams
         step = self.global_step
+        self._staged_step = step
         lr = self.learning_rate_at(step)
         if self.dnets:
             self.d_adam_t += 1
@@ -680,17 +682,35 @@ class TrainMixin(object):
         self._scal_host[2] = klw / float(self.S * self.B)
         self.step_scalars.copy_(self._scal_host, non_blocking=True)
 
+    def loss_weights(self, step=None):
+        """name -> weight of every loss slot at `step` (base_model.py:733-852; the KL weight is annealed, :312-319)."""
+        hp = self.hparams
+        step = self._staged_step if step is None else step
+        kl = (self.kl_weight_at(step) or 0.0) if (hp.kl_weight and hp.nz) else 0.0
+        return OrderedDict([
+            ('gen_l1_loss', hp.l1_weight), ('gen_l2_loss', hp.l2_weight), ('gen_kl_loss', kl),
+            ('gen_video_sn_gan_loss', hp.video_sn_gan_weight), ('gen_video_sn_vae_gan_loss', hp.video_sn_vae_gan_weight),
+            ('gen_video_sn_vae_gan_feature_cdist_loss', hp.vae_gan_feature_cdist_weight),
+            ('gen_video_sn_gan_feature_cdist_loss', hp.gan_feature_cdist_weight),
+            ('discrim_video_sn_gan_loss', hp.video_sn_gan_weight), ('discrim_video_sn_vae_gan_loss', hp.video_sn_vae_gan_weight)])
+
     @staticmethod
-    def split_losses(vals):
-        """name -> value dict of one step -> (g_losses, d_losses, g_loss, d_loss) as the reference exposes them
-        (base_model.py:461-465: the totals are the sums of the already-weighted terms)."""
-        g = OrderedDict((k, v) for k, v in vals.items() if k.startswith('gen_') and v != 0.0)
-        d = OrderedDict((k, v) for k, v in vals.items() if k.startswith('discrim_') and v != 0.0)
-        return g, d, float(sum(g.values())), float(sum(d.values()))
+    def split_losses(vals, weights):
+        """UNWEIGHTED per-term values of one step + their weights -> (g_losses, d_losses, g_loss, d_loss) as the reference
+        exposes them: the dicts hold the unweighted terms, the totals are sum(loss * weight) (base_model.py:461)."""
+        g = OrderedDict((k, v) for k, v in vals.items() if k.startswith('gen_') and weights.get(k))
+        d = OrderedDict((k, v) for k, v in vals.items() if k.startswith('discrim_') and weights.get(k))
+        return (g, d, float(sum(v * weights[k] for k, v in g.items())), float(sum(v * weights[k] for k, v in d.items())))
 
     def losses(self):
-        """Weighted loss terms of the last step (device -> host read); also refreshes g_losses / d_losses / g_loss / d_loss."""
-        vals = self.loss_vals.detach().cpu().numpy()
+        """Unweighted loss terms of the last step (device -> host read, averaged over data-parallel replicas as
+        tf_utils.py:489-490 does); also refreshes g_losses / d_losses / g_loss / d_loss.  The generator's GAN / feature
+        terms are the POST-update values (the quantity train_op differentiates, base_model.py:497-503)."""
+        lv = self.loss_vals.detach().clone()
+        if self.world_size > 1:
+            from .. import dp
+            dp.mean_scalars(lv)
+        vals = lv.cpu().numpy()
         out = OrderedDict((k, float(v)) for k, v in zip(LOSS_SLOTS, vals))
-        self.g_losses, self.d_losses, self.g_loss, self.d_loss = self.split_losses(out)
+        self.g_losses, self.d_losses, self.g_loss, self.d_loss = self.split_losses(out, self.loss_weights())
         return out
