@@ -47,7 +47,8 @@ typedef struct vp_conv_geom {
 
 enum { VP_ACT_NONE = 0, VP_ACT_RELU = 1, VP_ACT_LRELU = 2, VP_ACT_SIGMOID = 3, VP_ACT_TANH = 4 };
 enum { VP_WKIND_PLAIN = 0, VP_WKIND_POOLED = 1, VP_WKIND_UPSAMPLED = 2 };
-enum { VP_WLAYOUT_FWD = 0, VP_WLAYOUT_DGRAD = 1 };
+enum { VP_WLAYOUT_FWD = 0, VP_WLAYOUT_DGRAD = 1,
+       VP_WLAYOUT_RESIDUAL = 4 /* OR-ed in: pack tf32(w - tf32(w)), the low part of the fp32-exact 3xTF32 mode */ };
 
 const char* vp_last_error(void);
 /* debug: per-CTA globaltimer stamps of the last vp_conv_igemm launch made with VP_FWD_TRACE=1 (8 x u64 per CTA) */
@@ -61,7 +62,8 @@ int vp_version(void);
  * GEMM K = kc 32-channel chunks of in->c per tap.  out->c columns are stored.
  * split_k > 1: partial sums are atomically added into `out` (caller zero-fills; act must be NONE;
  * bias is added by split 0).  split_k == 0: automatic -- an under-filled grid with a long K loop is split and a DENSE
- * output (out->c == out->cstride) is cleared by the call itself.  accumulate != 0: out += result (act must be NONE). */
+ * output (out->c == out->cstride) is cleared by the call itself.  accumulate = 1: out += result (act must be NONE);
+ * accumulate = 2: out = act(out + result + bias) -- the last pass of a multi-pass (3xTF32) accumulation. */
 int vp_conv_igemm(const vp_tensor* in, const vp_conv_geom* g, const float* wpacked, int n_pad, int kc,
                   const vp_tensor* out, const float* bias, int act, float alpha, int split_k, int accumulate,
                   vp_stream_t stream);
@@ -72,7 +74,11 @@ int vp_conv_igemm(const vp_tensor* in, const vp_conv_geom* g, const float* wpack
  * (lrelu(conv3d), networks.py:83-102), where it removes one full read+write pass per layer. */
 int vp_conv_igemm_actgrad(const vp_tensor* in, const vp_conv_geom* g, const float* wpacked, int n_pad, int kc,
                           const vp_tensor* out, const float* act_output, const float* addend, int act, float alpha,
-                          vp_stream_t stream);
+                          int accumulate /* 0, or 2: the existing `out` is added to conv(in) first */, vp_stream_t stream);
+
+/* lo = x - tf32_truncate(x) over n floats (16-byte aligned, n % 4 == 0): the part of an fp32 activation the tensor core
+ * does not read.  conv(x, W) + conv(lo, W) + conv(x, W_residual) is the fp32-exact ("3xTF32") debug mode. */
+int vp_tf32_residual(const float* x, float* lo, long long n, vp_stream_t stream);
 
 /* Halo-resident variant of vp_conv_igemm for 2-D stride-1 convolutions (the ConvLSTM gate convolutions,
  * rnn_ops.py:121, and their input gradients).  `in` is a zero-padded FLATTENED plane stack: dims (n, 1, Hp, P) with

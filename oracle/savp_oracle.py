@@ -105,16 +105,20 @@ def _nhwc(x):
 # dgrad sees tf32(dy) x tf32(W), wgrad sees tf32(x) x tf32(dy)) quantises its operands the same way, so a
 # difference between the CUDA path and this oracle that is NOT explained by operand rounding shows up
 # at fp32-summation-order level.  Default None = the reference's plain fp32 arithmetic.
-_TF32 = dict(mode=None, exempt=())
+_TF32 = dict(mode=None, exempt=(), weight_mode='rna')
 
 
-def set_tf32_emulation(mode, exempt=()):
-    """mode: None | 'trunc' (drop the low 13 mantissa bits) | 'rna' (round to nearest, ties away).
+def set_tf32_emulation(mode, exempt=(), weight_mode='rna'):
+    """mode: quantisation of the ACTIVATION-side operands (x in the forward, dy in dgrad, x and dy in wgrad), which the
+    tensor core reads raw from fp32 memory: None | 'trunc' (drop the low 13 mantissa bits) | 'rna' (round to nearest,
+    ties away).  weight_mode: quantisation of the filter operand of forward and dgrad -- the CUDA path rounds weights
+    with cvt.rna.tf32.f32 when it packs them (csrc/pack.cu), independent of what the tensor core does.
     exempt: iterable of substrings; a conv called with a `tag` containing one of them stays exact
     (layers the CUDA path runs on fp32 CUDA cores)."""
-    assert mode in (None, 'trunc', 'rna')
+    assert mode in (None, 'trunc', 'rna') and weight_mode in ('trunc', 'rna')
     _TF32['mode'] = mode
     _TF32['exempt'] = tuple(exempt)
+    _TF32['weight_mode'] = weight_mode
 
 
 def tf32_quantize(x, mode=None):
@@ -137,14 +141,14 @@ class _QuantConv(torch.autograd.Function):
     def forward(ctx, x, w, fn):
         ctx.fn = fn
         ctx.save_for_backward(x, w)
-        return fn(tf32_quantize(x), tf32_quantize(w))
+        return fn(tf32_quantize(x), tf32_quantize(w, _TF32['weight_mode']))
 
     @staticmethod
     def backward(ctx, dy):
         x, w = ctx.saved_tensors
         with torch.enable_grad():
             xq = tf32_quantize(x).requires_grad_(True)
-            wq = tf32_quantize(w).requires_grad_(True)
+            wq = tf32_quantize(w, _TF32['weight_mode']).requires_grad_(True)   # dgrad reads the packed (rna) weights
             y = ctx.fn(xq, wq)
             dx, dw = torch.autograd.grad(y, (xq, wq), tf32_quantize(dy))
         return dx, dw, None

@@ -18,6 +18,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <algorithm>
+#include <tuple>
 #include <vector>
 
 #include "common.h"
@@ -308,6 +309,10 @@ __global__ void __launch_bounds__(224, KSUB == 1 ? 2 : 1) igemm_fwd_kernel(const
         tmem_ld16(t_acc + c0, v);
         const int col0 = n0 + c0;
         if (rvalid && col0 < a.out_c) {
+          if (a.accumulate == 2) {      // last pass of a multi-pass accumulation: the partial sum is added BEFORE bias / activation
+#pragma unroll
+            for (int j = 0; j < 16; ++j) if (col0 + j < a.out_c) v[j] += orow[col0 + j];
+          }
           if (add_bias) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) if (col0 + j < a.out_c) v[j] += __ldg(a.bias + col0 + j);
@@ -338,13 +343,13 @@ __global__ void __launch_bounds__(224, KSUB == 1 ? 2 : 1) igemm_fwd_kernel(const
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
                 float4 o = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-                if (a.accumulate) { const float4 e = o4[j]; o.x += e.x; o.y += e.y; o.z += e.z; o.w += e.w; }
+                if (a.accumulate == 1) { const float4 e = o4[j]; o.x += e.x; o.y += e.y; o.z += e.z; o.w += e.w; }
                 o4[j] = o;
               }
             } else {
 #pragma unroll
               for (int j = 0; j < 16; ++j)
-                if (col0 + j < a.out_c) orow[col0 + j] = a.accumulate ? orow[col0 + j] + v[j] : v[j];
+                if (col0 + j < a.out_c) orow[col0 + j] = a.accumulate == 1 ? orow[col0 + j] + v[j] : v[j];
             }
           }
         }
@@ -360,6 +365,318 @@ __global__ void __launch_bounds__(224, KSUB == 1 ? 2 : 1) igemm_fwd_kernel(const
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, a.tmem_cols);
   if (threadIdx.x == 0) VP_TRACE(6);
+}
+
+// ------------------------------------------------------------------------------------------------
+// HALO MODE forward / dgrad kernel.
+//
+// The box-mode kernel above fetches a 16 KB activation tile for every (tap, 32-channel chunk) and a weight tile for every
+// 128-pixel tile: 629 MB of L2 -> SM traffic for the 27 MB lstm_h0 gate convolution, which pins it at the L2 fabric limit
+// (tensor pipe 37 %).  Here a CTA owns a tile of 256 output positions = two 128-row sub-tiles (8 positions x 16 lines each)
+// and the taps are grouped by (stride parity, depth shift[, line shift]): for each (group, 32-channel chunk) ONE halo tile
+// (tile + filter reach, <= 512 rows of 128 B, TMA zero-fills the padding) is loaded, and every tap of the group is the same
+// shared-memory tile read through a UMMA descriptor whose start address is shifted by (dy * pitch + dx) rows and whose
+// 8-row-group stride (SBO) is the halo line pitch: the 128-byte swizzle is a function of the absolute shared-memory address,
+// so a row-shifted start addresses the shifted window.  Only the weight tile streams per tap, and it feeds both sub-tiles
+// (M = 256 per CTA).  lstm_h0: 0.46 MB of operand loads per 200 MMAs instead of 3.2 MB.
+//
+// Warp roles (224 threads): w0 halo producer, w6 weight producer, w1 TMEM allocator + MMA issuer, w2..5 epilogue.
+// ------------------------------------------------------------------------------------------------
+constexpr int kHaloMaxGroups = 72;
+constexpr int kHaloMaxBStages = 8;
+constexpr int kHaloMaxAStages = 3;
+
+struct HaloGroup {
+  int8_t map, cd0, ch0, cw0;    // tensor map (stride parity) and the smallest shifts of the group = halo origin
+  int16_t tap_begin, tap_end;
+};
+
+struct alignas(64) HaloArgs {
+  CUtensorMap amap[kMaxMaps];
+  CUtensorMap bmap;
+  int32_t tiles_w, tiles_h, tiles_d, tiles_n;
+  int32_t tile_w, bh, bd, bn;      // a tile is tile_w (8|16) positions x (bh*bd*bn = 16|32) lines
+  int32_t sub_off;                 // descriptor units (16 B) between the start addresses of the two sub-tiles
+  int32_t sub_lines, sub_x;        // epilogue: line / x offset of sub-tile 1
+  int32_t hw;                      // halo line pitch (rows)
+  uint32_t halo_bytes, halo_stride;
+  int32_t a_stages, b_stages;
+  int32_t kc, n_pad, bn_tile, tmem_cols, dbuf, k_tail;
+  int32_t num_phases, splits;
+  int32_t group_begin[9];
+  int8_t phase_ooff[8][4];
+  int32_t os_d, os_h, os_w;
+  float* out;
+  long long so_n, so_d, so_h, so_w;
+  int32_t out_n, out_d, out_h, out_w, out_c;
+  const float* bias;
+  int32_t act;
+  float alpha;
+  int32_t accumulate;
+  const float* aux_y;
+  const float* aux_add;
+  int32_t aux_act;
+  HaloGroup groups[kHaloMaxGroups];
+  uint16_t tap_aoff[kMaxTaps];     // row offset of the tap's window inside its group's halo tile
+  int32_t tap_wslot[kMaxTaps];
+};
+
+template <bool DBG>
+__global__ void __launch_bounds__(224, 1) igemm_halo_kernel(const __grid_constant__ HaloArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ uint64_t a_full[kHaloMaxAStages], a_empty[kHaloMaxAStages], b_full[kHaloMaxBStages], b_empty[kHaloMaxBStages];
+  __shared__ uint64_t tmem_full_bar[2], tmem_empty_bar[2];
+  __shared__ uint32_t tmem_base_smem;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_mtiles = a.tiles_w * a.tiles_h * a.tiles_d * a.tiles_n;
+  const int n0 = blockIdx.y * a.bn_tile;
+  const int phase = blockIdx.z / a.splits, split = blockIdx.z % a.splits;
+  const int g_begin = a.group_begin[phase];
+  const int n_items = (a.group_begin[phase + 1] - g_begin) * a.kc;       // item = (group, 32-channel chunk)
+  const int it0 = static_cast<int>(static_cast<long long>(n_items) * split / a.splits);
+  const int it1 = static_cast<int>(static_cast<long long>(n_items) * (split + 1) / a.splits);
+  if (it1 <= it0) return;
+  const uint32_t b_bytes = static_cast<uint32_t>(a.bn_tile) * 128u;
+  const int trace_cta = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+  if (DBG && threadIdx.x == 0 && trace_cta < 2048) g_trace[trace_cta * 16 + 0] = gtimer();
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < a.a_stages; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < a.b_stages; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full_bar[i], 1); mbar_init(&tmem_empty_bar[i], 4); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(&tmem_base_smem, a.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+  if (DBG && threadIdx.x == 0 && trace_cta < 2048) g_trace[trace_cta * 16 + 1] = gtimer();
+  const uint32_t smem0 = smem_u32(smem);
+  const uint32_t bring0 = smem0 + static_cast<uint32_t>(a.a_stages) * a.halo_stride;
+  const int g_first = g_begin + it0 / a.kc, c_first = it0 % a.kc;
+
+  if (warp == 0) {
+    // ---- halo tiles: one 5-D TMA box per (group, chunk)
+    if (elect_one_sync()) {
+      const uint32_t af0 = opaque_u32(smem_u32(&a_full[0])), ae0 = opaque_u32(smem_u32(&a_empty[0]));
+      uint32_t st = 0, ph = 0;
+#pragma unroll 1
+      for (int mtile = blockIdx.x; mtile < num_mtiles; mtile += gridDim.x) {
+        int mt = mtile;
+        const int tw = mt % a.tiles_w; mt /= a.tiles_w;
+        const int th = mt % a.tiles_h; mt /= a.tiles_h;
+        const int td = mt % a.tiles_d;
+        const int tn = mt / a.tiles_d;
+        const int x0 = tw * a.tile_w, y0 = th * a.bh, d0 = td * a.bd, s0 = tn * a.bn;
+        int g = g_first, c = c_first;
+#pragma unroll 1
+        for (int it = it0; it < it1; ++it) {
+          const HaloGroup G = a.groups[g];
+          mbar_wait_addr(ae0 + st * 8, ph ^ 1);
+          mbar_expect_tx_addr(af0 + st * 8, a.halo_bytes);
+          tma_load_5d_addr(smem0 + st * a.halo_stride, &a.amap[G.map], af0 + st * 8, c * 32, x0 + G.cw0, y0 + G.ch0, d0 + G.cd0, s0);
+          if (++st == static_cast<uint32_t>(a.a_stages)) { st = 0; ph ^= 1; }
+          if (++c == a.kc) { c = 0; ++g; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 6) {
+    // ---- weight tiles: one 2-D TMA per (tap, chunk)
+    if (elect_one_sync()) {
+      const uint32_t bf0 = opaque_u32(smem_u32(&b_full[0])), be0 = opaque_u32(smem_u32(&b_empty[0]));
+      uint32_t st = 0, ph = 0;
+#pragma unroll 1
+      for (int mtile = blockIdx.x; mtile < num_mtiles; mtile += gridDim.x) {
+        int g = g_first, c = c_first;
+#pragma unroll 1
+        for (int it = it0; it < it1; ++it) {
+          const int t1 = a.groups[g].tap_end;
+#pragma unroll 1
+          for (int t = a.groups[g].tap_begin; t < t1; ++t) {
+            mbar_wait_addr(be0 + st * 8, ph ^ 1);
+            mbar_expect_tx_addr(bf0 + st * 8, b_bytes);
+            tma_load_2d_addr(bring0 + st * b_bytes, &a.bmap, bf0 + st * 8, c * 32, a.tap_wslot[t] * a.n_pad + n0);
+            if (++st == static_cast<uint32_t>(a.b_stages)) { st = 0; ph ^= 1; }
+          }
+          if (++c == a.kc) { c = 0; ++g; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (elect_one_sync()) {
+      const uint32_t idesc = make_idesc_tf32(128, a.bn_tile, 0, 0);
+      // A: K-major, 128B swizzle, 8-row groups at the halo line pitch; B: the usual 1024-byte groups
+      const uint64_t ad_base = make_smem_desc(smem0, 16, static_cast<uint32_t>(a.hw) * 128u, 0);
+      const uint64_t bd_base = make_smem_desc(bring0, 16, 1024, 0);
+      const uint32_t af0 = opaque_u32(smem_u32(&a_full[0])), ae0 = opaque_u32(smem_u32(&a_empty[0]));
+      const uint32_t bf0 = opaque_u32(smem_u32(&b_full[0])), be0 = opaque_u32(smem_u32(&b_empty[0]));
+      const uint32_t a_adv = a.halo_stride >> 4, b_adv = b_bytes >> 4;
+      const uint32_t sub_off = static_cast<uint32_t>(a.sub_off);
+      uint32_t ast = 0, aph = 0, bst = 0, bph = 0;
+      int ti = 0;
+      long long w_a = 0, w_b = 0, w_t = 0, t_begin = 0;     // DBG: cycles this thread waited for halo tiles / weight tiles / TMEM
+      if (DBG) t_begin = clock64();
+#pragma unroll 1
+      for (int mtile = blockIdx.x; mtile < num_mtiles; mtile += gridDim.x, ++ti) {
+        const int acc = a.dbuf ? (ti & 1) : 0, use = a.dbuf ? (ti >> 1) : ti;
+        long long c0 = 0;
+        if (DBG) c0 = clock64();
+        mbar_wait(&tmem_empty_bar[acc], (use & 1) ^ 1);
+        if (DBG) w_t += clock64() - c0;
+        tc_fence_after();
+        const uint32_t d0 = tmem_base + static_cast<uint32_t>(acc * 2 * a.bn_tile), d1 = d0 + a.bn_tile;
+        uint32_t accum = 0;
+        int g = g_first, c = c_first;
+#pragma unroll 1
+        for (int it = it0; it < it1; ++it) {
+          if (DBG) c0 = clock64();
+          mbar_wait_addr(af0 + ast * 8, aph);
+          if (DBG) w_a += clock64() - c0;
+          tc_fence_after();
+          const uint64_t ad_s = ad_base + ast * a_adv;
+          const int nk = (c == a.kc - 1) ? a.k_tail : 4;
+          const int t1 = a.groups[g].tap_end;
+#pragma unroll 1
+          for (int t = a.groups[g].tap_begin; t < t1; ++t) {
+            if (DBG) c0 = clock64();
+            mbar_wait_addr(bf0 + bst * 8, bph);
+            if (DBG) w_b += clock64() - c0;
+            tc_fence_after();
+            const uint64_t ad = ad_s + static_cast<uint32_t>(a.tap_aoff[t]) * 8u;    // rows * 128 B >> 4
+            const uint64_t ad2 = ad + sub_off;
+            const uint64_t bd = bd_base + bst * b_adv;
+            umma_tf32(d0, ad, bd, idesc, accum);
+            umma_tf32(d1, ad2, bd, idesc, accum);
+            if (nk > 1) { umma_tf32(d0, ad + 2, bd + 2, idesc, 1u); umma_tf32(d1, ad2 + 2, bd + 2, idesc, 1u); }
+            if (nk > 2) { umma_tf32(d0, ad + 4, bd + 4, idesc, 1u); umma_tf32(d1, ad2 + 4, bd + 4, idesc, 1u); }
+            if (nk > 3) { umma_tf32(d0, ad + 6, bd + 6, idesc, 1u); umma_tf32(d1, ad2 + 6, bd + 6, idesc, 1u); }
+            umma_commit_addr(be0 + bst * 8);
+            accum = 1u;
+            if (++bst == static_cast<uint32_t>(a.b_stages)) { bst = 0; bph ^= 1; }
+          }
+          umma_commit_addr(ae0 + ast * 8);
+          if (++ast == static_cast<uint32_t>(a.a_stages)) { ast = 0; aph ^= 1; }
+          if (++c == a.kc) { c = 0; ++g; }
+        }
+        umma_commit(&tmem_full_bar[acc]);
+      }
+      if (DBG) {
+        const int cta = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+        if (cta < 2048) {
+          g_trace[cta * 16 + 8] = static_cast<unsigned long long>(clock64() - t_begin);
+          g_trace[cta * 16 + 9] = static_cast<unsigned long long>(w_a);
+          g_trace[cta * 16 + 10] = static_cast<unsigned long long>(w_b);
+          g_trace[cta * 16 + 11] = static_cast<unsigned long long>(w_t);
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ---- epilogue: warp w owns TMEM lanes 32*(w%4)..+31; thread <-> one output position of each sub-tile
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int px = row & 7, line0 = row >> 3;
+    const bool add_bias = (a.bias != nullptr) && (split == 0);
+    int ti = 0;
+    for (int mtile = blockIdx.x; mtile < num_mtiles; mtile += gridDim.x, ++ti) {
+      int mt = mtile;
+      const int tw = mt % a.tiles_w; mt /= a.tiles_w;
+      const int th = mt % a.tiles_h; mt /= a.tiles_h;
+      const int td = mt % a.tiles_d;
+      const int tn = mt / a.tiles_d;
+      const int acc = a.dbuf ? (ti & 1) : 0, use = a.dbuf ? (ti >> 1) : ti;
+      mbar_wait(&tmem_full_bar[acc], use & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int sub = 0; sub < 2; ++sub) {
+        int line = line0 + sub * a.sub_lines;
+        const int ly = line % a.bh; line /= a.bh;
+        const int ld = line % a.bd;
+        const int ln = line / a.bd;
+        const int ow = (tw * a.tile_w + sub * a.sub_x + px) * a.os_w + a.phase_ooff[phase][2];
+        const int oh = (th * a.bh + ly) * a.os_h + a.phase_ooff[phase][1];
+        const int od = (td * a.bd + ld) * a.os_d + a.phase_ooff[phase][0];
+        const int on = tn * a.bn + ln;
+        const bool rvalid = (ow < a.out_w) && (oh < a.out_h) && (od < a.out_d) && (on < a.out_n);
+        const long long ooff = on * a.so_n + od * a.so_d + oh * a.so_h + ow * a.so_w;
+        float* orow = a.out + ooff;
+        const uint32_t t_acc = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>((acc * 2 + sub) * a.bn_tile);
+        for (int c0 = 0; c0 < a.bn_tile; c0 += 16) {
+          float v[16];
+          __syncwarp();
+          tmem_ld16(t_acc + c0, v);
+          const int col0 = n0 + c0;
+          if (rvalid && col0 < a.out_c) {
+            if (a.accumulate == 2) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) if (col0 + j < a.out_c) v[j] += orow[col0 + j];
+            }
+            if (add_bias) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) if (col0 + j < a.out_c) v[j] += __ldg(a.bias + col0 + j);
+            }
+            if (a.splits > 1) {
+              if (col0 + 16 <= a.out_c) {
+#pragma unroll
+                for (int j = 0; j < 16; j += 4) red_add_v4(orow + col0 + j, v[j], v[j + 1], v[j + 2], v[j + 3]);
+              } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) if (col0 + j < a.out_c) atomicAdd(orow + col0 + j, v[j]);
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) v[j] = apply_act(v[j], a.act, a.alpha);
+              if (a.aux_y != nullptr) {   // fused backward of the previous layer's activation: (v + add) * act'(y)
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                  if (col0 + j < a.out_c) {
+                    const float yv = __ldg(a.aux_y + ooff + col0 + j);
+                    float t = v[j];
+                    if (a.aux_add != nullptr) t += __ldg(a.aux_add + ooff + col0 + j);
+                    if (a.aux_act == VP_ACT_LRELU) t = yv > 0.f ? t : a.alpha * t;
+                    else if (a.aux_act == VP_ACT_RELU) t = yv > 0.f ? t : 0.f;
+                    else if (a.aux_act == VP_ACT_SIGMOID) t *= yv * (1.f - yv);
+                    else if (a.aux_act == VP_ACT_TANH) t *= (1.f - yv * yv);
+                    v[j] = t;
+                  }
+                }
+              }
+              if (col0 + 16 <= a.out_c) {
+                float4* o4 = reinterpret_cast<float4*>(orow + col0);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  float4 o = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                  if (a.accumulate == 1) { const float4 e = o4[j]; o.x += e.x; o.y += e.y; o.z += e.z; o.w += e.w; }
+                  o4[j] = o;
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                  if (col0 + j < a.out_c) orow[col0 + j] = a.accumulate == 1 ? orow[col0 + j] + v[j] : v[j];
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, a.tmem_cols);
+  if (DBG && threadIdx.x == 0 && trace_cta < 2048) {
+    g_trace[trace_cta * 16 + 2] = gtimer();
+    unsigned smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    g_trace[trace_cta * 16 + 7] = smid;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -693,10 +1010,8 @@ static int check_tensor(const vp_tensor* t, const char* what) {
   return 0;
 }
 
-// Fills taps / phases / maps for the tap-shifted tensor `sh_t`; the iteration lattice has dims `lat`.
-static int build_geometry(IgemmArgs& A, const vp_conv_geom* g, const vp_tensor* sh_t, int rows_per_tile,
-                          const int lat_in[4] /*w,h,d,n*/, bool mn_major = false) {
-  int lat[4] = {lat_in[0], lat_in[1], lat_in[2], lat_in[3]};
+// Fills taps / phases / output strides of the geometry; `lat` (w,h,d,n) is divided by the stride for transposed convs.
+static int build_taps(IgemmArgs& A, const vp_conv_geom* g, int lat[4]) {
   int ntaps = 0;
   const int K = g->kd * g->kh * g->kw;
   if (K > kMaxTaps) return set_error("too many filter taps (%d)", K);
@@ -748,6 +1063,14 @@ static int build_geometry(IgemmArgs& A, const vp_conv_geom* g, const vp_tensor* 
     A.phase_begin[P] = ntaps;
     lat[0] = ceil_div(lat[0], g->sw); lat[1] = ceil_div(lat[1], g->sh); lat[2] = ceil_div(lat[2], g->sd);
   }
+  return 0;
+}
+
+// Fills taps / phases / maps for the tap-shifted tensor `sh_t`; the iteration lattice has dims `lat`.
+static int build_geometry(IgemmArgs& A, const vp_conv_geom* g, const vp_tensor* sh_t, int rows_per_tile,
+                          const int lat_in[4] /*w,h,d,n*/, bool mn_major = false) {
+  int lat[4] = {lat_in[0], lat_in[1], lat_in[2], lat_in[3]};
+  if (build_taps(A, g, lat)) return -1;
   // box shape: product == rows_per_tile, powers of two, w fastest
   int rem = rows_per_tile;
   A.bw = std::min(floor_pow2(lat[0]), rem); rem /= A.bw;
@@ -777,6 +1100,184 @@ static int next_pow2_cols(int n) { int c = 32; while (c < n) c *= 2; return c; }
 
 using namespace vp;
 
+// Host side of halo mode.  Returns 0 = launched, 1 = not eligible (the caller uses box mode), -1 = error.
+static int conv_halo_try(const vp_tensor* in, const vp_conv_geom* g, const float* wpacked, int n_pad, int kc,
+                         const vp_tensor* out, const float* bias, int act, float alpha, int split_k, int accumulate,
+                         const float* aux_y, const float* aux_add, int aux_act, int mode, vp_stream_t stream) {
+  static thread_local IgemmArgs T;     // scratch: taps / phases of the geometry
+  static thread_local HaloArgs A;
+  std::memset(&A, 0, sizeof(A));
+  int lat[4] = {out->w, out->h, out->d, out->n};
+  if (build_taps(T, g, lat)) return -1;
+  const int ntaps_all = T.phase_begin[T.num_phases];
+  if (lat[0] % 8 != 0 || ntaps_all < 2) return 1;
+  // tile shape: 8 positions per line; two sub-tiles side by side (16 x 16 lines) or stacked (8 x 32 lines)
+  const bool side = lat[0] % 16 == 0;
+  const int tile_w = side ? 16 : 8, lines = side ? 16 : 32;
+  const int bh = std::min(floor_pow2(lat[1]), lines);
+  const int bd = std::min(floor_pow2(lat[2]), lines / bh);
+  const int bn = lines / (bh * bd);
+  // halo line pitch: the exact width by default (measured: a pitch padded to 8 rows, i.e. SBO a multiple of 1024 B, is
+  // never faster and 2.4x slower on the 8x8 planes); VP_HALO_PAD8=1 pads
+  const bool pad8 = getenv("VP_HALO_PAD8") && atoi(getenv("VP_HALO_PAD8")) == 1;
+  // groups: taps that share a halo tile.  With a y-halo the lines of a tile must all come from one (d, n) plane.
+  bool yhalo = (bd * bn == 1);
+  int hw = 0, hh = 0, ngroups = 0;
+  std::vector<int> order(ntaps_all);
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    ngroups = 0; hw = 0; hh = 0;
+    bool ok = true;
+    int ti = 0;
+    for (int p = 0; p < T.num_phases && ok; ++p) {
+      A.group_begin[p] = ngroups;
+      const int tb = T.phase_begin[p], te = T.phase_begin[p + 1];
+      std::vector<int> idx;
+      for (int t = tb; t < te; ++t) idx.push_back(t);
+      auto key = [&](int t) { const Tap& x = T.taps[t]; return std::make_tuple(int(x.map), int(x.cd), yhalo ? 0 : int(x.ch)); };
+      std::stable_sort(idx.begin(), idx.end(), [&](int x, int y) { return key(x) < key(y); });
+      size_t i = 0;
+      while (i < idx.size()) {
+        size_t j = i;
+        int cw0 = 127, cw1 = -128, ch0 = 127, ch1 = -128;
+        while (j < idx.size() && key(idx[j]) == key(idx[i])) {
+          const Tap& x = T.taps[idx[j]];
+          cw0 = std::min(cw0, int(x.cw)); cw1 = std::max(cw1, int(x.cw));
+          ch0 = std::min(ch0, int(x.ch)); ch1 = std::max(ch1, int(x.ch));
+          ++j;
+        }
+        if (ngroups >= kHaloMaxGroups) { ok = false; break; }
+        HaloGroup& G = A.groups[ngroups++];
+        const Tap& f = T.taps[idx[i]];
+        G.map = f.map; G.cd0 = f.cd; G.ch0 = static_cast<int8_t>(ch0); G.cw0 = static_cast<int8_t>(cw0);
+        G.tap_begin = static_cast<int16_t>(ti);
+        for (size_t k = i; k < j; ++k) order[ti++] = idx[k];
+        G.tap_end = static_cast<int16_t>(ti);
+        hw = std::max(hw, tile_w + cw1 - cw0);
+        hh = std::max(hh, bh + ch1 - ch0);
+        i = j;
+      }
+    }
+    A.group_begin[T.num_phases] = ngroups;
+    if (pad8) hw = (hw + 7) / 8 * 8;
+    if (ok && hw <= 256 && hh <= 256 && hw * hh * bd * bn <= 512) break;
+    if (!yhalo || attempt == 1) return 1;
+    yhalo = false;                  // the 2-D halo does not fit: one group per filter row
+  }
+  for (int gi = 0; gi < ngroups; ++gi) {
+    const HaloGroup& G = A.groups[gi];
+    for (int t = G.tap_begin; t < G.tap_end; ++t) {
+      const Tap& x = T.taps[order[t]];
+      A.tap_aoff[t] = static_cast<uint16_t>((x.ch - G.ch0) * hw + (x.cw - G.cw0));
+      A.tap_wslot[t] = x.wslot;
+    }
+  }
+  A.tile_w = tile_w; A.bh = bh; A.bd = bd; A.bn = bn; A.hw = hw;
+  A.sub_off = side ? 8 * 8 : 16 * hw * 8;
+  A.sub_lines = side ? 0 : 16; A.sub_x = side ? 8 : 0;
+  A.halo_bytes = static_cast<uint32_t>(hw) * hh * bd * bn * 128u;
+  A.halo_stride = (A.halo_bytes + 1023u) / 1024u * 1024u;
+  A.tiles_w = ceil_div(lat[0], tile_w); A.tiles_h = ceil_div(lat[1], bh);
+  A.tiles_d = ceil_div(lat[2], bd); A.tiles_n = ceil_div(lat[3], bn);
+  A.num_phases = T.num_phases;
+  std::memcpy(A.phase_ooff, T.phase_ooff, sizeof(A.phase_ooff));
+  A.os_d = T.os_d; A.os_h = T.os_h; A.os_w = T.os_w;
+  // tensor maps of the halo boxes (one per stride parity)
+  const int box[4] = {hw, hh, bd, bn};
+  if (!g->transposed) {
+    for (int qd = 0; qd < g->sd; ++qd)
+      for (int qh = 0; qh < g->sh; ++qh)
+        for (int qw = 0; qw < g->sw; ++qw)
+          if (make_act_map(&A.amap[(qd * g->sh + qh) * g->sw + qw], in, qd, qh, qw, g->sd, g->sh, g->sw, box)) return 1;
+  } else {
+    if (make_act_map(&A.amap[0], in, 0, 0, 0, 1, 1, 1, box)) return 1;
+  }
+  A.kc = kc; A.n_pad = n_pad;
+  A.k_tail = std::min(4, std::max(1, ceil_div(in->c - (kc - 1) * 32, 8)));
+  if (n_pad <= 128) A.bn_tile = n_pad;
+  else if (n_pad % 128 == 0) A.bn_tile = 128;
+  else if (n_pad <= 256) A.bn_tile = n_pad;
+  else {
+    const int tiles = ceil_div(n_pad, 256);
+    if (n_pad % tiles == 0 && (n_pad / tiles) % 16 == 0) A.bn_tile = n_pad / tiles;
+  }
+  if (const char* e = getenv("VP_HALO_BN")) { const int v = atoi(e); if (v >= 16 && v <= 256 && v % 16 == 0 && n_pad % v == 0) A.bn_tile = v; }
+  if (A.bn_tile == 0) return 1;
+  A.dbuf = (4 * A.bn_tile <= 512) ? 1 : 0;
+  A.tmem_cols = next_pow2_cols((A.dbuf ? 4 : 2) * A.bn_tile);
+  const size_t b_bytes = static_cast<size_t>(A.bn_tile) * 128;
+  const size_t smem_max = 227 * 1024 - 2048;
+  A.a_stages = 2;
+  long long b_budget = static_cast<long long>(smem_max) - 1024 - 2LL * A.halo_stride;
+  A.b_stages = static_cast<int>(std::min<long long>(kHaloMaxBStages, b_budget / static_cast<long long>(b_bytes)));
+  if (A.b_stages < 3) return 1;
+  if (b_budget - A.b_stages * static_cast<long long>(b_bytes) >= static_cast<long long>(A.halo_stride) && A.b_stages >= 6) A.a_stages = 3;
+  // split the (group, chunk) items over CTAs when the grid would leave SMs idle
+  const int m_tiles = A.tiles_w * A.tiles_h * A.tiles_d * A.tiles_n;
+  const int n_tiles = n_pad / A.bn_tile;
+  int min_items = 1 << 30;
+  for (int p = 0; p < A.num_phases; ++p) min_items = std::min(min_items, (A.group_begin[p + 1] - A.group_begin[p]) * kc);
+  if (min_items < 1) return 1;
+  const long long base_ctas = 1LL * m_tiles * n_tiles * A.num_phases;
+  if (split_k <= 0) {
+    split_k = 1;
+    const bool dense = out->c == out->cstride;
+    if (dense && act == VP_ACT_NONE && !accumulate && !aux_y && base_ctas * 2 <= 148) {
+      split_k = static_cast<int>(std::min<long long>(std::min(min_items, 8), 148 / base_ctas));
+    }
+  }
+  A.splits = std::max(1, std::min(split_k, min_items));
+  if (A.splits > 1) {
+    if (act != VP_ACT_NONE || aux_y) return 1;
+    if (!accumulate) {
+      if (out->c != out->cstride) return 1;
+      const size_t bytes = static_cast<size_t>(out->n) * out->d * out->h * out->w * out->cstride * sizeof(float);
+      if (cudaMemsetAsync(out->ptr, 0, bytes, static_cast<cudaStream_t>(stream)) != cudaSuccess)
+        return set_error("vp_conv_igemm(halo): cudaMemsetAsync failed");
+    }
+  }
+  A.aux_y = aux_y; A.aux_add = aux_add; A.aux_act = aux_act;
+  A.out = out->ptr;
+  A.so_w = out->cstride; A.so_h = A.so_w * out->w; A.so_d = A.so_h * out->h; A.so_n = A.so_d * out->d;
+  A.out_n = out->n; A.out_d = out->d; A.out_h = out->h; A.out_w = out->w; A.out_c = out->c;
+  A.bias = bias; A.act = act; A.alpha = alpha; A.accumulate = (A.splits > 1) ? 0 : accumulate;
+  if (A.splits > 1 && accumulate == 2) return 1;
+  {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return set_error("cuTensorMapEncodeTiled entry point not found");
+    const int slots = g->kd * g->kh * g->kw;
+    cuuint64_t dims[2] = {static_cast<cuuint64_t>(std::min(kc * 32, (in->c + 3) / 4 * 4)), static_cast<cuuint64_t>(slots) * n_pad};
+    cuuint64_t strides[1] = {static_cast<cuuint64_t>(kc) * 128};
+    cuuint32_t wbox[2] = {32, static_cast<cuuint32_t>(A.bn_tile)};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = enc(&A.bmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(wpacked), dims, strides, wbox, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_error("cuTensorMapEncodeTiled(weights) failed with %d", static_cast<int>(r));
+  }
+  const size_t smem = static_cast<size_t>(A.a_stages) * A.halo_stride + static_cast<size_t>(A.b_stages) * b_bytes + 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(igemm_halo_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_max)) != cudaSuccess ||
+        cudaFuncSetAttribute(igemm_halo_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_max)) != cudaSuccess)
+      return set_error("cudaFuncSetAttribute(igemm_halo_kernel) failed: %s", cudaGetErrorString(cudaGetLastError()));
+    attr_set = true;
+  }
+  const bool trace = getenv("VP_FWD_TRACE") != nullptr;
+  const int other = n_tiles * A.num_phases * A.splits;
+  const int gx = std::min(m_tiles, std::max(1, 148 / other));
+  dim3 grid(gx, n_tiles, A.num_phases * A.splits);
+  if (trace) {
+    fprintf(stderr, "[halo] grid (%d,%d,%d) tile_w %d bh %d bd %d bn %d hw %d halo %u B x%d, B tile %zu B x%d, N tile %d, groups %d, kc %d k_tail %d splits %d\n",
+            gx, n_tiles, A.num_phases * A.splits, A.tile_w, A.bh, A.bd, A.bn, A.hw, A.halo_bytes, A.a_stages, b_bytes, A.b_stages,
+            A.bn_tile, ngroups, kc, A.k_tail, A.splits);
+    igemm_halo_kernel<true><<<grid, 224, std::max(smem, static_cast<size_t>(120 * 1024)), static_cast<cudaStream_t>(stream)>>>(A);
+  } else {
+    igemm_halo_kernel<false><<<grid, 224, std::max(smem, static_cast<size_t>(120 * 1024)), static_cast<cudaStream_t>(stream)>>>(A);
+  }
+  (void)mode;
+  return check_launch("igemm_halo_kernel");
+}
+
 static int conv_igemm_impl(const vp_tensor* in, const vp_conv_geom* g, const float* wpacked, int n_pad, int kc,
                            const vp_tensor* out, const float* bias, int act, float alpha, int split_k, int accumulate,
                            const float* aux_y, const float* aux_add, int aux_act, vp_stream_t stream) {
@@ -788,6 +1289,16 @@ static int conv_igemm_impl(const vp_tensor* in, const vp_conv_geom* g, const flo
   if (in->n != out->n) return set_error("vp_conv_igemm: batch mismatch");
   if (split_k > 1 && act != VP_ACT_NONE) return set_error("vp_conv_igemm: split_k needs act NONE");
   if (aux_y && split_k > 1) return set_error("vp_conv_igemm: the fused activation gradient needs split_k <= 1");
+  {
+    // halo mode (one activation tile per tap GROUP, M = 256 per CTA) whenever the geometry allows it; VP_HALO=0 disables
+    const char* e = getenv("VP_HALO");
+    const int halo_mode = e ? atoi(e) : 1;
+    if (halo_mode > 0) {
+      const int rc = conv_halo_try(in, g, wpacked, n_pad, kc, out, bias, act, alpha, split_k, accumulate, aux_y, aux_add, aux_act,
+                                   halo_mode, stream);
+      if (rc <= 0) return rc;
+    }
+  }
   static thread_local IgemmArgs A;  // large POD; per-thread host-side scratch (ctypes releases the GIL during calls)
   std::memset(&A, 0, sizeof(A));
   const int lat[4] = {out->w, out->h, out->d, out->n};
@@ -839,7 +1350,7 @@ static int conv_igemm_impl(const vp_tensor* in, const vp_conv_geom* g, const flo
   A.so_w = out->cstride; A.so_h = A.so_w * out->w; A.so_d = A.so_h * out->h; A.so_n = A.so_d * out->d;
   A.out_n = out->n; A.out_d = out->d; A.out_h = out->h; A.out_w = out->w; A.out_c = out->c;
   A.bias = bias; A.act = act; A.alpha = alpha; A.accumulate = accumulate;
-  if (accumulate && act != VP_ACT_NONE) return set_error("vp_conv_igemm: accumulate needs act NONE");
+  if (accumulate == 1 && act != VP_ACT_NONE) return set_error("vp_conv_igemm: accumulate = 1 needs act NONE");
   // weights: 2-D [slots*n_pad rows][kc*32]
   {
     EncodeTiledFn enc = get_encode();
@@ -904,10 +1415,11 @@ extern "C" int vp_conv_igemm(const vp_tensor* in, const vp_conv_geom* g, const f
 
 extern "C" int vp_conv_igemm_actgrad(const vp_tensor* in, const vp_conv_geom* g, const float* wpacked, int n_pad, int kc,
                                      const vp_tensor* out, const float* act_output, const float* addend, int act,
-                                     float alpha, vp_stream_t stream) {
+                                     float alpha, int accumulate, vp_stream_t stream) {
   if (!act_output) return set_error("vp_conv_igemm_actgrad: act_output is required");
   if (out->c != out->cstride) return set_error("vp_conv_igemm_actgrad: dense output required");
-  return conv_igemm_impl(in, g, wpacked, n_pad, kc, out, nullptr, VP_ACT_NONE, alpha, 1, 0, act_output, addend, act, stream);
+  if (accumulate != 0 && accumulate != 2) return set_error("vp_conv_igemm_actgrad: accumulate must be 0 or 2");
+  return conv_igemm_impl(in, g, wpacked, n_pad, kc, out, nullptr, VP_ACT_NONE, alpha, 1, accumulate, act_output, addend, act, stream);
 }
 
 extern "C" int vp_conv_wgrad(const vp_tensor* x, const vp_tensor* dy, const vp_conv_geom* g, float* dwpacked,

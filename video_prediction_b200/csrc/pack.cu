@@ -9,6 +9,9 @@
 // descriptors read:  FWD  [tap][co -> n_pad][ci -> kc*32],  DGRAD [tap][ci -> n_pad][co -> kc*32].
 // A channel map lets the engine's internal (16-byte aligned, padded) concat layouts differ from the
 // reference's channel order.
+#include <algorithm>
+#include <cstdint>
+
 #include "common.h"
 #include "ptx.cuh"
 
@@ -58,8 +61,8 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, int kd, int kh,
   const int k = static_cast<int>(idx % kpad);
   const int n = static_cast<int>((idx / kpad) % n_pad);
   const int tap = static_cast<int>(idx / (static_cast<long long>(kpad) * n_pad));
-  const int co = layout == VP_WLAYOUT_FWD ? n : k;
-  const int ci = layout == VP_WLAYOUT_FWD ? k : n;
+  const int co = (layout & 3) == VP_WLAYOUT_FWD ? n : k;
+  const int ci = (layout & 3) == VP_WLAYOUT_FWD ? k : n;
   float v = 0.f;
   if (co < co_n && ci < ci_int) {
     const int cr = cmap ? cmap[ci] : ci;
@@ -68,7 +71,22 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, int kd, int kh,
       if (inv_scale) v = v / __ldg(inv_scale);
     }
   }
-  wp[idx] = round_tf32(v);
+  // VP_WLAYOUT_RESIDUAL: the part of the weight the TF32 rounding dropped (the "lo" term of the fp32-exact 3xTF32 mode)
+  wp[idx] = (layout & VP_WLAYOUT_RESIDUAL) ? round_tf32(v - round_tf32(v)) : round_tf32(v);
+}
+
+// lo = x - tf32_truncate(x): what the tensor core does not see of an fp32 activation (it reads the top 19 bits)
+__global__ void tf32_residual_kernel(const float4* __restrict__ x, float4* __restrict__ lo, long long n4) {
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float4 v = x[i];
+    float4 r;
+    r.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
+    r.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
+    r.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
+    r.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
+    lo[i] = r;
+  }
 }
 
 // dw[i][j][cmap[ci]][co] += sum_taps dKeff/dw * dwp[tap][co][ci]   (dwp in FWD layout)
@@ -119,7 +137,7 @@ extern "C" int vp_pack_weights(const float* w, int kd, int kh, int kw, int ci_re
   if (kind != VP_WKIND_PLAIN && kd != 1) return set_error("vp_pack_weights: pooled/upsampled kernels are 2-D");
   const int taps = eff_taps(kd, kh, kw, kind);
   const int kpad = kc * 32;
-  const int rows = layout == VP_WLAYOUT_FWD ? co : ci_int, cols = layout == VP_WLAYOUT_FWD ? ci_int : co;
+  const int rows = (layout & 3) == VP_WLAYOUT_FWD ? co : ci_int, cols = (layout & 3) == VP_WLAYOUT_FWD ? ci_int : co;
   if (rows > n_pad || cols > kpad) return set_error("vp_pack_weights: n_pad/kc too small (%d>%d or %d>%d)", rows, n_pad, cols, kpad);
   const long long total = static_cast<long long>(taps) * n_pad * kpad;
   pack_weights_kernel<<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(w, kd, kh, kw, ci_ref, co, kind, layout, cmap,
@@ -134,4 +152,14 @@ extern "C" int vp_unpack_wgrad(const float* dwpacked, int kd, int kh, int kw, in
   unpack_wgrad_kernel<<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(dwpacked, kd, kh, kw, ci_ref, co, kind, cmap,
                                                                          ci_int, dw, n_pad, kc * 32);
   return check_launch("unpack_wgrad_kernel");
+}
+
+extern "C" int vp_tf32_residual(const float* x, float* lo, long long n, vp_stream_t stream) {
+  if (!x || !lo || (n & 3) || (reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(lo) & 15))
+    return set_error("vp_tf32_residual: pointers must be 16B aligned and n a multiple of 4");
+  const long long n4 = n / 4;
+  const int blocks = static_cast<int>(std::min<long long>(148 * 8, (n4 + 255) / 256));
+  tf32_residual_kernel<<<std::max(blocks, 1), 256, 0, as_stream(stream)>>>(reinterpret_cast<const float4*>(x),
+                                                                          reinterpret_cast<float4*>(lo), n4);
+  return check_launch("tf32_residual_kernel");
 }

@@ -29,6 +29,7 @@ class VpConvGeom(C.Structure):
 ACT_NONE, ACT_RELU, ACT_LRELU, ACT_SIGMOID, ACT_TANH = range(5)
 WKIND_PLAIN, WKIND_POOLED, WKIND_UPSAMPLED = range(3)
 WLAYOUT_FWD, WLAYOUT_DGRAD = range(2)
+WLAYOUT_RESIDUAL = 4
 
 
 class VpError(RuntimeError):
@@ -82,10 +83,24 @@ def conv_igemm(x_view, g, wpacked, n_pad, kc, out_view, bias=None, act=ACT_NONE,
                               act, C.c_float(alpha), split_k, int(accumulate), stream_ptr()))
 
 
-def conv_igemm_actgrad(x_view, g, wpacked, n_pad, kc, out_view, act_output_addr, addend_addr, act, alpha=0.0):
+def conv_igemm_actgrad(x_view, g, wpacked, n_pad, kc, out_view, act_output_addr, addend_addr, act, alpha=0.0, accumulate=0):
     check(lib().vp_conv_igemm_actgrad(C.byref(x_view), C.byref(g), ptr(wpacked), n_pad, kc, C.byref(out_view),
                                       C.c_void_p(act_output_addr), C.c_void_p(addend_addr or 0), act, C.c_float(alpha),
-                                      stream_ptr()))
+                                      int(accumulate), stream_ptr()))
+
+
+def tf32_residual(x):
+    """x - tf32_truncate(x) with the layout of x (the 'lo' operand of the fp32-exact 3xTF32 mode)."""
+    assert x.is_contiguous() and x.dtype == torch.float32
+    lo = torch.empty_like(x)
+    check(lib().vp_tf32_residual(ptr(x), ptr(lo), C.c_longlong(x.numel()), stream_ptr()))
+    return lo
+
+
+def exact_mode():
+    """VP_EXACT=1: every tensor-core convolution (forward, dgrad, wgrad) runs as three TF32 passes
+    hi*hi + lo*hi + hi*lo with fp32 accumulation = fp32-exact up to 2^-21 (debug / parity mode, ~3x the conv time)."""
+    return os.environ.get('VP_EXACT', '0') == '1'
 
 
 def conv_flat(x_view, valid_h, valid_w, g, wpacked, n_pad, kc, out_view, bias=None, act=ACT_NONE, alpha=0.0, split_k=1,
@@ -124,7 +139,7 @@ def choose_n_pad(rows):
 def pack_weights(w, k, ci_ref, co, kind, layout, ci_int=None, cmap=None, inv_scale=None, out=None):
     """Returns (wpacked, n_pad, kc)."""
     ci_int = ci_ref if ci_int is None else ci_int
-    rows, cols = (co, ci_int) if layout == WLAYOUT_FWD else (ci_int, co)
+    rows, cols = (co, ci_int) if (layout & 3) == WLAYOUT_FWD else (ci_int, co)
     n_pad, kc = choose_n_pad(rows), pad_to(cols, 32) // 32
     taps = eff_taps(k, kind)
     if out is None:

@@ -86,6 +86,9 @@ class ConvLayer(object):
         w = self.model.params[self.wname]
         self.wp, self.n_pad, self.kc = L.pack_weights(w, self.k, self.ci_ref, self.co, self.kind, L.WLAYOUT_FWD,
                                                       ci_int=self.ci_int, cmap=self.cmap, out=self.wp)
+        if L.exact_mode():      # fp32-exact 3xTF32 mode: the part of the weights the TF32 rounding dropped
+            self.wp_lo, _, _ = L.pack_weights(w, self.k, self.ci_ref, self.co, self.kind, L.WLAYOUT_FWD | L.WLAYOUT_RESIDUAL,
+                                              ci_int=self.ci_int, cmap=self.cmap, out=getattr(self, 'wp_lo', None))
 
     def prepare_backward(self):
         self.geom_bwd = L.geom(self.ke, self.stride, self.pad, not self.transposed)
@@ -97,33 +100,58 @@ class ConvLayer(object):
         w = self.model.params[self.wname]
         self.wpd, self.n_pad_d, self.kc_d = L.pack_weights(w, self.k, self.ci_ref, self.co, self.kind, L.WLAYOUT_DGRAD,
                                                           ci_int=self.ci_int, cmap=self.cmap, out=getattr(self, 'wpd', None))
+        if L.exact_mode():
+            self.wpd_lo, _, _ = L.pack_weights(w, self.k, self.ci_ref, self.co, self.kind, L.WLAYOUT_DGRAD | L.WLAYOUT_RESIDUAL,
+                                               ci_int=self.ci_int, cmap=self.cmap, out=getattr(self, 'wpd_lo', None))
 
     def dgrad(self, dy, dx, dy_c=None, accumulate=False):
         """dx[.., ci_int] (+)= conv^T(dy): the same engine with the transposed flag flipped."""
-        dyv = L.tensor_view(dy.view((-1,) + tuple(dy.shape[-3:])), self.co if dy_c is None else dy_c)
+        dy4 = dy.view((-1,) + tuple(dy.shape[-3:]))
+        dyv = L.tensor_view(dy4, self.co if dy_c is None else dy_c)
         dxv = L.tensor_view(dx.view((-1,) + tuple(dx.shape[-3:])), self.ci_int)
+        if L.exact_mode():
+            conv3x(dy4, dyv.c, self.geom_bwd, self.wpd, self.wpd_lo, self.n_pad_d, self.kc_d, dxv, None, L.ACT_NONE, 0.0,
+                   accumulate)
+            return
         L.conv_igemm(dyv, self.geom_bwd, self.wpd, self.n_pad_d, self.kc_d, dxv, None, L.ACT_NONE, 0.0, 1 if accumulate else 0,
                      accumulate)
 
     def wgrad(self, x, dy, dy_c=None):
         """grads[w] += dL/dw from ONE GEMM over every position of the (time-stacked) tensors."""
-        xv = L.tensor_view(x.reshape((-1,) + tuple(x.shape[-3:])), self.ci_int)
-        dyv = L.tensor_view(dy.reshape((-1,) + tuple(dy.shape[-3:])), self.co if dy_c is None else dy_c)
-        taps = L.eff_taps(self.k, self.kind)
-        tiles = ((self.n_pad + 127) // 128) * ((self.kc + 3) // 4) * taps
-        pix = xv.n * max(xv.h, dyv.h) * max(xv.w, dyv.w)
-        splits = max(1, min(pix // 256, (592 + tiles - 1) // tiles))
+        x4, dy4 = x.reshape((-1,) + tuple(x.shape[-3:])), dy.reshape((-1,) + tuple(dy.shape[-3:]))
+        xv = L.tensor_view(x4, self.ci_int)
+        dyv = L.tensor_view(dy4, self.co if dy_c is None else dy_c)
         self.dwp.zero_()
         L.conv_wgrad(xv, dyv, self.geom, self.dwp, self.n_pad, self.kc, split_k=0)
+        if L.exact_mode():      # + x_lo^T dy + x^T dy_lo
+            L.conv_wgrad(L.tensor_view(L.tf32_residual(x4), self.ci_int), dyv, self.geom, self.dwp, self.n_pad, self.kc, split_k=0)
+            L.conv_wgrad(xv, L.tensor_view(L.tf32_residual(dy4), dyv.c), self.geom, self.dwp, self.n_pad, self.kc, split_k=0)
         L.unpack_wgrad(self.dwp, self.k, self.ci_ref, self.co, self.kind, self.model.grads[self.wname], self.n_pad, self.kc,
                        ci_int=self.ci_int, cmap=self.cmap)
 
     def fwd(self, x, out, out_off=0, out_c=None, act=L.ACT_NONE, alpha=0.0, split_k=0):
         """x: stacked buffer [.., h, w, cstride] (4-D or 5-D torch tensor, leading dims folded into n)."""
-        xv = L.tensor_view(x.view((-1,) + tuple(x.shape[-3:])), self.ci_int)
+        x4 = x.view((-1,) + tuple(x.shape[-3:]))
+        xv = L.tensor_view(x4, self.ci_int)
         ov = L.tensor_view(out.view((-1,) + tuple(out.shape[-3:])), self.co if out_c is None else out_c, out_off)
         bias = self.model.params[self.bname] if self.bname else None
+        if L.exact_mode():
+            conv3x(x4, self.ci_int, self.geom, self.wp, self.wp_lo, self.n_pad, self.kc, ov, bias, act, alpha)
+            return
         L.conv_igemm(xv, self.geom, self.wp, self.n_pad, self.kc, ov, bias, act, alpha, split_k)
+
+
+def conv3x(x, c, geom, wp, wp_lo, n_pad, kc, ov, bias, act, alpha, accumulate=False, aux=None):
+    """fp32-exact convolution on the TF32 tensor cores (VP_EXACT=1): x = x_hi + x_lo (x_hi = what the tensor core reads),
+    W = W_hi + W_lo (W_hi = the packed, rounded weights);  out = act(x_hi W_hi + x_lo W_hi + x_hi W_lo + bias), the dropped
+    x_lo W_lo term is 2^-21 relative.  aux = (act_output_addr, addend_addr, act): the fused activation-gradient epilogue."""
+    xv = L.tensor_view(x, c)
+    L.conv_igemm(xv, geom, wp, n_pad, kc, ov, None, L.ACT_NONE, 0.0, 1, 1 if accumulate else 0)
+    L.conv_igemm(L.tensor_view(L.tf32_residual(x), c), geom, wp, n_pad, kc, ov, None, L.ACT_NONE, 0.0, 1, 1)
+    if aux is None:
+        L.conv_igemm(xv, geom, wp_lo, n_pad, kc, ov, bias, act, alpha, 1, 2)
+    else:
+        L.conv_igemm_actgrad(xv, geom, wp_lo, n_pad, kc, ov, aux[0], aux[1], aux[2], alpha, accumulate=2)
 
 
 class SAVPVideoPredictionModel(TrainMixin, VideoPredictionModel):

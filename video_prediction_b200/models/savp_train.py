@@ -76,6 +76,11 @@ class SNLayer(object):
                                                       ci_int=self.cin_int, cmap=self.cmap, inv_scale=self.sigma, out=self.wp)
         self.wpd, self.n_pad_d, self.kc_d = L.pack_weights(w, kk, self.cin_ref, self.co, L.WKIND_PLAIN, L.WLAYOUT_DGRAD,
                                                           ci_int=self.cin_int, cmap=self.cmap, inv_scale=self.sigma, out=self.wpd)
+        if L.exact_mode():
+            self.wp_lo, _, _ = L.pack_weights(w, kk, self.cin_ref, self.co, L.WKIND_PLAIN, L.WLAYOUT_FWD | L.WLAYOUT_RESIDUAL,
+                                              ci_int=self.cin_int, cmap=self.cmap, inv_scale=self.sigma, out=getattr(self, 'wp_lo', None))
+            self.wpd_lo, _, _ = L.pack_weights(w, kk, self.cin_ref, self.co, L.WKIND_PLAIN, L.WLAYOUT_DGRAD | L.WLAYOUT_RESIDUAL,
+                                               ci_int=self.cin_int, cmap=self.cmap, inv_scale=self.sigma, out=getattr(self, 'wpd_lo', None))
         if self.dwp is None:
             self.dwp = torch.zeros(self.k ** 3 * self.n_pad * self.kc * 32, device=w.device)
 
@@ -94,6 +99,11 @@ class SNLayer(object):
             n, d, h, w = x.shape[:4]
             L.conv3d_c4_fwd(x, P[self.wname], self.sigma, P[self.bname], out, n, d, h, w, self.cin_ref, 0.1)
             return
+        if L.exact_mode():
+            from .savp_model import conv3x
+            conv3x(x, self.cin_int, self.geom, self.wp, self.wp_lo, self.n_pad, self.kc, L.tensor_view(out, self.co),
+                   self.m.params[self.bname], L.ACT_LRELU, 0.1)
+            return
         L.conv_igemm(L.tensor_view(x, self.cin_int), self.geom, self.wp, self.n_pad, self.kc, L.tensor_view(out, self.co),
                      self.m.params[self.bname], L.ACT_LRELU, 0.1)
 
@@ -101,6 +111,11 @@ class SNLayer(object):
         """dx = conv^T(dy); with act_y: dx = (conv^T(dy) + addend) * lrelu'(act_y) -- the backward of the previous
         layer's leaky relu fused into the epilogue."""
         dyv, dxv = L.tensor_view(dy, self.co), L.tensor_view(dx, self.cin_int)
+        if L.exact_mode():
+            from .savp_model import conv3x
+            aux = None if act_y is None else (act_y.data_ptr(), addend.data_ptr() if addend is not None else 0, L.ACT_LRELU)
+            conv3x(dy, self.co, self.geom_t, self.wpd, self.wpd_lo, self.n_pad_d, self.kc_d, dxv, None, L.ACT_NONE, 0.1, aux=aux)
+            return
         if act_y is None:
             L.conv_igemm(dyv, self.geom_t, self.wpd, self.n_pad_d, self.kc_d, dxv, None, L.ACT_NONE, 0.0, 0)
         else:
@@ -117,8 +132,11 @@ class SNLayer(object):
             self.sn_backward()
             return
         self.dwp.zero_()
-        L.conv_wgrad(L.tensor_view(x, self.cin_int), L.tensor_view(dy, self.co), self.geom, self.dwp, self.n_pad, self.kc,
-                     split_k=0)
+        xv, dyv = L.tensor_view(x, self.cin_int), L.tensor_view(dy, self.co)
+        L.conv_wgrad(xv, dyv, self.geom, self.dwp, self.n_pad, self.kc, split_k=0)
+        if L.exact_mode():
+            L.conv_wgrad(L.tensor_view(L.tf32_residual(x.contiguous()), self.cin_int), dyv, self.geom, self.dwp, self.n_pad, self.kc, split_k=0)
+            L.conv_wgrad(xv, L.tensor_view(L.tf32_residual(dy.contiguous()), self.co), self.geom, self.dwp, self.n_pad, self.kc, split_k=0)
         self.gwbar.zero_()
         L.unpack_wgrad(self.dwp, (self.k,) * 3, self.cin_ref, self.co, L.WKIND_PLAIN, self.gwbar, self.n_pad, self.kc,
                        ci_int=self.cin_int, cmap=self.cmap)
@@ -523,7 +541,7 @@ class TrainMixin(object):
             self.redraw_step_randomness(noise, sampling)      # resident inputs: fresh eps / z_prior / sampling mask per step
         if not staged:
             self.stage_step(noise)
-        if self.use_cuda_graph and not staged and self._eager_steps >= 1:
+        if self.use_cuda_graph and not staged and self._eager_steps >= 1 and not L.exact_mode():
             # the device part of the step (~1.5 k launches, no host sync) is captured once and replayed
             if self._graph is None:
                 try:
