@@ -68,6 +68,12 @@ int vp_conv_igemm(const vp_tensor* in, const vp_conv_geom* g, const float* wpack
                   const vp_tensor* out, const float* bias, int act, float alpha, int split_k, int accumulate,
                   vp_stream_t stream);
 
+/* Engine selection for vp_conv_igemm / vp_conv_igemm_actgrad on the calling thread: 0 = box mode (one activation tile per
+ * filter tap), 1 = halo mode (one halo tile per tap group, 256 output positions per CTA; falls back to box mode when the
+ * geometry is not eligible), -1 = default (halo unless the environment says VP_HALO=0).  Both engines compute the same
+ * sums (fp32 summation order differs); the host layer times both once per geometry and keeps the faster. */
+int vp_conv_set_engine(int engine);
+
 /* Input-gradient convolution fused with the backward of the previous layer's activation:
  *   out = (conv(in) + addend) * act'(act_output),  act' evaluated from the activation OUTPUT (lrelu/relu/sigmoid/tanh);
  * act_output / addend (optional) have exactly the layout of the dense `out`.  Used for the discriminator towers

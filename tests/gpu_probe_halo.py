@@ -45,9 +45,9 @@ def run(name, xs, cin, cout, k, s, p, kind=0, transposed=False, dgrad=False, act
     geom = L.geom(kk, s, p, tr)
     outs, times = {}, {}
     aux = rnd(*oshape, seed=5) if actgrad else None
-    for mode in ('0', '1', '1p0'):
+    for mode in ('0', '1', '1s0'):
         os.environ['VP_HALO'] = mode[0]
-        os.environ['VP_HALO_PAD8'] = '0' if mode.endswith('p0') else '1'
+        os.environ['VP_HALO_STAGGER'] = '0' if mode.endswith('s0') else '1'
         out = torch.zeros(*oshape, device='cuda') if not accumulate else torch.ones(*oshape, device='cuda')
         def call():
             if actgrad:
@@ -80,15 +80,15 @@ def run(name, xs, cin, cout, k, s, p, kind=0, transposed=False, dgrad=False, act
     if transposed != dgrad and any(st > 1 for st in s):
         fl /= (s[0] * s[1] * s[2])
     res = []
-    for mode in ('1', '1p0'):
+    for mode in ('1', '1s0'):
         if outs[mode] is None:
             res.append('ERR')
             continue
         err = (outs[mode] - ref).abs().max().item() / sc
         res.append('%s rel %.1e' % ('ok ' if err < 2e-5 else 'BAD', err))
-    print('%-34s box %7.1f us %6.0f TF/s | halo %7.1f us %6.0f TF/s (%s) | unpadded %7.1f us (%s)' % (
+    print('%-34s box %7.1f us %6.0f TF/s | halo %7.1f us %6.0f TF/s (%s) | no stagger %7.1f us (%s)' % (
         name, times.get('0', 0), fl / max(times.get('0', 1), 1e-9) / 1e6, times.get('1', 0), fl / max(times.get('1', 1), 1e-9) / 1e6, res[0],
-        times.get('1p0', 0), res[1]))
+        times.get('1s0', 0), res[1]))
     sys.stdout.flush()
 
 

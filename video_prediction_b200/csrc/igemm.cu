@@ -380,10 +380,11 @@ __global__ void __launch_bounds__(224, KSUB == 1 ? 2 : 1) igemm_fwd_kernel(const
 // so a row-shifted start addresses the shifted window.  Only the weight tile streams per tap, and it feeds both sub-tiles
 // (M = 256 per CTA).  lstm_h0: 0.46 MB of operand loads per 200 MMAs instead of 3.2 MB.
 //
-// Warp roles (224 threads): w0 halo producer, w6 weight producer, w1 TMEM allocator + MMA issuer, w2..5 epilogue.
+// Warp roles (256 threads): w0 halo producer, w6 weight producer, w1 (TMEM allocator) and w7 MMA issuers (one per sub-tile),
+// w2..5 epilogue.
 // ------------------------------------------------------------------------------------------------
 constexpr int kHaloMaxGroups = 72;
-constexpr int kHaloMaxBStages = 8;
+constexpr int kHaloMaxBStages = 14;
 constexpr int kHaloMaxAStages = 3;
 
 struct HaloGroup {
@@ -402,7 +403,7 @@ struct alignas(64) HaloArgs {
   uint32_t halo_bytes, halo_stride;
   int32_t a_stages, b_stages;
   int32_t kc, n_pad, bn_tile, tmem_cols, dbuf, k_tail;
-  int32_t num_phases, splits;
+  int32_t num_phases, splits, stagger, dbg_skip;
   int32_t group_begin[9];
   int8_t phase_ooff[8][4];
   int32_t os_d, os_h, os_w;
@@ -422,7 +423,7 @@ struct alignas(64) HaloArgs {
 };
 
 template <bool DBG>
-__global__ void __launch_bounds__(224, 1) igemm_halo_kernel(const __grid_constant__ HaloArgs a) {
+__global__ void __launch_bounds__(256, 1) igemm_halo_kernel(const __grid_constant__ HaloArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   __shared__ uint64_t a_full[kHaloMaxAStages], a_empty[kHaloMaxAStages], b_full[kHaloMaxBStages], b_empty[kHaloMaxBStages];
@@ -443,9 +444,10 @@ __global__ void __launch_bounds__(224, 1) igemm_halo_kernel(const __grid_constan
   if (DBG && threadIdx.x == 0 && trace_cta < 2048) g_trace[trace_cta * 16 + 0] = gtimer();
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < a.a_stages; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
-    for (int i = 0; i < a.b_stages; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full_bar[i], 1); mbar_init(&tmem_empty_bar[i], 4); }
+    // two MMA-issuing threads (one per sub-tile, warps 1 and 7) release the operand stages and publish the accumulators
+    for (int i = 0; i < a.a_stages; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 2); }
+    for (int i = 0; i < a.b_stages; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 2); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full_bar[i], 2); mbar_init(&tmem_empty_bar[i], 4); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(&tmem_base_smem, a.tmem_cols);
@@ -457,6 +459,7 @@ __global__ void __launch_bounds__(224, 1) igemm_halo_kernel(const __grid_constan
   const uint32_t smem0 = smem_u32(smem);
   const uint32_t bring0 = smem0 + static_cast<uint32_t>(a.a_stages) * a.halo_stride;
   const int g_first = g_begin + it0 / a.kc, c_first = it0 % a.kc;
+  const uint32_t rot = a.stagger ? (blockIdx.x * 7u + blockIdx.y * 3u) : 0u;      // tap-order rotation of this CTA
 
   if (warp == 0) {
     // ---- halo tiles: one 5-D TMA box per (group, chunk)
@@ -476,8 +479,12 @@ __global__ void __launch_bounds__(224, 1) igemm_halo_kernel(const __grid_constan
         for (int it = it0; it < it1; ++it) {
           const HaloGroup G = a.groups[g];
           mbar_wait_addr(ae0 + st * 8, ph ^ 1);
-          mbar_expect_tx_addr(af0 + st * 8, a.halo_bytes);
-          tma_load_5d_addr(smem0 + st * a.halo_stride, &a.amap[G.map], af0 + st * 8, c * 32, x0 + G.cw0, y0 + G.ch0, d0 + G.cd0, s0);
+          if (DBG && (a.dbg_skip & 1)) {
+            mbar_arrive_addr(af0 + st * 8);       // timing experiment: no halo loads (wrong results)
+          } else {
+            mbar_expect_tx_addr(af0 + st * 8, a.halo_bytes);
+            tma_load_5d_addr(smem0 + st * a.halo_stride, &a.amap[G.map], af0 + st * 8, c * 32, x0 + G.cw0, y0 + G.ch0, d0 + G.cd0, s0);
+          }
           if (++st == static_cast<uint32_t>(a.a_stages)) { st = 0; ph ^= 1; }
           if (++c == a.kc) { c = 0; ++g; }
         }
@@ -494,21 +501,33 @@ __global__ void __launch_bounds__(224, 1) igemm_halo_kernel(const __grid_constan
         int g = g_first, c = c_first;
 #pragma unroll 1
         for (int it = it0; it < it1; ++it) {
-          const int t1 = a.groups[g].tap_end;
+          // every CTA walks the taps of a group in a rotated order: at any moment the CTAs of a wave ask the L2 for
+          // DIFFERENT weight tiles instead of all for the same 16 KB
+          const int t0 = a.groups[g].tap_begin, t1 = a.groups[g].tap_end;
+          int t = t0 + static_cast<int>(rot % static_cast<uint32_t>(t1 - t0));
 #pragma unroll 1
-          for (int t = a.groups[g].tap_begin; t < t1; ++t) {
+          for (int i = t0; i < t1; ++i) {
             mbar_wait_addr(be0 + st * 8, ph ^ 1);
-            mbar_expect_tx_addr(bf0 + st * 8, b_bytes);
-            tma_load_2d_addr(bring0 + st * b_bytes, &a.bmap, bf0 + st * 8, c * 32, a.tap_wslot[t] * a.n_pad + n0);
+            if (DBG && (a.dbg_skip & 2)) {
+              mbar_arrive_addr(bf0 + st * 8);     // timing experiment: no weight loads (wrong results)
+            } else {
+              mbar_expect_tx_addr(bf0 + st * 8, b_bytes);
+              tma_load_2d_addr(bring0 + st * b_bytes, &a.bmap, bf0 + st * 8, c * 32, a.tap_wslot[t] * a.n_pad + n0);
+            }
             if (++st == static_cast<uint32_t>(a.b_stages)) { st = 0; ph ^= 1; }
+            if (++t == t1) t = t0;
           }
           if (++c == a.kc) { c = 0; ++g; }
         }
       }
     }
     __syncwarp();
-  } else if (warp == 1) {
+  } else if (warp == 1 || warp == 7) {
+    // ---- MMA issue.  One elected thread per SUB-TILE: a thread retires ~1 instruction per 4-5 cycles and a tap costs ~60
+    // instructions of barrier / descriptor work, which is about the tensor-pipe time of the tap's 8 MMAs; with two issuing
+    // threads (independent TMEM accumulators, so their relative order does not matter) each has twice the budget.
     if (elect_one_sync()) {
+      const uint32_t sub = warp == 1 ? 0u : 1u;
       const uint32_t idesc = make_idesc_tf32(128, a.bn_tile, 0, 0);
       // A: K-major, 128B swizzle, 8-row groups at the halo line pitch; B: the usual 1024-byte groups
       const uint64_t ad_base = make_smem_desc(smem0, 16, static_cast<uint32_t>(a.hw) * 128u, 0);
@@ -516,7 +535,7 @@ __global__ void __launch_bounds__(224, 1) igemm_halo_kernel(const __grid_constan
       const uint32_t af0 = opaque_u32(smem_u32(&a_full[0])), ae0 = opaque_u32(smem_u32(&a_empty[0]));
       const uint32_t bf0 = opaque_u32(smem_u32(&b_full[0])), be0 = opaque_u32(smem_u32(&b_empty[0]));
       const uint32_t a_adv = a.halo_stride >> 4, b_adv = b_bytes >> 4;
-      const uint32_t sub_off = static_cast<uint32_t>(a.sub_off);
+      const uint32_t sub_off = sub * static_cast<uint32_t>(a.sub_off);
       uint32_t ast = 0, aph = 0, bst = 0, bph = 0;
       int ti = 0;
       long long w_a = 0, w_b = 0, w_t = 0, t_begin = 0;     // DBG: cycles this thread waited for halo tiles / weight tiles / TMEM
@@ -529,7 +548,7 @@ __global__ void __launch_bounds__(224, 1) igemm_halo_kernel(const __grid_constan
         mbar_wait(&tmem_empty_bar[acc], (use & 1) ^ 1);
         if (DBG) w_t += clock64() - c0;
         tc_fence_after();
-        const uint32_t d0 = tmem_base + static_cast<uint32_t>(acc * 2 * a.bn_tile), d1 = d0 + a.bn_tile;
+        const uint32_t d0 = tmem_base + (static_cast<uint32_t>(acc * 2) + sub) * static_cast<uint32_t>(a.bn_tile);
         uint32_t accum = 0;
         int g = g_first, c = c_first;
 #pragma unroll 1
@@ -538,26 +557,26 @@ __global__ void __launch_bounds__(224, 1) igemm_halo_kernel(const __grid_constan
           mbar_wait_addr(af0 + ast * 8, aph);
           if (DBG) w_a += clock64() - c0;
           tc_fence_after();
-          const uint64_t ad_s = ad_base + ast * a_adv;
+          const uint64_t ad_s = ad_base + ast * a_adv + sub_off;
           const int nk = (c == a.kc - 1) ? a.k_tail : 4;
-          const int t1 = a.groups[g].tap_end;
+          const int t0 = a.groups[g].tap_begin, t1 = a.groups[g].tap_end;
+          int t = t0 + static_cast<int>(rot % static_cast<uint32_t>(t1 - t0));
 #pragma unroll 1
-          for (int t = a.groups[g].tap_begin; t < t1; ++t) {
+          for (int i = t0; i < t1; ++i) {
             if (DBG) c0 = clock64();
             mbar_wait_addr(bf0 + bst * 8, bph);
             if (DBG) w_b += clock64() - c0;
             tc_fence_after();
             const uint64_t ad = ad_s + static_cast<uint32_t>(a.tap_aoff[t]) * 8u;    // rows * 128 B >> 4
-            const uint64_t ad2 = ad + sub_off;
             const uint64_t bd = bd_base + bst * b_adv;
             umma_tf32(d0, ad, bd, idesc, accum);
-            umma_tf32(d1, ad2, bd, idesc, accum);
-            if (nk > 1) { umma_tf32(d0, ad + 2, bd + 2, idesc, 1u); umma_tf32(d1, ad2 + 2, bd + 2, idesc, 1u); }
-            if (nk > 2) { umma_tf32(d0, ad + 4, bd + 4, idesc, 1u); umma_tf32(d1, ad2 + 4, bd + 4, idesc, 1u); }
-            if (nk > 3) { umma_tf32(d0, ad + 6, bd + 6, idesc, 1u); umma_tf32(d1, ad2 + 6, bd + 6, idesc, 1u); }
+            if (nk > 1) umma_tf32(d0, ad + 2, bd + 2, idesc, 1u);
+            if (nk > 2) umma_tf32(d0, ad + 4, bd + 4, idesc, 1u);
+            if (nk > 3) umma_tf32(d0, ad + 6, bd + 6, idesc, 1u);
             umma_commit_addr(be0 + bst * 8);
             accum = 1u;
             if (++bst == static_cast<uint32_t>(a.b_stages)) { bst = 0; bph ^= 1; }
+            if (++t == t1) t = t0;
           }
           umma_commit_addr(ae0 + ast * 8);
           if (++ast == static_cast<uint32_t>(a.a_stages)) { ast = 0; aph ^= 1; }
@@ -565,7 +584,7 @@ __global__ void __launch_bounds__(224, 1) igemm_halo_kernel(const __grid_constan
         }
         umma_commit(&tmem_full_bar[acc]);
       }
-      if (DBG) {
+      if (DBG && sub == 0) {
         const int cta = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
         if (cta < 2048) {
           g_trace[cta * 16 + 8] = static_cast<unsigned long long>(clock64() - t_begin);
@@ -1100,6 +1119,13 @@ static int next_pow2_cols(int n) { int c = 32; while (c < n) c *= 2; return c; }
 
 using namespace vp;
 
+static thread_local int g_engine_override = -1;
+extern "C" int vp_conv_set_engine(int engine) {
+  if (engine < -1 || engine > 1) return set_error("vp_conv_set_engine: engine must be -1 (default), 0 (box) or 1 (halo)");
+  g_engine_override = engine;
+  return 0;
+}
+
 // Host side of halo mode.  Returns 0 = launched, 1 = not eligible (the caller uses box mode), -1 = error.
 static int conv_halo_try(const vp_tensor* in, const vp_conv_geom* g, const float* wpacked, int n_pad, int kc,
                          const vp_tensor* out, const float* bias, int act, float alpha, int split_k, int accumulate,
@@ -1209,7 +1235,9 @@ static int conv_halo_try(const vp_tensor* in, const vp_conv_geom* g, const float
   A.a_stages = 2;
   long long b_budget = static_cast<long long>(smem_max) - 1024 - 2LL * A.halo_stride;
   A.b_stages = static_cast<int>(std::min<long long>(kHaloMaxBStages, b_budget / static_cast<long long>(b_bytes)));
-  if (A.b_stages < 3) return 1;
+  if (const char* e = getenv("VP_HALO_BSTAGES")) { const int v = atoi(e); if (v >= 2 && v <= A.b_stages) A.b_stages = v; }
+  if (const char* e = getenv("VP_HALO_SKIP")) A.dbg_skip = atoi(e);
+  if (A.b_stages < 3 && !getenv("VP_HALO_BSTAGES")) return 1;
   if (b_budget - A.b_stages * static_cast<long long>(b_bytes) >= static_cast<long long>(A.halo_stride) && A.b_stages >= 6) A.a_stages = 3;
   // split the (group, chunk) items over CTAs when the grid would leave SMs idle
   const int m_tiles = A.tiles_w * A.tiles_h * A.tiles_d * A.tiles_n;
@@ -1226,6 +1254,9 @@ static int conv_halo_try(const vp_tensor* in, const vp_conv_geom* g, const float
     }
   }
   A.splits = std::max(1, std::min(split_k, min_items));
+  // rotating the tap order per CTA (to spread simultaneous requests for the same weight tile over the L2) measured no gain
+  // (the kernel is issue-bound, not load-bound) and makes a sample's summation order depend on its tile: off by default
+  A.stagger = getenv("VP_HALO_STAGGER") && atoi(getenv("VP_HALO_STAGGER")) == 1;
   if (A.splits > 1) {
     if (act != VP_ACT_NONE || aux_y) return 1;
     if (!accumulate) {
@@ -1262,7 +1293,7 @@ static int conv_halo_try(const vp_tensor* in, const vp_conv_geom* g, const float
       return set_error("cudaFuncSetAttribute(igemm_halo_kernel) failed: %s", cudaGetErrorString(cudaGetLastError()));
     attr_set = true;
   }
-  const bool trace = getenv("VP_FWD_TRACE") != nullptr;
+  const bool trace = getenv("VP_FWD_TRACE") != nullptr || A.dbg_skip != 0;
   const int other = n_tiles * A.num_phases * A.splits;
   const int gx = std::min(m_tiles, std::max(1, 148 / other));
   dim3 grid(gx, n_tiles, A.num_phases * A.splits);
@@ -1270,9 +1301,9 @@ static int conv_halo_try(const vp_tensor* in, const vp_conv_geom* g, const float
     fprintf(stderr, "[halo] grid (%d,%d,%d) tile_w %d bh %d bd %d bn %d hw %d halo %u B x%d, B tile %zu B x%d, N tile %d, groups %d, kc %d k_tail %d splits %d\n",
             gx, n_tiles, A.num_phases * A.splits, A.tile_w, A.bh, A.bd, A.bn, A.hw, A.halo_bytes, A.a_stages, b_bytes, A.b_stages,
             A.bn_tile, ngroups, kc, A.k_tail, A.splits);
-    igemm_halo_kernel<true><<<grid, 224, std::max(smem, static_cast<size_t>(120 * 1024)), static_cast<cudaStream_t>(stream)>>>(A);
+    igemm_halo_kernel<true><<<grid, 256, std::max(smem, static_cast<size_t>(120 * 1024)), static_cast<cudaStream_t>(stream)>>>(A);
   } else {
-    igemm_halo_kernel<false><<<grid, 224, std::max(smem, static_cast<size_t>(120 * 1024)), static_cast<cudaStream_t>(stream)>>>(A);
+    igemm_halo_kernel<false><<<grid, 256, std::max(smem, static_cast<size_t>(120 * 1024)), static_cast<cudaStream_t>(stream)>>>(A);
   }
   (void)mode;
   return check_launch("igemm_halo_kernel");
@@ -1290,9 +1321,10 @@ static int conv_igemm_impl(const vp_tensor* in, const vp_conv_geom* g, const flo
   if (split_k > 1 && act != VP_ACT_NONE) return set_error("vp_conv_igemm: split_k needs act NONE");
   if (aux_y && split_k > 1) return set_error("vp_conv_igemm: the fused activation gradient needs split_k <= 1");
   {
-    // halo mode (one activation tile per tap GROUP, M = 256 per CTA) whenever the geometry allows it; VP_HALO=0 disables
+    // halo mode (one activation tile per tap GROUP, M = 256 per CTA) whenever the geometry allows it; VP_HALO=0 disables,
+    // vp_conv_set_engine() overrides per thread (the host layer times both engines once per geometry and keeps the faster)
     const char* e = getenv("VP_HALO");
-    const int halo_mode = e ? atoi(e) : 1;
+    const int halo_mode = g_engine_override >= 0 ? g_engine_override : (e ? atoi(e) : 1);
     if (halo_mode > 0) {
       const int rc = conv_halo_try(in, g, wpacked, n_pad, kc, out, bias, act, alpha, split_k, accumulate, aux_y, aux_add, aux_act,
                                    halo_mode, stream);

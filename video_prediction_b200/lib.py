@@ -78,15 +78,62 @@ def geom(k, s=(1, 1, 1), p=(0, 0, 0), transposed=False):
     return VpConvGeom(k[0], k[1], k[2], s[0], s[1], s[2], p[0], p[1], p[2], int(transposed))
 
 
+_ENGINE_CHOICE = {}     # geometry signature -> 0 (box) / 1 (halo), measured once per process
+
+
+def _conv_key(x_view, g, n_pad, kc, out_view, act, extra):
+    return (x_view.n, x_view.d, x_view.h, x_view.w, x_view.c, out_view.n, out_view.d, out_view.h, out_view.w, out_view.c,
+            out_view.c == out_view.cstride, g.kd, g.kh, g.kw, g.sd, g.sh, g.sw, g.pd, g.ph, g.pw, g.transposed, n_pad, kc, act, extra)
+
+
+def _pick_engine(key, call, idempotent):
+    """Both engines compute the same convolution; which one is faster depends on the geometry (plane size, taps per halo
+    group, N).  The first call of a geometry times both (3 launches each, CUDA events) and the winner is cached for the
+    process.  VP_HALO=0/1 or VP_AUTOTUNE=0 pin the engine; calls that accumulate into their output are never timed."""
+    choice = _ENGINE_CHOICE.get(key)
+    if choice is not None:
+        return choice
+    if os.environ.get('VP_AUTOTUNE', '1') == '0' or 'VP_HALO' in os.environ or not idempotent or torch.cuda.is_current_stream_capturing():
+        return -1
+    times = []
+    for eng in (0, 1):
+        check(lib().vp_conv_set_engine(eng))
+        call()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(3):
+            call()
+        e1.record()
+        e1.synchronize()
+        times.append(e0.elapsed_time(e1))
+    check(lib().vp_conv_set_engine(-1))
+    choice = 0 if times[0] <= times[1] else 1
+    _ENGINE_CHOICE[key] = choice
+    return choice
+
+
 def conv_igemm(x_view, g, wpacked, n_pad, kc, out_view, bias=None, act=ACT_NONE, alpha=0.0, split_k=1, accumulate=0):
-    check(lib().vp_conv_igemm(C.byref(x_view), C.byref(g), ptr(wpacked), n_pad, kc, C.byref(out_view), ptr(bias),
-                              act, C.c_float(alpha), split_k, int(accumulate), stream_ptr()))
+    def call():
+        check(lib().vp_conv_igemm(C.byref(x_view), C.byref(g), ptr(wpacked), n_pad, kc, C.byref(out_view), ptr(bias),
+                                  act, C.c_float(alpha), split_k, int(accumulate), stream_ptr()))
+    # an explicit split_k > 1 adds atomically into a caller-cleared output: repeating the call (timing) would change it
+    eng = _pick_engine(_conv_key(x_view, g, n_pad, kc, out_view, act, ('fwd', split_k)), call, not accumulate and split_k <= 1)
+    check(lib().vp_conv_set_engine(eng))
+    call()
+    if eng >= 0:
+        check(lib().vp_conv_set_engine(-1))
 
 
 def conv_igemm_actgrad(x_view, g, wpacked, n_pad, kc, out_view, act_output_addr, addend_addr, act, alpha=0.0, accumulate=0):
-    check(lib().vp_conv_igemm_actgrad(C.byref(x_view), C.byref(g), ptr(wpacked), n_pad, kc, C.byref(out_view),
-                                      C.c_void_p(act_output_addr), C.c_void_p(addend_addr or 0), act, C.c_float(alpha),
-                                      int(accumulate), stream_ptr()))
+    def call():
+        check(lib().vp_conv_igemm_actgrad(C.byref(x_view), C.byref(g), ptr(wpacked), n_pad, kc, C.byref(out_view),
+                                          C.c_void_p(act_output_addr), C.c_void_p(addend_addr or 0), act, C.c_float(alpha),
+                                          int(accumulate), stream_ptr()))
+    eng = _pick_engine(_conv_key(x_view, g, n_pad, kc, out_view, act, ('actgrad', bool(addend_addr))), call, not accumulate)
+    check(lib().vp_conv_set_engine(eng))
+    call()
+    if eng >= 0:
+        check(lib().vp_conv_set_engine(-1))
 
 
 def tf32_residual(x):
@@ -101,6 +148,11 @@ def exact_mode():
     """VP_EXACT=1: every tensor-core convolution (forward, dgrad, wgrad) runs as three TF32 passes
     hi*hi + lo*hi + hi*lo with fp32 accumulation = fp32-exact up to 2^-21 (debug / parity mode, ~3x the conv time)."""
     return os.environ.get('VP_EXACT', '0') == '1'
+
+
+def engine_choices():
+    """geometry signature -> engine chosen by the autotuner so far (for reports)."""
+    return dict(_ENGINE_CHOICE)
 
 
 def conv_flat(x_view, valid_h, valid_w, g, wpacked, n_pad, kc, out_view, bias=None, act=ACT_NONE, alpha=0.0, split_k=1,
