@@ -113,6 +113,24 @@ if __name__ == '__main__':
     run('masks dgrad', (NB, 64, 64), 53, 8, (1, 3, 3), (1, 1, 1), (0, 1, 1), dgrad=True, cs=60)
     run('posterior 4x4 s2 64->128', (NB * 5, 32, 32), 64, 128, (1, 4, 4), (1, 2, 2), (0, 1, 1), bias=True)
     # video discriminator (networks.py:83-102), one tower pass = 2B clips
+    run('D sn_conv0_0 k3 s1 3->32', (NB, 10, 64, 64), 3, 32, (3, 3, 3), (1, 1, 1), (1, 1, 1), bias=True, act=L.ACT_LRELU, iters=5)
+    run('D sn_conv0_0 dgrad', (NB, 10, 64, 64), 3, 32, (3, 3, 3), (1, 1, 1), (1, 1, 1), dgrad=True, iters=5)
+    if True:
+        x = rnd(NB, 10, 64, 64, 4)
+        w = rnd(3, 3, 3, 3, 32, seed=1, scale=0.05)
+        o = torch.zeros(NB, 10, 64, 64, 32, device='cuda')
+        one = torch.ones(1, device='cuda')
+        b = rnd(32, seed=2)
+        for _ in range(2):
+            L.conv3d_c4_fwd(x, w, one, b, o, NB, 10, 64, 64, 3, 0.1)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            L.conv3d_c4_fwd(x, w, one, b, o, NB, 10, 64, 64, 3, 0.1)
+        e1.record()
+        torch.cuda.synchronize()
+        print('D sn_conv0_0 CUDA-core kernel (conv3d_c4_fwd): %.1f us' % (e0.elapsed_time(e1) / 5 * 1e3))
     run('D sn_conv0_1 k4 s(1,2,2)', (NB, 10, 64, 64), 32, 64, (4, 4, 4), (1, 2, 2), (1, 1, 1), bias=True, act=L.ACT_LRELU, iters=5)
     run('D sn_conv0_1 dgrad', (NB, 10, 64, 64), 32, 64, (4, 4, 4), (1, 2, 2), (1, 1, 1), dgrad=True, iters=5)
     run('D sn_conv1_0 k3 s1', (NB, 9, 32, 32), 64, 64, (3, 3, 3), (1, 1, 1), (1, 1, 1), bias=True, act=L.ACT_LRELU, iters=5)

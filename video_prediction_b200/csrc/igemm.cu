@@ -787,6 +787,8 @@ __global__ void __launch_bounds__(192, 1) igemm_wgrad_kernel(const __grid_consta
       const uint64_t sh_base = make_smem_desc(smem0, kSub, 512, 0, 1);
       const uint32_t per_adv = static_cast<uint32_t>(n_per) * kSub >> 4, sh_adv = static_cast<uint32_t>(n_shared) * kSub >> 4;
       const uint32_t stage_adv = stage_bytes >> 4;
+      const int merge = (a.dbg_poll & 2) ? 1 : max(1, 256 / ncols);      // taps per merged MMA (dbg_poll bit 1: VP_WGRAD_MERGE=0)
+      const uint32_t idesc_m = make_idesc_tf32(128, min(merge, nt) * ncols, 1, 1);
       uint32_t b_off = 0, ph = 0, adv = 0, first = 1;
 #pragma unroll 1
       for (int it = it0; it < it1; ++it) {
@@ -795,12 +797,25 @@ __global__ void __launch_bounds__(192, 1) igemm_wgrad_kernel(const __grid_consta
         const uint64_t shd = sh_base + adv;
         uint64_t ptd = shd + sh_adv;
         const uint32_t accum0 = first ? 0u : 1u;
+        if (!a_shifted && merge > 1) {
+          // the shifted x tiles of consecutive taps are consecutive 32-channel groups in shared memory (LBO = kSub), and the
+          // taps' accumulators are consecutive TMEM columns: `merge` taps run as ONE MMA with N = merge * ncols (<= 256)
+          // instead of `merge` narrow ones (an N = 32 MMA costs 40 cycles, an N = 256 one 128)
 #pragma unroll 1
-        for (int t = 0; t < nt; ++t, ptd += per_adv) {
-          const uint64_t ad0 = a_shifted ? ptd : shd, bd0 = a_shifted ? shd : ptd;
-          const uint32_t d_tmem = tmem_base + t * ncols;
+          for (int t = 0; t < nt; t += merge, ptd += merge * per_adv) {
+            const uint32_t idesc_g = (nt - t >= merge) ? idesc_m : make_idesc_tf32(128, (nt - t) * ncols, 1, 1);
+            const uint32_t d_tmem = tmem_base + t * ncols;
 #pragma unroll
-          for (int k = 0; k < kWgPix / 8; ++k) umma_tf32(d_tmem, ad0 + k * 64, bd0 + k * 64, idesc, k == 0 ? accum0 : 1u);
+            for (int k = 0; k < kWgPix / 8; ++k) umma_tf32(d_tmem, shd + k * 64, ptd + k * 64, idesc_g, k == 0 ? accum0 : 1u);
+          }
+        } else {
+#pragma unroll 1
+          for (int t = 0; t < nt; ++t, ptd += per_adv) {
+            const uint64_t ad0 = a_shifted ? ptd : shd, bd0 = a_shifted ? shd : ptd;
+            const uint32_t d_tmem = tmem_base + t * ncols;
+#pragma unroll
+            for (int k = 0; k < kWgPix / 8; ++k) umma_tf32(d_tmem, ad0 + k * 64, bd0 + k * 64, idesc, k == 0 ? accum0 : 1u);
+          }
         }
         umma_commit_addr(empty0 + b_off);
         first = 0;
@@ -1541,6 +1556,7 @@ extern "C" int vp_conv_wgrad(const vp_tensor* x, const vp_tensor* dy, const vp_c
   const int groups = ceil_div(A.num_taps, tg);
   tg = ceil_div(A.num_taps, groups);     // balance the groups
   A.tap_group = tg;
+  if (const char* e = getenv("VP_WGRAD_MERGE")) { if (atoi(e) == 0) A.dbg_poll |= 2; }
   A.tmem_cols = next_pow2_cols(tg * 32 * nb_max);
   A.wg_stage_bytes = static_cast<uint32_t>(n_shared + tg * n_per) * kWgPix * 128;
   A.wg_stages = std::max(2, std::min(kWgMaxStages, static_cast<int>((200u * 1024u) / A.wg_stage_bytes)));

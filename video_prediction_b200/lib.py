@@ -109,6 +109,9 @@ def _pick_engine(key, call, idempotent):
     check(lib().vp_conv_set_engine(-1))
     choice = 0 if times[0] <= times[1] else 1
     _ENGINE_CHOICE[key] = choice
+    if os.environ.get('VP_AUTOTUNE_LOG'):
+        import sys
+        sys.stderr.write('[autotune] %s box %.1f us halo %.1f us -> %s\n' % (key, times[0] / 3 * 1e3, times[1] / 3 * 1e3, 'halo' if choice else 'box'))
     return choice
 
 

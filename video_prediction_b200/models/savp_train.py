@@ -94,7 +94,10 @@ class SNLayer(object):
         return (not self.is_fc) and self.k == 3 and tuple(self.stride) == (1, 1, 1) and self.cin_ref <= 3 and self.co == 32
 
     def fwd(self, x, out):
-        if self.cuda_core:
+        # the first layer's FORWARD runs on the tensor-core engine: halo mode loads one activation tile per 9 taps, which
+        # the box mode of round 1 could not (1070 us box / 417 us CUDA cores / 250 us halo per 32 clips); its weight
+        # gradient stays on the CUDA-core kernel (4 input channels = 3 % MMA efficiency as a GEMM over pixels)
+        if self.cuda_core and os.environ.get('VP_D0_FWD_CUDA_CORE', '0') == '1':
             P = self.m.params
             n, d, h, w = x.shape[:4]
             L.conv3d_c4_fwd(x, P[self.wname], self.sigma, P[self.bname], out, n, d, h, w, self.cin_ref, 0.1)
