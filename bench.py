@@ -4,15 +4,16 @@
   python bench.py --gpus N --steps K --warmup W            (N>1: launched by torch.distributed.run, one rank per GPU)
   python bench.py --impl reference ...                      (the CPU arm: the oracle port on the host cores)
 
-A "step" is one full optimisation step of config[1] of BASELINE.json (SAVP, bair_action_free/ours_savp hparams:
-VAE+GAN, 64x64x3, 2 context + 10 predicted, batch 16 per GPU): generator forward (posterior + prior unrolls),
+A "step" is one full optimisation step of --config (default cfg2 = configs[1] of BASELINE.json: SAVP, bair_action_free/ours_savp
+hparams: VAE+GAN, 64x64x3, 2 context + 10 predicted, batch 16 per GPU): generator forward (posterior + prior unrolls),
 4 discriminator towers, D backward + Adam(D), post-update D forward, G backward (BPTT) + Adam(G).
 frames/sec = global_batch * (T-1) generated frames per step / step time.
 
 `value`   : inputs resident in HBM, the whole step replayed from a CUDA graph, timed with CUDA events, max over ranks.
 `e2e`     : the public API call (model.train_step(inputs)) with HOST inputs: pinned H2D of the batch + D2H of the losses
             inside the timed region.
-`roofline`: the ConvLSTM gate convolutions (rnn_ops.py:121; the north-star kernel) timed alone with CUDA events.
+`roofline`: the ConvLSTM gate convolutions (rnn_ops.py:121; the north-star kernel) timed alone with CUDA events, and
+            `roofline.whole_engine`: every tensor-core call of one step (forward + dgrad + wgrad).
 """
 from __future__ import annotations
 
@@ -27,12 +28,41 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-SAVP_HPARAMS = dict(  # hparams/bair_action_free/ours_savp/model_hparams.json + dataset-provided frame counts
-    context_frames=2, sequence_length=12, batch_size=16, lr=0.0002, beta1=0.5, beta2=0.999, l1_weight=100.0, l2_weight=0.0,
-    kl_weight=1.0, video_sn_vae_gan_weight=0.1, video_sn_gan_weight=0.1, vae_gan_feature_cdist_weight=10.0,
-    gan_feature_cdist_weight=0.0, state_weight=0.0)
-IMAGE = (64, 64, 3)
-PER_GPU_BATCH = 16
+SAVP = dict(lr=0.0002, beta1=0.5, beta2=0.999, l1_weight=100.0, l2_weight=0.0, kl_weight=1.0, video_sn_vae_gan_weight=0.1,
+            video_sn_gan_weight=0.1, vae_gan_feature_cdist_weight=10.0, gan_feature_cdist_weight=0.0, state_weight=0.0)
+# BASELINE.json `configs`: name -> hparams (shipped hparams files of the reference), image shape, action dim,
+# per-GPU batch.  cfg2 is the configuration the metric is quoted on; the others are parity-test cases that can be timed too.
+CONFIGS = {
+    'cfg1': dict(what='BASELINE configs[0]: deterministic generator (hparams/bair_action_free/ours_deterministic_l1: no VAE, no GAN, '
+                      'L1), synthetic 64x64x3, 2 context + 10 predicted',
+                 hparams=dict(context_frames=2, sequence_length=12, batch_size=4, lr=0.001, beta1=0.9, beta2=0.999, l1_weight=1.0,
+                              l2_weight=0.0, kl_weight=0.0, video_sn_vae_gan_weight=0.0, video_sn_gan_weight=0.0, state_weight=0.0, nz=0),
+                 image=(64, 64, 3), actions=0, batch=4),
+    'cfg2': dict(what='BASELINE configs[1]: SAVP (VAE+GAN) bair_action_free/ours_savp hparams, synthetic 64x64x3, 2 context + 10 '
+                      'predicted',
+                 hparams=dict(SAVP, context_frames=2, sequence_length=12, batch_size=16), image=(64, 64, 3), actions=0, batch=16),
+    'cfg3': dict(what='BASELINE configs[2]: action-conditioned SAVP (ours_savp weights; the reference ships no hparams/bair), synthetic '
+                      '64x64x3 + 4-dim actions, 2 context + 28 predicted',
+                 hparams=dict(SAVP, context_frames=2, sequence_length=30, batch_size=32), image=(64, 64, 3), actions=4, batch=32),
+    'cfg4': dict(what='BASELINE configs[3]: SAVP synthetic 128x128x3, 4 context + 12 predicted (CDNA warp stress)',
+                 hparams=dict(SAVP, context_frames=4, sequence_length=16, batch_size=8), image=(128, 128, 3), actions=0, batch=8),
+    'cfg5': dict(what='BASELINE configs[4]: VAE-only (hparams/kth/ours_vae_l1: nz=32, L1 + KL 1e-5, no GAN), KTH-shape synthetic '
+                      '64x64x1, 10 context + 20 predicted',
+                 hparams=dict(context_frames=10, sequence_length=30, batch_size=32, lr=0.001, beta1=0.9, beta2=0.999, l1_weight=1.0,
+                              l2_weight=0.0, kl_weight=1e-05, video_sn_vae_gan_weight=0.0, video_sn_gan_weight=0.0, state_weight=0.0,
+                              nz=32),
+                 image=(64, 64, 1), actions=0, batch=32),
+}
+CFG = CONFIGS['cfg2']
+SAVP_HPARAMS = CFG['hparams']          # kept for tests/profile_step.py
+IMAGE = CFG['image']
+PER_GPU_BATCH = CFG['batch']
+
+
+def select_config(name):
+    global CFG, SAVP_HPARAMS, IMAGE, PER_GPU_BATCH
+    CFG = CONFIGS[name]
+    SAVP_HPARAMS, IMAGE, PER_GPU_BATCH = CFG['hparams'], CFG['image'], CFG['batch']
 
 
 def load_peaks():
@@ -79,34 +109,41 @@ def synthetic_batch(batch, seed):
     g = torch.Generator().manual_seed(seed)
     T = SAVP_HPARAMS['sequence_length']
     imgs = torch.rand(batch, T, *IMAGE, generator=g)
-    return {'images': imgs.pin_memory() if torch.cuda.is_available() else imgs}
+    out = {'images': imgs}
+    if CFG['actions']:
+        out['actions'] = torch.randn(batch, T - 1, CFG['actions'], generator=g)
+    return {k: (v.pin_memory() if torch.cuda.is_available() else v) for k, v in out.items()}
 
 
-def oracle_step_time(batch, steps):
-    """Times full SAVP training steps of the CPU oracle (the port of the reference's TF1 graph) at batch `batch`.
-    Returns (seconds per step, threads used)."""
+CPU_THREADS = 32      # the CPU arm is pinned to a fixed intra-op thread count (<= the box's cores) so that runs are comparable
+
+
+def oracle_step_time(batch, steps, threads=None):
+    """Times full training steps of the CPU oracle (the port of the reference's TF1 graph) of the selected config at batch
+    `batch`.  One untimed warm-up step (allocator / oneDNN primitive cache), then `steps` timed ones.
+    Returns (list of seconds per step, threads used)."""
     import torch
     from oracle import savp_oracle as O
+    torch.set_num_threads(max(1, min(threads or CPU_THREADS, os.cpu_count() or 1)))
     hk = {k: v for k, v in SAVP_HPARAMS.items() if k != 'batch_size'}
     hp = O.make_hparams(**hk)
-    params, _ = O.init_params(hp, IMAGE, seed=0)
+    params, _ = O.init_params(hp, IMAGE, action_dim=CFG['actions'], seed=0)
     opt = dict(m={k: torch.zeros_like(v) for k, v in params.items()}, v={k: torch.zeros_like(v) for k, v in params.items()}, t=0)
     times = []
     for s in range(steps + 1):
-        inputs, noise = O.make_synthetic_inputs(hp, batch, IMAGE, seed=s, smooth=False)
+        inputs, noise = O.make_synthetic_inputs(hp, batch, IMAGE, action_dim=CFG['actions'], seed=s, smooth=False)
         t0 = time.time()
         res = O.train_step(params, opt, hp, inputs, noise, step=s)
         times.append(time.time() - t0)
         params = res['params']
-    times = times[1:] if len(times) > 1 else times     # first step warms the allocator / oneDNN primitive cache
-    return sum(times) / len(times), torch.get_num_threads()
+    return times[1:], torch.get_num_threads()
 
 
-def cpu_baseline_subprocess(batch, steps, timeout_s=240):
-    """Runs the oracle timing in a fresh interpreter (no CUDA context, torch's default intra-op thread pool = the
-    host's physical cores) so that the GPU process's threads cannot interfere; bounded by a timeout."""
-    code = ('import sys, json; sys.path.insert(0, %r); import bench; '
-            't, n = bench.oracle_step_time(%d, %d); print(json.dumps(dict(sec_per_step=t, threads=n)))' % (ROOT, batch, steps))
+def cpu_baseline_subprocess(config, batch, steps, timeout_s=240):
+    """Runs the oracle timing in a fresh interpreter (no CUDA context) so that the GPU process's threads cannot interfere;
+    bounded by a timeout."""
+    code = ('import sys, json; sys.path.insert(0, %r); import bench; bench.select_config(%r); '
+            't, n = bench.oracle_step_time(%d, %d); print(json.dumps(dict(sec=t, threads=n)))' % (ROOT, config, batch, steps))
     env = dict(os.environ, CUDA_VISIBLE_DEVICES='')
     try:
         r = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, timeout=timeout_s, env=env)
@@ -116,22 +153,30 @@ def cpu_baseline_subprocess(batch, steps, timeout_s=240):
         return None
 
 
+def cpu_sample_batch():
+    """The CPU arm runs a bounded sample of the workload: full training steps at a small batch (cost is linear in the batch)."""
+    return 1 if IMAGE[0] >= 128 or SAVP_HPARAMS['sequence_length'] > 16 else 2
+
+
 def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    sample_b = 2
-    frames = sample_b * (SAVP_HPARAMS['sequence_length'] - 1)
-    k = max(1, min(args.steps, 3))
-    t, cores = oracle_step_time(sample_b, k)
-    fps = frames / t
-    sample = '%d full SAVP training steps at batch %d (of %d) on the host, torch/oneDNN fp32' % (k, sample_b, PER_GPU_BATCH)
+    sample_b = cpu_sample_batch()
+    S = SAVP_HPARAMS['sequence_length'] - 1
+    k = max(3, min(args.steps, 5))
+    times, cores = oracle_step_time(sample_b, k)
+    med = sorted(times)[len(times) // 2]
+    fps = sample_b * S / med
+    sample = ('%d full training steps (+1 warm-up) at batch %d (of %d) on the host, torch/oneDNN fp32, %d intra-op threads: median %.2f s, '
+              'min %.2f s, max %.2f s per step' % (k, sample_b, PER_GPU_BATCH, cores, med, min(times), max(times)))
     line = dict(metric='frames/sec SAVP 64x64 2+10 (training)', value=fps, unit='frames/s', n_gpus=args.gpus, steps=k,
-                warmup=1, ms_per_step=t * 1e3, higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f32',
+                warmup=1, ms_per_step=med * 1e3, higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f32',
                 data='synthetic', impl='reference',
-                config=dict(workload='BASELINE configs[1]: SAVP (VAE+GAN) bair_action_free hparams, 64x64x3, 2+10; CPU sample batch %d' % sample_b,
+                config=dict(workload='%s; CPU sample batch %d' % (CFG['what'], sample_b), name=args.config,
                             note='the TF1 reference cannot run here (needs tensorflow 1.x); this is its line-by-line CPU port (oracle/)'),
-                cpu_baseline=dict(value=fps, unit='frames/s', cores=cores, kind='port', sample=sample),
+                cpu_baseline=dict(value=fps, unit='frames/s', cores=cores, kind='port', sample=sample,
+                                  frames_per_s_min=sample_b * S / max(times), frames_per_s_max=sample_b * S / min(times)),
                 e2e=dict(value=fps, unit='frames/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0))
     print(json.dumps(line))
 
@@ -189,32 +234,47 @@ def time_gate_kernels(model, iters=3):
     return flops, ms, per_layer
 
 
+def engine_profile(model, batch):
+    """Whole-engine roofline: ONE eager training step with every tensor-core engine call (forward + dgrad = `igemm`, weight
+    gradients = `wgrad`) bracketed by CUDA events on its launching stream; algorithmic FLOPs as SURVEY.md 8(d) counts them
+    (internal channel counts: the image's 3 channels are stored as 4).  The discriminator towers run sequentially here
+    (VP_CONCURRENT_D=0) so that the event pairs do not time overlapping kernels."""
+    import torch
+    from video_prediction_b200 import lib as L
+    old = os.environ.get('VP_CONCURRENT_D')
+    os.environ['VP_CONCURRENT_D'] = '0'
+    try:
+        model.stage_step()
+        torch.cuda.synchronize()
+        L.profile_engine(True)
+        model._step_device(getattr(model, '_allreduce', None))
+        model.global_step += 1
+        return L.profile_engine(False)
+    finally:
+        if old is None:
+            os.environ.pop('VP_CONCURRENT_D', None)
+        else:
+            os.environ['VP_CONCURRENT_D'] = old
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
     from video_prediction_b200 import lib as L
-    from video_prediction_b200.models import SAVPVideoPredictionModel
+    from video_prediction_b200.models import get_model_class
     rank = int(os.environ.get('RANK', '0'))
     local = int(os.environ.get('LOCAL_RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
     torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
     B = PER_GPU_BATCH
-    model = SAVPVideoPredictionModel(mode='train', hparams_dict=dict(SAVP_HPARAMS), num_gpus=1)
-    model.world_size = world
+    # data parallelism lives in the model: build_graph reads torchrun's env (dp.init_from_env), broadcasts rank 0's variables
+    # and train_step all-reduces the two flat gradient buffers (weak scaling: num_gpus=1 -> every rank feeds its own batch)
+    model = get_model_class('savp')(mode='train', hparams_dict=dict(SAVP_HPARAMS), num_gpus=1)
     batch0 = synthetic_batch(B, seed=1000 * rank)
-    log('building model (batch %d per GPU)' % B)
+    log('building model %s (batch %d per GPU)' % (args.config, B))
     model.build_graph(batch0)
+    assert model.world_size == world
     log('built; warming up the eager path')
-    if world > 1:   # identical initial weights on every replica (base_model.py:640-646: post_init_ops copy tower 0)
-        dist.broadcast(model.g_flat, 0)
-        dist.broadcast(model.d_flat, 0)
-        for k, v in model.params.items():
-            if k.endswith('/u'):
-                dist.broadcast(v, 0)
-        model._pack_all()
-    allreduce = (lambda buf: dist.all_reduce(buf)) if world > 1 else None
     S = model.S
     frames_per_step = world * B * S
 
@@ -223,7 +283,7 @@ def run_ours(args):
     h2d = sum(v.numel() * 4 for v in batches[0].values())
     model.use_cuda_graph = not args.no_graph
     for i in range(max(3, args.warmup) + 1):
-        model.train_step(batches[i % 4], allreduce=allreduce)
+        model.train_step(batches[i % 4])
         model.losses()
     torch.cuda.synchronize()
     log('timing e2e')
@@ -234,8 +294,8 @@ def run_ours(args):
     t0 = time.time()
     e0.record()
     for i in range(k_e2e):
-        model.train_step(batches[i % 4], allreduce=allreduce)
-        lv = model.losses()              # D2H of the step's losses
+        model.train_step(batches[i % 4])
+        lv = model.losses()              # D2H of the step's losses (mean over replicas)
     e1.record()
     torch.cuda.synchronize()
     e2e_ms = max(e0.elapsed_time(e1), (time.time() - t0) * 1e3) / k_e2e
@@ -244,17 +304,16 @@ def run_ours(args):
 
     # ---------------- value: HBM-resident inputs, whole step as one CUDA graph
     graph = model._graph
-    launches_per_step = None
     model.set_inputs(batches[0])
     if graph is None:
         model.use_cuda_graph = False
 
     def one_step():
-        model.train_step(allreduce=allreduce)       # inputs already resident; replays the captured graph
+        model.train_step()       # inputs already resident; replays the captured graph
     # launches per step: counted on one eager execution of the same device step
     c0 = L.launch_count()
     model.stage_step()
-    model._step_device(allreduce)
+    model._step_device(getattr(model, '_allreduce', None))
     model.global_step += 1
     launches_per_step = L.launch_count() - c0
     log('graph=%s launches/step=%s; warm-up' % (graph is not None, launches_per_step))
@@ -285,25 +344,42 @@ def run_ours(args):
     losses = model.losses()
     finite = all(v == v for v in losses.values())
 
-    # ---------------- roofline of the dominant kernel + CPU baseline (rank 0, N = 1 only for the CPU leg)
+    # ---------------- rooflines + CPU baseline (rank 0; the CPU leg at N = 1 only)
+    prof = None if args.no_roofline else engine_profile(model, batches[0])     # every rank runs the same (collective-bearing) step
     if rank == 0:
         peaks = load_peaks()
-        flops, gate_ms, per_layer = time_gate_kernels(model)
-        log('gate kernels timed; cpu baseline leg')
-        achieved = flops / gate_ms / 1e9     # TFLOP/s over the five gate convolutions of one timestep
-        roof = dict(bound='tensor', kernel='igemm_fwd_kernel (ConvLSTM gate convolutions, tcgen05 kind::tf32)',
-                    achieved=achieved, peak=peaks['bf16'], unit='TFLOP/s', frac=achieved / peaks['bf16'],
-                    peak_source=peaks['src'] + ' cuBLAS bf16 (burst); tf32 MMA rate is half of bf16',
-                    peak_tf32_equiv=peaks['bf16'] / 2, frac_of_tf32_peak=achieved / (peaks['bf16'] / 2),
-                    per_layer=per_layer, **ncu_traffic())
+        roof = None
+        if not args.no_roofline:
+            flops, gate_ms, per_layer = time_gate_kernels(model)
+            log('gate kernels timed; cpu baseline leg')
+            achieved = flops / gate_ms / 1e9     # TFLOP/s over the gate convolutions of one timestep
+            roof = dict(bound='tensor', kernel='ConvLSTM gate convolutions (rnn_ops.py:121) on the tcgen05 kind::tf32 engine, forward',
+                        achieved=achieved, peak=peaks['bf16'], unit='TFLOP/s', frac=achieved / peaks['bf16'],
+                        peak_source=peaks['src'] + ' cuBLAS bf16 (burst); the tf32 MMA rate is half of bf16',
+                        peak_tf32_equiv=peaks['bf16'] / 2, frac_of_tf32_peak=achieved / (peaks['bf16'] / 2),
+                        per_layer=per_layer, **ncu_traffic())
+            tot_f = sum(d['flops'] for d in prof.values())
+            tot_ms = sum(d['ms'] for d in prof.values())
+            sustained = (peaks.get('bf16_sustained') or peaks['bf16']) / 2
+            roof['whole_engine'] = dict(
+                what='every tensor-core engine call of ONE training step (forward + dgrad + wgrad of all convolutions), '
+                     'algorithmic FLOPs / summed CUDA-event time of the calls (eager step, towers sequential)',
+                tflop_per_step=tot_f / 1e12, engine_ms_per_step=tot_ms, achieved=tot_f / tot_ms / 1e9, unit='TFLOP/s',
+                peak_tf32_equiv_sustained=sustained, frac_of_tf32_peak_sustained=tot_f / tot_ms / 1e9 / sustained,
+                frac_of_bf16_peak_sustained=tot_f / tot_ms / 1e9 / (2 * sustained),
+                by_kind={k: dict(calls=d['calls'], tflop=d['flops'] / 1e12, ms=d['ms'], tflops=d['flops'] / d['ms'] / 1e9)
+                         for k, d in prof.items()},
+                whole_step_tflops=tot_f / ms / 1e9)
         cpu = None
         if world == 1 and not args.no_cpu:
-            sb = 2
-            r = cpu_baseline_subprocess(sb, 2)
+            sb = cpu_sample_batch()
+            r = cpu_baseline_subprocess(args.config, sb, 3)
             if r is not None:
-                cpu = dict(value=sb * S / r['sec_per_step'], unit='frames/s', cores=r['threads'], kind='port',
-                           sample='2 full SAVP training steps at batch %d (of %d) with the CPU oracle (torch/oneDNN fp32, '
-                                  '%d intra-op threads, %d logical CPUs)' % (sb, B, r['threads'], os.cpu_count() or 0))
+                med = sorted(r['sec'])[len(r['sec']) // 2]
+                cpu = dict(value=sb * S / med, unit='frames/s', cores=r['threads'], kind='port',
+                           sample='3 full training steps (+1 warm-up) at batch %d (of %d) with the CPU oracle (torch/oneDNN fp32, %d '
+                                  'intra-op threads of %d logical CPUs): median %.2f s, min %.2f s, max %.2f s per step'
+                                  % (sb, B, r['threads'], os.cpu_count() or 0, med, min(r['sec']), max(r['sec'])))
             else:
                 cpu = dict(value=None, unit='frames/s', cores=os.cpu_count(), kind='port', sample='timed out')
         clocks = sampler.summary()
@@ -312,14 +388,13 @@ def run_ours(args):
                     scaling='weak', vs_baseline=None, dtype='tf32 tensor-core convolutions, fp32 accumulate / state / optimizer',
                     sequences_per_s=world * B / ms * 1e3,     # the reference's own `image/sec` print (train.py:331)
                     data='synthetic',
-                    config=dict(workload='BASELINE configs[1]: SAVP (VAE+GAN) bair_action_free/ours_savp hparams, synthetic 64x64x3, '
-                                         '2 context + 10 predicted, batch %d per GPU; full step = G fwd (2 unrolls) + 4 D towers + '
-                                         'Adam(D) + post-update D fwd + G BPTT + Adam(G)' % B,
-                                global_batch=world * B, per_gpu_batch=B, sequence_length=12, parallelism='dp%d' % world,
-                                cuda_graph=graph is not None,
-                                l2='working set of one step (~8 GB of activations) is far larger than the 126 MB L2'),
+                    config=dict(workload='%s, batch %d per GPU; full step = G fwd (posterior + prior unrolls) + D towers + Adam(D) + '
+                                         'post-update D fwd + G BPTT + Adam(G)' % (CFG['what'], B), name=args.config,
+                                global_batch=world * B, per_gpu_batch=B, sequence_length=SAVP_HPARAMS['sequence_length'],
+                                parallelism='dp%d' % world, cuda_graph=graph is not None,
+                                l2='working set of one step (GBs of activations) is far larger than the 126 MB L2'),
                     e2e=dict(value=frames_per_step / e2e_ms * 1e3, unit='frames/s', ms_per_step=e2e_ms, h2d_bytes_per_step=h2d,
-                             d2h_bytes_per_step=d2h, api='SAVPVideoPredictionModel.train_step(host inputs) + .losses()'),
+                             d2h_bytes_per_step=d2h, api='get_model_class("savp")(...).train_step(host inputs) + .losses()'),
                     gpu_launches=int(launches_per_step) * args.steps, gpu_launches_per_step=int(launches_per_step),
                     roofline=roof, cpu_baseline=cpu, clocks=clocks, losses_finite=finite,
                     losses={k: round(v, 6) for k, v in losses.items() if v})
@@ -353,7 +428,10 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--no-graph', action='store_true')
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
+    ap.add_argument('--no-roofline', action='store_true', help='skip the roofline legs (gate kernels, whole-engine profile)')
+    ap.add_argument('--config', default='cfg2', choices=sorted(CONFIGS), help='BASELINE.json configs[i-1]; the metric is quoted on cfg2')
     args = ap.parse_args()
+    select_config(args.config)
     if args.impl == 'reference':
         run_reference(args)
     else:

@@ -220,6 +220,16 @@ int vp_avgpool_bwd(const float* dy, float* dx, int dx_cstride, int n, int positi
 int vp_sample_z_bwd(const float* mu, const float* lss, const float* eps, const float* dz, float* dmu, float* dlss,
                     int total, const float* kl_scale, vp_stream_t stream);
 
+/* transformation = 'flow' (savp_model.py:522-530, 577-578; flow_ops.image_warp, flow_ops.py:4-79; apply_flows, :955-965):
+ * NK backward bilinear warps of `image` (float4 pixels) by the flows-conv output [N,H,W,flows_cstride] (channel k = x-flow of
+ * transform k, channel NK + k = y-flow), written with the previous and the first image as float4 slots 0..NK+1 of `layers`
+ * (the slot layout of vp_cdna_apply).  Backward: dimage += (zero-filled by the caller), dflows = (same layout as flows). */
+int vp_flow_apply(const float* image, const float* first_image, const float* flows, int flows_cstride, float* layers,
+                  int layers_cstride, int n, int h, int w, int nk, vp_stream_t stream);
+int vp_flow_apply_bwd(const float* image, const float* flows, int flows_cstride, const float* d_a, int d_a_cstride,
+                      const float* d_b, int d_b_cstride, float* dimage, float* dflows, int n, int h, int w, int nk,
+                      vp_stream_t stream);
+
 /* ---- losses (losses.py:6-67): out[0] += value; optional gradient = grad_scale * d value / d pred -------- */
 int vp_pixel_loss(const float* pred, int pred_cstride, const float* target, int target_cstride, float* dpred,
                   int dpred_cstride, long long rows, int c, int mode /*bit 0: 0 = L1, 1 = L2; bit 1: dpred += instead of =*/, long long mean_count,

@@ -506,18 +506,6 @@ def savp_cell_step(V, hp, scope, t, inp, first_image, states, ground_truth_t, ta
     nl = len(layers)
     top = layers[-1][-1]
 
-    # cdna kernels (:546-559)
-    kh, kw = hp.kernel_size
-    nk = hp.last_frames * hp.num_transformed_images
-    smallest = layers[n_enc - 1][-1]
-    flat = smallest.reshape(B, -1)
-    dk = V.get(scope + '/cdna_kernels/dense/kernel', (flat.shape[1], kh * kw * nk))
-    db = V.get(scope + '/cdna_kernels/dense/bias', (kh * kw * nk,), 'zeros')
-    kernels = dense(flat, dk, db).reshape(B, kh, kw, nk)
-    kernels = kernels + torch.tensor(identity_kernel((kh, kw)), dtype=kernels.dtype, device=kernels.device)[None, :, :, None]
-    kernels = torch.relu(kernels - RELU_SHIFT) + RELU_SHIFT                  # :558
-    kernels = kernels / kernels.sum(dim=(1, 2), keepdim=True)                # :559
-
     def conv3x3(name, x, oc):
         k = V.get('%s/%s/conv2d/kernel' % (scope, name), (3, 3, x.shape[-1], oc))
         b = V.get('%s/%s/conv2d/bias' % (scope, name), (oc,), 'zeros')
@@ -528,11 +516,35 @@ def savp_cell_step(V, hp, scope, t, inp, first_image, states, ground_truth_t, ta
         be = V.get('%s/%s/InstanceNorm/beta' % (scope, name), (x.shape[-1],), 'zeros')
         return torch.relu(instance_norm(x, g, be))
 
+    kh, kw = hp.kernel_size
+    nk = hp.last_frames * hp.num_transformed_images
+    kernels = flows = None
+    if hp.transformation == 'flow':
+        # flow heads (:522-530): flows [B,H,W,2*nk] reshaped to [B,H,W,2,nk] -> flow k = channels (k, nk + k)
+        h_flow = norm_relu('h%d_flow' % nl, conv3x3('h%d_flow' % nl, top, hp.ngf))
+        flows = conv3x3('flows', h_flow, 2 * nk).reshape(B, H, W, 2, nk)
+    elif hp.transformation == 'cdna':
+        # cdna kernels (:546-559)
+        smallest = layers[n_enc - 1][-1]
+        flat = smallest.reshape(B, -1)
+        dk = V.get(scope + '/cdna_kernels/dense/kernel', (flat.shape[1], kh * kw * nk))
+        db = V.get(scope + '/cdna_kernels/dense/bias', (kh * kw * nk,), 'zeros')
+        kernels = dense(flat, dk, db).reshape(B, kh, kw, nk)
+        kernels = kernels + torch.tensor(identity_kernel((kh, kw)), dtype=kernels.dtype, device=kernels.device)[None, :, :, None]
+        kernels = torch.relu(kernels - RELU_SHIFT) + RELU_SHIFT                  # :558
+        kernels = kernels / kernels.sum(dim=(1, 2), keepdim=True)                # :559
+    else:
+        raise ValueError('Invalid transformation %s' % hp.transformation)    # :545
+
     # scratch image (:561-572)
     h_scratch = norm_relu('h%d_scratch' % nl, conv3x3('h%d_scratch' % nl, top, hp.ngf))
     scratch = torch.sigmoid(conv3x3('scratch_image', h_scratch, C))
     # transformed images (:574-596): 4 CDNA, prev image, first image, scratch
-    transformed = apply_cdna_kernels(image, kernels) + [image, first_image, scratch]
+    if flows is not None:
+        warped = [image_warp(image, flows[..., k]) for k in range(nk)]       # apply_flows (:955-965)
+    else:
+        warped = apply_cdna_kernels(image, kernels)
+    transformed = warped + [image, first_image, scratch]
     # masks (:623-635)
     h_masks = norm_relu('h%d_masks' % nl, conv3x3('h%d_masks' % nl, top, hp.ngf))
     h_masks = torch.cat([h_masks] + transformed, dim=-1)                     # :632 dependent_mask

@@ -353,3 +353,32 @@ def test_image_warp_fwd_bwd(L):
     L.image_warp_bwd(im, 4, flow, dout, 4, dim, 4, dfl, N, H, W, C)
     close(dim[..., :C], g_im, 2e-5, 'image_warp dim')
     close(dfl, g_fl, 2e-5, 'image_warp dflow')
+
+
+def test_flow_apply_fwd_bwd(L):
+    # transformation='flow': NK bilinear warps of the previous image + the two background slots, against oracle.image_warp + autograd
+    N, H, W, NK = 2, 16, 20, 4
+    im = torch.zeros(N, H, W, 4, device='cuda')
+    im[..., :3] = rnd(N, H, W, 3)
+    first = torch.zeros(N, H, W, 4, device='cuda')
+    first[..., :3] = rnd(N, H, W, 3, seed=1)
+    flows = rnd(N, H, W, 2 * NK, seed=2, scale=2.5)
+    ls = 4 * (NK + 3) + 8
+    layers = torch.zeros(N, H, W, ls, device='cuda')
+    L.flow_apply(im, first, flows, 2 * NK, layers.data_ptr() + 4 * 8, ls, N, H, W, NK)
+    imd = im[..., :3].double().requires_grad_(True)
+    fd = flows.double().requires_grad_(True)
+    outs = [O.image_warp(imd, torch.stack([fd[..., k], fd[..., NK + k]], dim=-1)) for k in range(NK)]
+    for k in range(NK):
+        close(layers[..., 8 + 4 * k:8 + 4 * k + 3], outs[k], 1e-5, 'flow warp %d' % k)
+    close(layers[..., 8 + 4 * NK:8 + 4 * NK + 3], im[..., :3], 0, 'prev image slot')
+    close(layers[..., 8 + 4 * NK + 4:8 + 4 * NK + 7], first[..., :3], 0, 'first image slot')
+    dA, dB = rnd(N, H, W, ls, seed=3), rnd(N, H, W, 4 * (NK + 3), seed=4)
+    dimg = torch.zeros(N, H, W, 4, device='cuda')
+    dfl = torch.zeros(N, H, W, 2 * NK, device='cuda')
+    L.flow_apply_bwd(im, flows, 2 * NK, dA.data_ptr() + 4 * 8, ls, dB.data_ptr(), 4 * (NK + 3), dimg, dfl, N, H, W, NK)
+    loss = sum(((dA[..., 8 + 4 * k:8 + 4 * k + 3] + dB[..., 4 * k:4 * k + 3]).double() * outs[k]).sum() for k in range(NK))
+    loss = loss + ((dA[..., 8 + 4 * NK:8 + 4 * NK + 3] + dB[..., 4 * NK:4 * NK + 3]).double() * imd).sum()
+    gi, gf = torch.autograd.grad(loss, (imd, fd))
+    close(dimg[..., :3], gi, 2e-5, 'flow dimage')
+    close(dfl, gf, 2e-5, 'dflows')

@@ -639,3 +639,98 @@ extern "C" int vp_image_warp_bwd(const float* im, int im_cstride, const float* f
                                                                                           dim_cstride, dflow, n, h, w, c);
   return vp::check_launch("image_warp_bwd_kernel");
 }
+
+// ------------------------------------------------------------------------------------------------
+// transformation = 'flow' (savp_model.py:522-530, 577-578, 955-965): the transformed images are backward bilinear warps
+// of the previous image by NK predicted flow fields.  `flows` is the 3x3 flows-conv output [N,H,W,2*NK] reshaped by the
+// reference to [.., 2, NK]: channel k is the x-flow of transform k, channel NK + k its y-flow.  Writes the NK warped
+// images + the previous image + the first image as consecutive float4 slots of the masks-conv concat buffer (same slot
+// layout as cdna_apply_kernel).  flow_ops.image_warp semantics: floor, four neighbours clipped to the image.
+// ------------------------------------------------------------------------------------------------
+namespace vp {
+__global__ void __launch_bounds__(256) flow_apply_kernel(const float4* __restrict__ image, const float4* __restrict__ first,
+                                                         const float* __restrict__ flows, int fs, float* __restrict__ layers, int ls,
+                                                         int N, int H, int W, int NK) {
+  const long long p = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (p >= static_cast<long long>(N) * H * W) return;
+  const int x = static_cast<int>(p % W), y = static_cast<int>((p / W) % H);
+  const long long base = p - (static_cast<long long>(y) * W + x);
+  float* lp = layers + p * ls;
+  for (int k = 0; k < NK; ++k) {
+    const float fx = flows[p * fs + k], fy = flows[p * fs + NK + k];
+    const float flx = floorf(fx), fly = floorf(fy);
+    const float xw = fx - flx, yw = fy - fly;
+    const int x0 = min(max(x + static_cast<int>(flx), 0), W - 1), x1 = min(max(x + static_cast<int>(flx) + 1, 0), W - 1);
+    const int y0 = min(max(y + static_cast<int>(fly), 0), H - 1), y1 = min(max(y + static_cast<int>(fly) + 1, 0), H - 1);
+    const float4 Ia = image[base + static_cast<long long>(y0) * W + x0], Ib = image[base + static_cast<long long>(y1) * W + x0];
+    const float4 Ic = image[base + static_cast<long long>(y0) * W + x1], Id = image[base + static_cast<long long>(y1) * W + x1];
+    const float wa = (1.f - xw) * (1.f - yw), wb = (1.f - xw) * yw, wc = xw * (1.f - yw), wd = xw * yw;
+    *reinterpret_cast<float4*>(lp + 4 * k) = make_float4(wa * Ia.x + wb * Ib.x + wc * Ic.x + wd * Id.x, wa * Ia.y + wb * Ib.y + wc * Ic.y + wd * Id.y,
+                                                          wa * Ia.z + wb * Ib.z + wc * Ic.z + wd * Id.z, wa * Ia.w + wb * Ib.w + wc * Ic.w + wd * Id.w);
+  }
+  *reinterpret_cast<float4*>(lp + 4 * NK) = image[p];
+  *reinterpret_cast<float4*>(lp + 4 * NK + 4) = first[p];
+}
+
+// gradients of flow_apply: dT_k = dA[slot k] + dB[slot k] (through the masks conv and through the compositing);
+// dimage += scatter of the bilinear weights (+ the previous-image slot NK); dflows (overwritten): only the fractional
+// weights carry a gradient (floor has none, flow_ops.py:27-34).
+__global__ void __launch_bounds__(256) flow_apply_bwd_kernel(const float4* __restrict__ image, const float* __restrict__ flows, int fs,
+                                                             const float* __restrict__ dA, int das, const float* __restrict__ dB,
+                                                             int dbs, float* __restrict__ dimage, float* __restrict__ dflows, int N,
+                                                             int H, int W, int NK) {
+  const long long p = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (p >= static_cast<long long>(N) * H * W) return;
+  const int x = static_cast<int>(p % W), y = static_cast<int>((p / W) % H);
+  const long long base = p - (static_cast<long long>(y) * W + x);
+  {
+    const float4 a = *reinterpret_cast<const float4*>(dA + p * das + 4 * NK), b = *reinterpret_cast<const float4*>(dB + p * dbs + 4 * NK);
+    atomicAdd(dimage + p * 4 + 0, a.x + b.x); atomicAdd(dimage + p * 4 + 1, a.y + b.y); atomicAdd(dimage + p * 4 + 2, a.z + b.z);
+  }
+  for (int k = 0; k < NK; ++k) {
+    const float4 a = *reinterpret_cast<const float4*>(dA + p * das + 4 * k), b = *reinterpret_cast<const float4*>(dB + p * dbs + 4 * k);
+    const float d[3] = {a.x + b.x, a.y + b.y, a.z + b.z};
+    const float fx = flows[p * fs + k], fy = flows[p * fs + NK + k];
+    const float flx = floorf(fx), fly = floorf(fy);
+    const float xw = fx - flx, yw = fy - fly;
+    const int x0 = min(max(x + static_cast<int>(flx), 0), W - 1), x1 = min(max(x + static_cast<int>(flx) + 1, 0), W - 1);
+    const int y0 = min(max(y + static_cast<int>(fly), 0), H - 1), y1 = min(max(y + static_cast<int>(fly) + 1, 0), H - 1);
+    const long long ia = base + static_cast<long long>(y0) * W + x0, ib = base + static_cast<long long>(y1) * W + x0;
+    const long long ic = base + static_cast<long long>(y0) * W + x1, id = base + static_cast<long long>(y1) * W + x1;
+    const float4 A = image[ia], B = image[ib], Cc = image[ic], D = image[id];
+    const float va[3] = {A.x, A.y, A.z}, vb[3] = {B.x, B.y, B.z}, vc[3] = {Cc.x, Cc.y, Cc.z}, vd[3] = {D.x, D.y, D.z};
+    float gx = 0.f, gy = 0.f;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      gx += d[c] * ((1.f - yw) * (vc[c] - va[c]) + yw * (vd[c] - vb[c]));
+      gy += d[c] * ((1.f - xw) * (vb[c] - va[c]) + xw * (vd[c] - vc[c]));
+      atomicAdd(dimage + ia * 4 + c, d[c] * (1.f - xw) * (1.f - yw));
+      atomicAdd(dimage + ib * 4 + c, d[c] * (1.f - xw) * yw);
+      atomicAdd(dimage + ic * 4 + c, d[c] * xw * (1.f - yw));
+      atomicAdd(dimage + id * 4 + c, d[c] * xw * yw);
+    }
+    dflows[p * fs + k] = gx;
+    dflows[p * fs + NK + k] = gy;
+  }
+}
+}  // namespace vp
+
+extern "C" int vp_flow_apply(const float* image, const float* first_image, const float* flows, int flows_cstride, float* layers,
+                             int layers_cstride, int n, int h, int w, int nk, vp_stream_t stream) {
+  if (nk < 1 || nk > 6 || flows_cstride < 2 * nk) return vp::set_error("vp_flow_apply: bad nk / flows_cstride");
+  const long long total = static_cast<long long>(n) * h * w;
+  vp::flow_apply_kernel<<<vp::grid_for(total, 256), 256, 0, vp::as_stream(stream)>>>(
+      reinterpret_cast<const float4*>(image), reinterpret_cast<const float4*>(first_image), flows, flows_cstride, layers, layers_cstride,
+      n, h, w, nk);
+  return vp::check_launch("flow_apply_kernel");
+}
+
+extern "C" int vp_flow_apply_bwd(const float* image, const float* flows, int flows_cstride, const float* d_a, int d_a_cstride,
+                                 const float* d_b, int d_b_cstride, float* dimage, float* dflows, int n, int h, int w, int nk,
+                                 vp_stream_t stream) {
+  if (nk < 1 || nk > 6 || flows_cstride < 2 * nk) return vp::set_error("vp_flow_apply_bwd: bad nk / flows_cstride");
+  const long long total = static_cast<long long>(n) * h * w;
+  vp::flow_apply_bwd_kernel<<<vp::grid_for(total, 256), 256, 0, vp::as_stream(stream)>>>(
+      reinterpret_cast<const float4*>(image), flows, flows_cstride, d_a, d_a_cstride, d_b, d_b_cstride, dimage, dflows, n, h, w, nk);
+  return vp::check_launch("flow_apply_bwd_kernel");
+}

@@ -79,6 +79,44 @@ def geom(k, s=(1, 1, 1), p=(0, 0, 0), transposed=False):
 
 
 _ENGINE_CHOICE = {}     # geometry signature -> 0 (box) / 1 (halo), measured once per process
+_PROFILE = None         # list of (kind, algorithmic flops, start event, end event) while profile_engine(True) is active
+
+
+def profile_engine(on):
+    """Starts / stops recording every tensor-core engine call (CUDA events on the launching stream + algorithmic FLOPs).
+    Stopping returns {'igemm' | 'wgrad': dict(calls, flops, ms)} for the whole-engine roofline of bench.py."""
+    global _PROFILE
+    if on:
+        _PROFILE = []
+        return None
+    rec, _PROFILE = _PROFILE or [], None
+    torch.cuda.synchronize()
+    out = {}
+    for kind, flops, e0, e1 in rec:
+        d = out.setdefault(kind, dict(calls=0, flops=0.0, ms=0.0))
+        d['calls'] += 1
+        d['flops'] += flops
+        d['ms'] += e0.elapsed_time(e1)
+    return out
+
+
+def _conv_flops(x_view, g, out_view):
+    """Algorithmic FLOPs of a convolution call as SURVEY.md 8(d) counts them: 2 * output positions * Cout * Cin * taps executed
+    per output (a transposed convolution executes taps / stride-product taps per output position)."""
+    taps = g.kd * g.kh * g.kw
+    if g.transposed:
+        taps = taps / float(g.sd * g.sh * g.sw)
+    return 2.0 * out_view.n * out_view.d * out_view.h * out_view.w * out_view.c * x_view.c * taps
+
+
+def _profiled(kind, flops, call):
+    if _PROFILE is None:
+        return call()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    call()
+    e1.record()
+    _PROFILE.append((kind, flops, e0, e1))
 
 
 def _conv_key(x_view, g, n_pad, kc, out_view, act, extra):
@@ -122,7 +160,7 @@ def conv_igemm(x_view, g, wpacked, n_pad, kc, out_view, bias=None, act=ACT_NONE,
     # an explicit split_k > 1 adds atomically into a caller-cleared output: repeating the call (timing) would change it
     eng = _pick_engine(_conv_key(x_view, g, n_pad, kc, out_view, act, ('fwd', split_k)), call, not accumulate and split_k <= 1)
     check(lib().vp_conv_set_engine(eng))
-    call()
+    _profiled('igemm', _conv_flops(x_view, g, out_view), call)
     if eng >= 0:
         check(lib().vp_conv_set_engine(-1))
 
@@ -134,7 +172,7 @@ def conv_igemm_actgrad(x_view, g, wpacked, n_pad, kc, out_view, act_output_addr,
                                           int(accumulate), stream_ptr()))
     eng = _pick_engine(_conv_key(x_view, g, n_pad, kc, out_view, act, ('actgrad', bool(addend_addr))), call, not accumulate)
     check(lib().vp_conv_set_engine(eng))
-    call()
+    _profiled('igemm', _conv_flops(x_view, g, out_view), call)
     if eng >= 0:
         check(lib().vp_conv_set_engine(-1))
 
@@ -165,8 +203,12 @@ def conv_flat(x_view, valid_h, valid_w, g, wpacked, n_pad, kc, out_view, bias=No
 
 
 def conv_wgrad(x_view, dy_view, g, dwpacked, n_pad, kc, split_k=1):
-    check(lib().vp_conv_wgrad(C.byref(x_view), C.byref(dy_view), C.byref(g), ptr(dwpacked), n_pad, kc, split_k,
-                              stream_ptr()))
+    if 'wgrad' in _SKIP:
+        return
+    taps = g.kd * g.kh * g.kw / (float(g.sd * g.sh * g.sw) if g.transposed else 1.0)
+    flops = 2.0 * dy_view.n * dy_view.d * dy_view.h * dy_view.w * dy_view.c * x_view.c * taps
+    _profiled('wgrad', flops, lambda: check(lib().vp_conv_wgrad(C.byref(x_view), C.byref(dy_view), C.byref(g), ptr(dwpacked), n_pad, kc,
+                                                               split_k, stream_ptr())))
 
 
 def eff_taps(k, kind):
@@ -199,12 +241,16 @@ def pack_weights(w, k, ci_ref, co, kind, layout, ci_int=None, cmap=None, inv_sca
     taps = eff_taps(k, kind)
     if out is None:
         out = torch.empty(taps * n_pad * kc * 32, device=w.device, dtype=torch.float32)
+    elif 'pack' in _SKIP:
+        return out, n_pad, kc
     check(lib().vp_pack_weights(ptr(w), k[0], k[1], k[2], ci_ref, co, kind, layout, ptr(cmap), ci_int,
                                 ptr(inv_scale), ptr(out), n_pad, kc, stream_ptr()))
     return out, n_pad, kc
 
 
 def unpack_wgrad(dwpacked, k, ci_ref, co, kind, dw, n_pad, kc, ci_int=None, cmap=None):
+    if 'pack' in _SKIP:
+        return
     ci_int = ci_ref if ci_int is None else ci_int
     check(lib().vp_unpack_wgrad(ptr(dwpacked), k[0], k[1], k[2], ci_ref, co, kind, ptr(cmap), ci_int, ptr(dw),
                                 n_pad, kc, stream_ptr()))
@@ -215,13 +261,20 @@ def _f(v):
     return C.c_float(v)
 
 
+_SKIP = set(filter(None, os.environ.get('VP_SKIP', '').split(',')))   # timing ablations only (wrong results): kernel families not launched
+
+
 def inorm_act(x_addr, x_cs, y_addr, y_cs, n, positions, c, gamma, beta, act=ACT_NONE, alpha=0.0, stats=None, eps=1e-6):
+    if 'inorm' in _SKIP:
+        return
     check(lib().vp_inorm_act(C.c_void_p(x_addr), x_cs, C.c_void_p(y_addr), y_cs, n, positions, c, ptr(gamma), ptr(beta), _f(eps), act, _f(alpha),
                              ptr(stats), stream_ptr()))
 
 
 def lstm_gates_fwd(pre, n, positions, filters, c_prev, g1, b1, g2, b2, c_new, h_dsts, stats1=None, stats2=None,
                    forget_bias=1.0, eps=1e-6):
+    if 'gates' in _SKIP:
+        return
     """h_dsts: list of (address:int, cstride:int)."""
     k = len(h_dsts)
     pa = (C.c_void_p * k)(*[C.c_void_p(a) for a, _ in h_dsts])
@@ -236,6 +289,8 @@ def broadcast_channels(vec, vec_stride, dst_addr, dst_cs, n, positions, c):
 
 
 def copy_channels(src_addr, src_cs, dst_addr, dst_cs, rows, c):
+    if 'copy' in _SKIP:
+        return
     check(lib().vp_copy_channels(C.c_void_p(src_addr), src_cs, C.c_void_p(dst_addr), dst_cs, C.c_longlong(rows), c,
                                  stream_ptr()))
 
@@ -249,6 +304,8 @@ def avgpool(x, x_cs, y, n, positions, c):
 
 
 def dense_fwd(x, x_stride, w, bias, y, y_stride, b, k, j, k_splits=1, inv_scale=None):
+    if 'dense' in _SKIP:
+        return
     check(lib().vp_dense_fwd(ptr(x), x_stride, ptr(w), ptr(bias), ptr(inv_scale), ptr(y), y_stride, b, k, j, k_splits,
                              stream_ptr()))
 
@@ -266,11 +323,24 @@ def cdna_kernel_norm(raw, out, b, kh, kw, nk):
 
 
 def cdna_apply(image, first, kernels, layers_addr, layers_cs, n, h, w, kh, kw, nk):
+    if 'cdna' in _SKIP:
+        return
     check(lib().vp_cdna_apply(ptr(image), ptr(first), ptr(kernels), C.c_void_p(layers_addr), layers_cs, n, h, w, kh, kw, nk,
                               stream_ptr()))
 
 
+def flow_apply(image, first, flows, flows_cs, layers_addr, layers_cs, n, h, w, nk):
+    check(lib().vp_flow_apply(ptr(image), ptr(first), ptr(flows), flows_cs, C.c_void_p(layers_addr), layers_cs, n, h, w, nk, stream_ptr()))
+
+
+def flow_apply_bwd(image, flows, flows_cs, da_addr, da_cs, db_addr, db_cs, dimage, dflows, n, h, w, nk):
+    check(lib().vp_flow_apply_bwd(ptr(image), ptr(flows), flows_cs, C.c_void_p(da_addr), da_cs, C.c_void_p(db_addr), db_cs, ptr(dimage),
+                                  ptr(dflows), n, h, w, nk, stream_ptr()))
+
+
 def composite(logits, logits_cs, layers_addr, layers_cs, masks, masks_cs, gen, positions, num_layers):
+    if 'cdna' in _SKIP:
+        return
     check(lib().vp_composite(ptr(logits), logits_cs, C.c_void_p(layers_addr), layers_cs, ptr(masks), masks_cs, ptr(gen),
                              C.c_longlong(positions), num_layers, stream_ptr()))
 
@@ -287,6 +357,8 @@ def addr(a):
 
 
 def inorm_act_bwd(x_addr, x_cs, dy_srcs, dx_addr, dx_cs, n, positions, c, gamma, beta, stats, act, alpha, dgamma, dbeta):
+    if 'inorm' in _SKIP:
+        return
     pa, sa, k = _srcs(dy_srcs)
     check(lib().vp_inorm_act_bwd(addr(x_addr), x_cs, pa, sa, k, addr(dx_addr), dx_cs, n, positions, c, ptr(gamma), ptr(beta),
                                  ptr(stats), act, _f(alpha), ptr(dgamma), ptr(dbeta), stream_ptr()))
@@ -294,6 +366,8 @@ def inorm_act_bwd(x_addr, x_cs, dy_srcs, dx_addr, dx_cs, n, positions, c, gamma,
 
 def lstm_gates_bwd(pre, n, positions, filters, c_prev, g1, b1, g2, b2, stats1, stats2, dh_srcs, dc_next, dpre, dc_prev,
                    dg1, db1, dg2, db2, forget_bias=1.0):
+    if 'gates' in _SKIP:
+        return
     pa, sa, k = _srcs(dh_srcs)
     check(lib().vp_lstm_gates_bwd(ptr(pre), n, positions, filters, ptr(c_prev), ptr(g1), ptr(b1), ptr(g2), ptr(b2), ptr(stats1),
                                   ptr(stats2), _f(forget_bias), pa, sa, k, ptr(dc_next), ptr(dpre), ptr(dc_prev), ptr(dg1),
@@ -301,11 +375,15 @@ def lstm_gates_bwd(pre, n, positions, filters, c_prev, g1, b1, g2, b2, stats1, s
 
 
 def composite_bwd(dgen, masks, masks_cs, layers_addr, layers_cs, dlogits, dlogits_cs, dlayers, dlayers_cs, positions, num_layers):
+    if 'cdna' in _SKIP:
+        return
     check(lib().vp_composite_bwd(ptr(dgen), ptr(masks), masks_cs, addr(layers_addr), layers_cs, ptr(dlogits), dlogits_cs,
                                  ptr(dlayers), dlayers_cs, C.c_longlong(positions), num_layers, stream_ptr()))
 
 
 def cdna_apply_bwd(image, kernels, da_addr, da_cs, db_addr, db_cs, dimage, dkernels, n, h, w, kh, kw, nk):
+    if 'cdna' in _SKIP:
+        return
     check(lib().vp_cdna_apply_bwd(ptr(image), ptr(kernels), addr(da_addr), da_cs, addr(db_addr), db_cs, ptr(dimage), ptr(dkernels),
                                   n, h, w, kh, kw, nk, stream_ptr()))
 
@@ -316,6 +394,8 @@ def cdna_kernel_norm_bwd(raw, out, dout, draw, b, kh, kw, nk):
 
 def dense_bwd(x, x_stride, w, dy, dy_stride, b, k, j, dx=None, dx_stride=0, dx_accumulate=False, dw=None, dbias=None,
               inv_scale=None):
+    if 'dense' in _SKIP:
+        return
     check(lib().vp_dense_bwd(ptr(x), x_stride, ptr(w), ptr(inv_scale), ptr(dy), dy_stride, ptr(dx), dx_stride,
                              int(dx_accumulate), ptr(dw), ptr(dbias), b, k, j, stream_ptr()))
 
@@ -326,6 +406,8 @@ def lstm_cell_bwd(gates, c_prev, c_new, dh, dc_next, dgates, dc_prev, b, units, 
 
 
 def colsum(x_addr, x_cs, out, n, positions, c, scale=1.0, out_stride=None):
+    if 'colsum' in _SKIP:
+        return
     check(lib().vp_colsum(addr(x_addr), x_cs, ptr(out), c if out_stride is None else out_stride, n, C.c_longlong(positions), c,
                           _f(scale), stream_ptr()))
 
@@ -369,10 +451,14 @@ def kl_loss(mu, lss, rows, nz, out):
 
 
 def cosine_distance(a, b, da, rows, c, grad_scale, out):
+    if 'cosd' in _SKIP:
+        return
     check(lib().vp_cosine_distance(ptr(a), ptr(b), ptr(da), C.c_longlong(rows), c, _f(grad_scale), ptr(out), stream_ptr()))
 
 
 def adam(p, g, m, v, n, lr_t_dev, beta1, beta2, grad_scale=1.0, eps=1e-8):
+    if 'adam' in _SKIP:
+        return
     check(lib().vp_adam(ptr(p), ptr(g), ptr(m), ptr(v), C.c_longlong(n), ptr(lr_t_dev), _f(beta1), _f(beta2), _f(eps),
                         _f(grad_scale), stream_ptr()))
 
@@ -384,10 +470,14 @@ def launch_count():
 
 
 def spectral_norm_fwd(w, u, rows, cols, v, s, u_new, scal):
+    if 'sn' in _SKIP:
+        return
     check(lib().vp_spectral_norm_fwd(ptr(w), ptr(u), rows, cols, ptr(v), ptr(s), ptr(u_new), ptr(scal), stream_ptr()))
 
 
 def spectral_norm_bwd(w, u, g_wbar, rows, cols, v, s, scal, gs, gt, dw):
+    if 'sn' in _SKIP:
+        return
     check(lib().vp_spectral_norm_bwd(ptr(w), ptr(u), ptr(g_wbar), rows, cols, ptr(v), ptr(s), ptr(scal), ptr(gs), ptr(gt), ptr(dw),
                                      stream_ptr()))
 
@@ -403,10 +493,14 @@ def scatter_clip(dclip, t_start, dvideo, clips, clip_len, pixels, video_batch, b
 
 
 def conv3d_c4_fwd(x, w, inv_scale, bias, out, n, d, h, wd, ci, alpha):
+    if 'c4fwd' in _SKIP:
+        return
     check(lib().vp_conv3d_c4_fwd(ptr(x), ptr(w), ptr(inv_scale), ptr(bias), ptr(out), n, d, h, wd, ci, _f(alpha), stream_ptr()))
 
 
 def conv3d_c4_wgrad(x, dy, gw, n, d, h, wd, ci):
+    if 'c4wgrad' in _SKIP:
+        return
     check(lib().vp_conv3d_c4_wgrad(ptr(x), ptr(dy), ptr(gw), n, d, h, wd, ci, stream_ptr()))
 
 

@@ -219,7 +219,7 @@ class SAVPVideoPredictionModel(TrainMixin, VideoPredictionModel):
                           ('repeat', 1)):
             if getattr(hp, key) != want:
                 unsupported.append('%s=%r' % (key, getattr(hp, key)))
-        if hp.transformation not in ('cdna',):
+        if hp.transformation not in ('cdna', 'flow'):
             unsupported.append('transformation=%r' % (hp.transformation,))
         if tuple(hp.dilation_rate) != (1, 1):
             unsupported.append('dilation_rate=%r' % (hp.dilation_rate,))
@@ -317,9 +317,16 @@ class SAVPVideoPredictionModel(TrainMixin, VideoPredictionModel):
         nk = hp.last_frames * hp.num_transformed_images
         sh = H // (2 ** n_enc)
         sw = W // (2 ** n_enc)
-        specs[sc + '/cdna_kernels/dense/kernel'] = ((sh * sw * outs[n_enc - 1], kh * kw * nk), 'kernel')
-        specs[sc + '/cdna_kernels/dense/bias'] = ((kh * kw * nk,), 'zeros')
         top = outs[-1]
+        if hp.transformation == 'flow':         # savp_model.py:522-530: flow heads instead of the CDNA kernel dense layer
+            specs['%s/h%d_flow/conv2d/kernel' % (sc, nl)] = ((3, 3, top, hp.ngf), 'kernel')
+            specs['%s/h%d_flow/conv2d/bias' % (sc, nl)] = ((hp.ngf,), 'zeros')
+            norm('%s/h%d_flow/InstanceNorm' % (sc, nl), hp.ngf)
+            specs[sc + '/flows/conv2d/kernel'] = ((3, 3, hp.ngf, 2 * nk), 'kernel')
+            specs[sc + '/flows/conv2d/bias'] = ((2 * nk,), 'zeros')
+        else:
+            specs[sc + '/cdna_kernels/dense/kernel'] = ((sh * sw * outs[n_enc - 1], kh * kw * nk), 'kernel')
+            specs[sc + '/cdna_kernels/dense/bias'] = ((kh * kw * nk,), 'zeros')
         for nm in ('h%d_scratch' % nl, 'h%d_masks' % nl):
             specs['%s/%s/conv2d/kernel' % (sc, nm)] = ((3, 3, top, hp.ngf), 'kernel')
             specs['%s/%s/conv2d/bias' % (sc, nm)] = ((hp.ngf,), 'zeros')
@@ -369,8 +376,8 @@ class SAVPVideoPredictionModel(TrainMixin, VideoPredictionModel):
         if (H % total_stride) or (W % total_stride):
             raise ValueError('The image has dimension (%d, %d), but it should be divisible by the total stride, '
                              'which is %d.' % (H, W, total_stride))
-        if C > 4:
-            raise NotImplementedError('at most 4 colour channels')
+        if C > 3:
+            raise NotImplementedError('at most 3 colour channels (pixels are stored as float4 with one padding lane)')
         self.param_specs = self._generator_param_specs()
         if self.mode == 'train':
             self.param_specs.update(self._discriminator_param_specs())
@@ -619,6 +626,17 @@ class SAVPVideoPredictionModel(TrainMixin, VideoPredictionModel):
         self.conv_masks = ConvLayer(self, sc + '/masks/conv2d/kernel', sc + '/masks/conv2d/bias', (1, 3, 3), L.WKIND_PLAIN,
                                     (1, 1, 1), (0, 1, 1), False, self.mk_spec, self.nlayers)
         self.convs += [self.conv_scratch, self.conv_hmasks, self.conv_simg, self.conv_masks]
+        self.flow = hp.transformation == 'flow'
+        if self.flow:
+            self.conv_hflow = ConvLayer(self, '%s/h%d_flow/conv2d/kernel' % (sc, nl), '%s/h%d_flow/conv2d/bias' % (sc, nl),
+                                        (1, 3, 3), L.WKIND_PLAIN, (1, 1, 1), (0, 1, 1), False, top_spec, hp.ngf)
+            self.conv_flows = ConvLayer(self, sc + '/flows/conv2d/kernel', sc + '/flows/conv2d/bias', (1, 3, 3), L.WKIND_PLAIN,
+                                        (1, 1, 1), (0, 1, 1), False, hs_spec, 2 * nk)
+            self.convs += [self.conv_hflow, self.conv_flows]
+            Bf['fpre'] = self._z(S, NB, H, W, hp.ngf)
+            Bf['fst'] = self._z(S, NB, hp.ngf, 2)
+            Bf['hf'] = self._z(S, NB, H, W, hp.ngf)
+            Bf['flows'] = self._z(S, NB, H, W, _ceil4(2 * nk))
         Bf['spre'] = self._z(S, NB, H, W, hp.ngf)
         Bf['mpre'] = self._z(S, NB, H, W, hp.ngf)
         Bf['sst'] = self._z(S, NB, hp.ngf, 2)
@@ -885,7 +903,7 @@ class SAVPVideoPredictionModel(TrainMixin, VideoPredictionModel):
             i = n_enc - 1 - li
             sp = self.gl[n_enc + i]['in_spec']
             dests.append((Bf['in%d' % (n_enc + i)][t].data_ptr() + 4 * sp.off('skip'), sp.cstride))
-        if li == n_enc - 1:
+        if li == n_enc - 1 and not self.flow:     # flattened input of the CDNA kernel dense layer
             dests.append((Bf['small'][t].data_ptr(), d['oc']))
         return dests
 
@@ -927,18 +945,26 @@ class SAVPVideoPredictionModel(TrainMixin, VideoPredictionModel):
                             L.ACT_RELU, 0.0, Bf['nst%d' % li][t])
                 for addr, cs in dests:
                     L.copy_channels(out.data_ptr(), oc, addr, cs, NB * hh * ww, oc)
-        # cdna kernels (savp_model.py:546-559)
         nk, kh, kw = self.nk, self.kh, self.kw
-        small = Bf['small'][t]
-        K = small.shape[1]
-        Bf['kraw'][t].zero_()
-        L.dense_fwd(small, K, P[sc + '/cdna_kernels/dense/kernel'], P[sc + '/cdna_kernels/dense/bias'], Bf['kraw'][t],
-                    kh * kw * nk, NB, K, kh * kw * nk, k_splits=32)
-        L.cdna_kernel_norm(Bf['kraw'][t], Bf['kern'][t], NB, kh, kw, nk)
-        # heads
         top = Bf['out%d' % (self.nl - 1)][t] if not self.gl[-1]['use'] else None
         ngf = hp.ngf
         nl = self.nl
+        if self.flow:
+            # flow heads (savp_model.py:522-530): h_flow = relu(IN(conv3x3(top))), flows = conv3x3(h_flow) [.., 2, nk]
+            self.conv_hflow.fwd(top, Bf['fpre'][t])
+            nm = '%s/h%d_flow/InstanceNorm' % (sc, nl)
+            L.inorm_act(Bf['fpre'][t].data_ptr(), ngf, Bf['hf'][t].data_ptr(), ngf, NB, HW, ngf, P[nm + '/gamma'], P[nm + '/beta'],
+                        L.ACT_RELU, 0.0, Bf['fst'][t])
+            self.conv_flows.fwd(Bf['hf'][t], Bf['flows'][t], out_c=2 * nk)
+        else:
+            # cdna kernels (savp_model.py:546-559)
+            small = Bf['small'][t]
+            K = small.shape[1]
+            Bf['kraw'][t].zero_()
+            L.dense_fwd(small, K, P[sc + '/cdna_kernels/dense/kernel'], P[sc + '/cdna_kernels/dense/bias'], Bf['kraw'][t],
+                        kh * kw * nk, NB, K, kh * kw * nk, k_splits=32)
+            L.cdna_kernel_norm(Bf['kraw'][t], Bf['kern'][t], NB, kh, kw, nk)
+        # heads
         self.conv_scratch.fwd(top, Bf['spre'][t])
         self.conv_hmasks.fwd(top, Bf['mpre'][t])
         nm = '%s/h%d_scratch/InstanceNorm' % (sc, nl)
@@ -951,9 +977,13 @@ class SAVPVideoPredictionModel(TrainMixin, VideoPredictionModel):
                     P[nm + '/gamma'], P[nm + '/beta'], L.ACT_RELU, 0.0, Bf['mst'][t])
         # scratch image -> last layer slot (savp_model.py:570-572, 595-596)
         self.conv_simg.fwd(Bf['hs'][t], mk, out_off=msp.off('l%d' % (self.nlayers - 1)), out_c=C, act=L.ACT_SIGMOID)
-        # transformed images: 4 CDNA + prev image + first image (savp_model.py:574-584)
-        L.cdna_apply(Bf['img'][t], Bf['x'][0], Bf['kern'][t], mk.data_ptr() + 4 * msp.off('l0'), msp.cstride, NB, H, W,
-                     kh, kw, nk)
+        # transformed images: 4 CDNA (or flow-warped) + prev image + first image (savp_model.py:574-584)
+        if self.flow:
+            L.flow_apply(Bf['img'][t], Bf['x'][0], Bf['flows'][t], Bf['flows'].shape[-1], mk.data_ptr() + 4 * msp.off('l0'),
+                         msp.cstride, NB, H, W, nk)
+        else:
+            L.cdna_apply(Bf['img'][t], Bf['x'][0], Bf['kern'][t], mk.data_ptr() + 4 * msp.off('l0'), msp.cstride, NB, H, W,
+                         kh, kw, nk)
         # masks + compositing (savp_model.py:623-646)
         self.conv_masks.fwd(mk, Bf['mlog'][t], out_c=self.nlayers)
         L.composite(Bf['mlog'][t], 8, mk.data_ptr() + 4 * msp.off('l0'), msp.cstride, Bf['masks'][t], 8, Bf['gen'][t],

@@ -245,6 +245,10 @@ class TrainMixin(object):
         G['dkern'] = torch.zeros_like(Bf['kern'])
         G['dkraw'] = torch.zeros_like(Bf['kraw'])
         G['dsmall'] = torch.zeros_like(Bf['small'])
+        if self.flow:
+            G['dflows'] = torch.zeros_like(Bf['flows'])
+            G['dhf'] = z(S, NB, H, W, ngf)
+            G['dfpre'] = z(S, NB, H, W, ngf)
         if self.Zc:
             G['dzvec'] = torch.zeros_like(Bf['zvec'])
         if hp.nz:
@@ -359,18 +363,28 @@ class TrainMixin(object):
         L.inorm_act_bwd(Bf['spre'][t].data_ptr(), ngf, [(G['dhs'][t].data_ptr(), ngf)], G['dspre'][t].data_ptr(), ngf, NB, HW, ngf,
                         P[nm + '/gamma'], P[nm + '/beta'], Bf['sst'][t], L.ACT_RELU, 0.0, Gp[nm + '/gamma'], Gp[nm + '/beta'])
         self.conv_scratch.dgrad(G['dspre'][t], G['dtop'][t], accumulate=True)
-        # CDNA
         nk, kh, kw = self.nk, self.kh, self.kw
         G['dimg'][t].zero_()
-        G['dkern'][t].zero_()
-        L.cdna_apply_bwd(Bf['img'][t], Bf['kern'][t], dmk.data_ptr() + 4 * msp.off('l0'), msp.cstride, G['dlay'][t].data_ptr(),
-                         4 * nlay, G['dimg'][t], G['dkern'][t], NB, H, W, kh, kw, nk)
-        L.cdna_kernel_norm_bwd(Bf['kraw'][t], Bf['kern'][t], G['dkern'][t], G['dkraw'][t], NB, kh, kw, nk)
-        K = Bf['small'].shape[-1]
-        dn = sc + '/cdna_kernels/dense'
-        # dx only; dW / dbias of this layer are one GEMM over all time steps in _gen_backward_params
-        L.dense_bwd(Bf['small'][t], K, P[dn + '/kernel'], G['dkraw'][t], kh * kw * nk, NB, K, kh * kw * nk, dx=G['dsmall'][t],
-                    dx_stride=K)
+        if self.flow:
+            # flow warps (flow_ops.py:4-79) -> flows conv -> h_flow instance norm -> h_flow conv (savp_model.py:522-530)
+            L.flow_apply_bwd(Bf['img'][t], Bf['flows'][t], Bf['flows'].shape[-1], dmk.data_ptr() + 4 * msp.off('l0'), msp.cstride,
+                             G['dlay'][t].data_ptr(), 4 * nlay, G['dimg'][t], G['dflows'][t], NB, H, W, nk)
+            self.conv_flows.dgrad(G['dflows'][t], G['dhf'][t], dy_c=2 * nk)
+            nm = '%s/h%d_flow/InstanceNorm' % (sc, nl)
+            L.inorm_act_bwd(Bf['fpre'][t].data_ptr(), ngf, [(G['dhf'][t].data_ptr(), ngf)], G['dfpre'][t].data_ptr(), ngf, NB, HW, ngf,
+                            P[nm + '/gamma'], P[nm + '/beta'], Bf['fst'][t], L.ACT_RELU, 0.0, Gp[nm + '/gamma'], Gp[nm + '/beta'])
+            self.conv_hflow.dgrad(G['dfpre'][t], G['dtop'][t], accumulate=True)
+        else:
+            # CDNA
+            G['dkern'][t].zero_()
+            L.cdna_apply_bwd(Bf['img'][t], Bf['kern'][t], dmk.data_ptr() + 4 * msp.off('l0'), msp.cstride, G['dlay'][t].data_ptr(),
+                             4 * nlay, G['dimg'][t], G['dkern'][t], NB, H, W, kh, kw, nk)
+            L.cdna_kernel_norm_bwd(Bf['kraw'][t], Bf['kern'][t], G['dkern'][t], G['dkraw'][t], NB, kh, kw, nk)
+            K = Bf['small'].shape[-1]
+            dn = sc + '/cdna_kernels/dense'
+            # dx only; dW / dbias of this layer are one GEMM over all time steps in _gen_backward_params
+            L.dense_bwd(Bf['small'][t], K, P[dn + '/kernel'], G['dkraw'][t], kh * kw * nk, NB, K, kh * kw * nk, dx=G['dsmall'][t],
+                        dx_stride=K)
         # encoder/decoder stack in reverse
         n_enc = len(self.enc_specs)
         for li in range(nl - 1, -1, -1):
@@ -386,7 +400,7 @@ class TrainMixin(object):
                 i = n_enc - 1 - li
                 sp = self.gl[n_enc + i]['in_spec']
                 srcs.append((G['din%d' % (n_enc + i)][t].data_ptr() + 4 * sp.off('skip'), sp.cstride))
-            if li == n_enc - 1:
+            if li == n_enc - 1 and not self.flow:
                 srcs.append((G['dsmall'][t].data_ptr(), oc))
             nm = '%s/h%d/InstanceNorm' % (sc, li)
             if d['use']:
@@ -435,11 +449,17 @@ class TrainMixin(object):
         L.colsum(G['dsimg'].data_ptr(), 4, Gp[self.conv_simg.bname], 1, rows_top, C)
         self.conv_masks.wgrad(Bf['mk'], G['dmlog'], dy_c=self.nlayers)
         L.colsum(G['dmlog'].data_ptr(), 8, Gp[self.conv_masks.bname], 1, rows_top, self.nlayers)
-        # CDNA kernel dense layer: dW = sum over all time steps of small_t^T dkraw_t, one launch
-        Kd = Bf['small'].shape[-1]
-        dn = 'generator/rnn/savp_cell/cdna_kernels/dense'
-        nkk = self.kh * self.kw * self.nk
-        L.dense_bwd(Bf['small'], Kd, P[dn + '/kernel'], G['dkraw'], nkk, S * NB, Kd, nkk, dw=Gp[dn + '/kernel'], dbias=Gp[dn + '/bias'])
+        if self.flow:
+            self.conv_hflow.wgrad(top, G['dfpre'])
+            L.colsum(G['dfpre'].data_ptr(), ngf, Gp[self.conv_hflow.bname], 1, rows_top, ngf)
+            self.conv_flows.wgrad(Bf['hf'], G['dflows'], dy_c=2 * self.nk)
+            L.colsum(G['dflows'].data_ptr(), G['dflows'].shape[-1], Gp[self.conv_flows.bname], 1, rows_top, 2 * self.nk)
+        else:
+            # CDNA kernel dense layer: dW = sum over all time steps of small_t^T dkraw_t, one launch
+            Kd = Bf['small'].shape[-1]
+            dn = 'generator/rnn/savp_cell/cdna_kernels/dense'
+            nkk = self.kh * self.kw * self.nk
+            L.dense_bwd(Bf['small'], Kd, P[dn + '/kernel'], G['dkraw'], nkk, S * NB, Kd, nkk, dw=Gp[dn + '/kernel'], dbias=Gp[dn + '/bias'])
         if not self.Zc:
             return
         # tile_concat adjoint: sum the z-slot gradients of every concat buffer over space
