@@ -708,6 +708,37 @@ def video_sn_discriminator(V, scope, clips, ndf, u_out=None):
     return feats, logits
 
 
+IMAGE_D_LAYERS = [  # networks.py:45-63
+    ('sn_conv0_0', 1, 3, (1, 1)), ('sn_conv0_1', 2, 4, (2, 2)), ('sn_conv1_0', 2, 3, (1, 1)), ('sn_conv1_1', 4, 4, (2, 2)),
+    ('sn_conv2_0', 4, 3, (1, 1)), ('sn_conv2_1', 8, 4, (2, 2)), ('sn_conv3_0', 8, 3, (1, 1)),
+]
+
+
+def image_sn_discriminator(V, scope, images, ndf, u_out=None):
+    """networks.image_sn_discriminator (networks.py:35-69): images [B,H,W,C] -> 7 feature maps + logits [B,1]."""
+    x = images
+    feats = []
+    for name, mult, k, strides in IMAGE_D_LAYERS:
+        oc = ndf * mult
+        W = V.get('%s/%s/conv2d/kernel' % (scope, name), (k, k, x.shape[-1], oc))
+        u = V.get('%s/%s/conv2d/u' % (scope, name), (1, oc), 'u', trainable=False)
+        b = V.get('%s/%s/conv2d/bias' % (scope, name), (oc,), 'zeros')
+        Wb, u1 = spectral_normed_weight(W, u)
+        if u_out is not None:
+            u_out['%s/%s/conv2d/u' % (scope, name)] = u1.detach()
+        xp = F.pad(x, (0, 0, 1, 1, 1, 1))                                    # networks.py:38-43
+        x = lrelu(conv2d_tf(xp, Wb, strides=strides, padding='VALID', bias=b, tag='%s/%s' % (scope, name)), 0.1)
+        feats.append(x)
+    flat = x.reshape(x.shape[0], -1)
+    W = V.get('%s/sn_fc4/dense/kernel' % scope, (flat.shape[1], 1))
+    u = V.get('%s/sn_fc4/dense/u' % scope, (1, 1), 'u', trainable=False)
+    b = V.get('%s/sn_fc4/dense/bias' % scope, (1,), 'zeros')
+    Wb, u1 = spectral_normed_weight(W, u)
+    if u_out is not None:
+        u_out['%s/sn_fc4/dense/u' % scope] = u1.detach()
+    return feats, dense(flat, Wb, b)
+
+
 def gather_clip(targets, t_start, clip_length):
     """savp_model.py:97-102: per-sample clip of clip_length frames starting at t_start[b]."""
     T, B = targets.shape[:2]
@@ -716,25 +747,35 @@ def gather_clip(targets, t_start, clip_length):
 
 
 def discriminator(V, hp, inputs, gen_outputs, t_starts, u_out=None):
-    """discriminator_fn (savp_model.py:129-166), video_sn discriminators only (image / images
-    discriminators are disabled by every shipped hparams file).  t_starts: dict with int64[B]
-    entries 'real','fake' (+ 'enc_real','enc_fake' if nz>0)."""
+    """discriminator_fn / discriminator_given_video_fn (savp_model.py:88-166): image_sn (one sampled frame per video) and
+    video_sn (a clip) discriminators; the per-frame `images_sn` variant is not restated.  t_starts: dict with int64[B]
+    entries 'real','fake' (+ 'enc_real','enc_fake' if nz>0) = clip offsets, and 'image_real', ... = sampled frame indices."""
     out = OrderedDict()
-    if not (hp.video_sn_gan_weight or hp.video_sn_vae_gan_weight):
-        return out
     real = inputs['images'][1:]
+    has_image = bool(hp.image_sn_gan_weight or hp.image_sn_vae_gan_weight)
+    has_video = bool(hp.video_sn_gan_weight or hp.video_sn_vae_gan_weight)
 
-    def run(scope, video, key, suffix):
-        clip = gather_clip(video, t_starts[key], hp.clip_length)
-        feats, logits = video_sn_discriminator(V, scope, clip, hp.ndf, u_out)
-        out['discrim_video_sn_logits' + suffix] = logits
-        for i, f in enumerate(feats):
-            out['discrim_video_sn_feature%d%s' % (i, suffix)] = f
+    def run(prefix, video, key, suffix):
+        if has_image:
+            B = video.shape[1]
+            frame = video[t_starts['image_' + key], torch.arange(B)]             # savp_model.py:93-94
+            feats, logits = image_sn_discriminator(V, prefix + '/image', frame, hp.ndf, u_out)
+            out['discrim_image_sn_logits' + suffix] = logits
+            for i, f in enumerate(feats):
+                out['discrim_image_sn_feature%d%s' % (i, suffix)] = f
+        if has_video:
+            clip = gather_clip(video, t_starts[key], hp.clip_length)
+            feats, logits = video_sn_discriminator(V, prefix + '/video', clip, hp.ndf, u_out)
+            out['discrim_video_sn_logits' + suffix] = logits
+            for i, f in enumerate(feats):
+                out['discrim_video_sn_feature%d%s' % (i, suffix)] = f
+    if not (has_image or has_video):
+        return out
     if hp.nz:
-        run('discriminator/encoder/video', real, 'enc_real', '_enc_real')
-        run('discriminator/encoder/video', gen_outputs['gen_images_enc'], 'enc_fake', '_enc_fake')
-    run('discriminator/video', real, 'real', '_real')
-    run('discriminator/video', gen_outputs['gen_images'], 'fake', '_fake')
+        run('discriminator/encoder', real, 'enc_real', '_enc_real')
+        run('discriminator/encoder', gen_outputs['gen_images_enc'], 'enc_fake', '_enc_fake')
+    run('discriminator', real, 'real', '_real')
+    run('discriminator', gen_outputs['gen_images'], 'fake', '_fake')
     return out
 
 
@@ -806,20 +847,20 @@ def generator_losses(hp, inputs, outputs, step):
         L['gen_l1_loss'] = (l1_loss(gen, target), hp.l1_weight)
     if hp.l2_weight:
         L['gen_l2_loss'] = (l2_loss(gen, target), hp.l2_weight)
-    if hp.video_sn_gan_weight:
-        L['gen_video_sn_gan_loss'] = (gan_loss(outputs['discrim_video_sn_logits_fake'], 1.0, hp.gan_loss_type),
-                                      hp.video_sn_gan_weight)
-        if hp.gan_feature_cdist_weight:
-            s = sum(cosine_distance(outputs['discrim_video_sn_feature%d_fake' % i],
-                                    outputs['discrim_video_sn_feature%d_real' % i]) for i in range(7))
-            L['gen_video_sn_gan_feature_cdist_loss'] = (s, hp.gan_feature_cdist_weight)
-    if hp.video_sn_vae_gan_weight:
-        L['gen_video_sn_vae_gan_loss'] = (gan_loss(outputs['discrim_video_sn_logits_enc_fake'], 1.0, hp.gan_loss_type),
-                                          hp.video_sn_vae_gan_weight)
-        if hp.vae_gan_feature_cdist_weight:
-            s = sum(cosine_distance(outputs['discrim_video_sn_feature%d_enc_fake' % i],
-                                    outputs['discrim_video_sn_feature%d_enc_real' % i]) for i in range(7))
-            L['gen_video_sn_vae_gan_feature_cdist_loss'] = (s, hp.vae_gan_feature_cdist_weight)
+    for infix, w_gan, w_vae in (('_image_sn', hp.image_sn_gan_weight, hp.image_sn_vae_gan_weight),
+                                ('_video_sn', hp.video_sn_gan_weight, hp.video_sn_vae_gan_weight)):
+        if w_gan:
+            L['gen%s_gan_loss' % infix] = (gan_loss(outputs['discrim%s_logits_fake' % infix], 1.0, hp.gan_loss_type), w_gan)
+            if hp.gan_feature_cdist_weight:
+                sm = sum(cosine_distance(outputs['discrim%s_feature%d_fake' % (infix, i)],
+                                         outputs['discrim%s_feature%d_real' % (infix, i)]) for i in range(7))
+                L['gen%s_gan_feature_cdist_loss' % infix] = (sm, hp.gan_feature_cdist_weight)
+        if w_vae and hp.nz:
+            L['gen%s_vae_gan_loss' % infix] = (gan_loss(outputs['discrim%s_logits_enc_fake' % infix], 1.0, hp.gan_loss_type), w_vae)
+            if hp.vae_gan_feature_cdist_weight:
+                sm = sum(cosine_distance(outputs['discrim%s_feature%d_enc_fake' % (infix, i)],
+                                         outputs['discrim%s_feature%d_enc_real' % (infix, i)]) for i in range(7))
+                L['gen%s_vae_gan_feature_cdist_loss' % infix] = (sm, hp.vae_gan_feature_cdist_weight)
     if hp.kl_weight:
         L['gen_kl_loss'] = (kl_loss(outputs['zs_mu_enc'], outputs['zs_log_sigma_sq_enc']), kl_weight(hp, step))
     return L
@@ -829,14 +870,14 @@ def discriminator_losses(hp, outputs):
     """base_model.py:831-852."""
     L = OrderedDict()
     t = hp.gan_loss_type
-    if hp.video_sn_gan_weight:
-        L['discrim_video_sn_gan_loss'] = (gan_loss(outputs['discrim_video_sn_logits_real'], 1.0, t) +
-                                          gan_loss(outputs['discrim_video_sn_logits_fake'], 0.0, t),
-                                          hp.video_sn_gan_weight)
-    if hp.video_sn_vae_gan_weight:
-        L['discrim_video_sn_vae_gan_loss'] = (gan_loss(outputs['discrim_video_sn_logits_enc_real'], 1.0, t) +
-                                              gan_loss(outputs['discrim_video_sn_logits_enc_fake'], 0.0, t),
-                                              hp.video_sn_vae_gan_weight)
+    for infix, w_gan, w_vae in (('_image_sn', hp.image_sn_gan_weight, hp.image_sn_vae_gan_weight),
+                                ('_video_sn', hp.video_sn_gan_weight, hp.video_sn_vae_gan_weight)):
+        if w_gan:
+            L['discrim%s_gan_loss' % infix] = (gan_loss(outputs['discrim%s_logits_real' % infix], 1.0, t) +
+                                               gan_loss(outputs['discrim%s_logits_fake' % infix], 0.0, t), w_gan)
+        if w_vae and hp.nz:
+            L['discrim%s_vae_gan_loss' % infix] = (gan_loss(outputs['discrim%s_logits_enc_real' % infix], 1.0, t) +
+                                                   gan_loss(outputs['discrim%s_logits_enc_fake' % infix], 0.0, t), w_vae)
     return L
 
 
@@ -875,7 +916,7 @@ def train_step(params, opt, hp, inputs, noise, step, sampling=None):
     lr = learning_rate(hp, step)
     t = opt['t'] + 1
     newp = OrderedDict((k, v.detach()) for k, v in P.items())
-    has_d = bool(hp.video_sn_gan_weight or hp.video_sn_vae_gan_weight)
+    has_d = bool(hp.video_sn_gan_weight or hp.video_sn_vae_gan_weight or hp.image_sn_gan_weight or hp.image_sn_vae_gan_weight)
     u_new = {}
     if has_d:
         gen_det = {k: v.detach() for k, v in gen_out.items()}
@@ -932,9 +973,10 @@ def init_params(hp, image_shape, batch=1, action_dim=0, seed=0, dtype=torch.floa
         saved = hp.sequence_length
         gt = ground_truth_mask(hp, batch)
         out = generator(V, hp, inputs, noise, gt)
-        if hp.video_sn_gan_weight or hp.video_sn_vae_gan_weight:
+        if hp.video_sn_gan_weight or hp.video_sn_vae_gan_weight or hp.image_sn_gan_weight or hp.image_sn_vae_gan_weight:
             z = torch.zeros(batch, dtype=torch.long)
-            discriminator(V, hp, inputs, out, dict(real=z, fake=z, enc_real=z, enc_fake=z))
+            discriminator(V, hp, inputs, out, dict(real=z, fake=z, enc_real=z, enc_fake=z, image_real=z, image_fake=z,
+                                                   image_enc_real=z, image_enc_fake=z))
         assert hp.sequence_length == saved
     return V.params, V.trainable
 
@@ -971,4 +1013,7 @@ def make_synthetic_inputs(hp, batch, image_shape, action_dim=0, seed=0, dtype=to
         for which in ('d_pre', 'd_post'):
             noise[which] = {k: torch.tensor(rng.integers(0, hi, size=batch), dtype=torch.long)
                             for k in ('real', 'fake', 'enc_real', 'enc_fake')}
+        for which in ('d_pre', 'd_post'):      # t_sample of the image discriminators (drawn after, so earlier fixtures keep their values)
+            noise[which].update({'image_' + k: torch.tensor(rng.integers(0, T - 1, size=batch), dtype=torch.long)
+                                 for k in ('real', 'fake', 'enc_real', 'enc_fake')})
     return inputs, noise

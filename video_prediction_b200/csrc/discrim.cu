@@ -134,9 +134,8 @@ __global__ void scatter_clip_kernel(const float4* __restrict__ dclip, const int3
   const int b = static_cast<int>(idx / (P * clip_len));
   float4* o = dvideo + (static_cast<long long>(t_start[b] + j) * NBv + b_off + b) * P + p;
   const float4 d = dclip[idx];
-  float4 c = *o;
-  c.x += d.x; c.y += d.y; c.z += d.z; c.w += d.w;
-  *o = c;
+  // towers of different kinds (image / video) on the same unroll run as parallel graph branches and add into the same rows
+  red_add_v4(reinterpret_cast<float*>(o), d.x, d.y, d.z, d.w);
 }
 
 }  // namespace vp

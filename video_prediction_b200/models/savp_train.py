@@ -24,10 +24,17 @@ VIDEO_D_LAYERS = [  # networks.py:83-102: (scope, ndf multiplier, kernel, stride
     ('sn_conv2_0', 4, 3, (1, 1, 1)), ('sn_conv2_1', 8, 4, (2, 2, 2)),
     ('sn_conv3_0', 8, 3, (1, 1, 1)),
 ]
+IMAGE_D_LAYERS = [  # networks.py:45-63 (image_sn_discriminator): the 2-D analogue, applied to ONE sampled frame per video
+    ('sn_conv0_0', 1, 3, (1, 1, 1)), ('sn_conv0_1', 2, 4, (1, 2, 2)),
+    ('sn_conv1_0', 2, 3, (1, 1, 1)), ('sn_conv1_1', 4, 4, (1, 2, 2)),
+    ('sn_conv2_0', 4, 3, (1, 1, 1)), ('sn_conv2_1', 8, 4, (1, 2, 2)),
+    ('sn_conv3_0', 8, 3, (1, 1, 1)),
+]
 
-LOSS_SLOTS = ['gen_l1_loss', 'gen_l2_loss', 'gen_kl_loss', 'gen_video_sn_gan_loss', 'gen_video_sn_vae_gan_loss',
-              'gen_video_sn_vae_gan_feature_cdist_loss', 'gen_video_sn_gan_feature_cdist_loss',
-              'discrim_video_sn_gan_loss', 'discrim_video_sn_vae_gan_loss']
+LOSS_SLOTS = ['gen_l1_loss', 'gen_l2_loss', 'gen_kl_loss']
+for _kind in ('video', 'image'):
+    LOSS_SLOTS += ['gen_%s_sn_gan_loss' % _kind, 'gen_%s_sn_vae_gan_loss' % _kind, 'gen_%s_sn_vae_gan_feature_cdist_loss' % _kind,
+                   'gen_%s_sn_gan_feature_cdist_loss' % _kind, 'discrim_%s_sn_gan_loss' % _kind, 'discrim_%s_sn_vae_gan_loss' % _kind]
 
 
 def _ceil4(v):
@@ -37,15 +44,17 @@ def _ceil4(v):
 class SNLayer(object):
     """A spectrally-normalised conv3d (or the final dense) of the video discriminator."""
 
-    def __init__(self, model, scope, name, k, stride, cin_ref, cin_int, cmap, co, is_fc=False, fc_in=0):
+    def __init__(self, model, scope, name, k, stride, cin_ref, cin_int, cmap, co, is_fc=False, fc_in=0, two_d=False):
         self.m, self.is_fc = model, is_fc
         self.k, self.stride, self.co = k, stride, co
+        self.two_d = two_d                          # image discriminator: conv2d kernels [k,k,ci,co], no temporal extent
+        self.k3 = (1, k, k) if two_d else (k, k, k)
         self.cin_ref, self.cin_int = cin_ref, cin_int
-        sub = 'dense' if is_fc else 'conv3d'
+        sub = 'dense' if is_fc else ('conv2d' if two_d else 'conv3d')
         self.wname = '%s/%s/%s/kernel' % (scope, name, sub)
         self.uname = '%s/%s/%s/u' % (scope, name, sub)
         self.bname = '%s/%s/%s/bias' % (scope, name, sub)
-        self.rows = fc_in if is_fc else k * k * k * cin_ref
+        self.rows = fc_in if is_fc else int(np.prod(self.k3)) * cin_ref
         self.cols = co
         dev = model.device
         z = lambda *s: torch.zeros(*s, device=dev, dtype=torch.float32)
@@ -55,8 +64,9 @@ class SNLayer(object):
         self.u_next = z(self.cols)
         self.cmap = None if cmap is None else torch.tensor(cmap, dtype=torch.int32, device=dev)
         if not is_fc:
-            self.geom = L.geom((k, k, k), stride, (1, 1, 1), False)
-            self.geom_t = L.geom((k, k, k), stride, (1, 1, 1), True)
+            pad = (0, 1, 1) if two_d else (1, 1, 1)        # tf.pad of 1 on H,W (and T for conv3d) + VALID (networks.py:38-43, 76-81)
+            self.geom = L.geom(self.k3, stride, pad, False)
+            self.geom_t = L.geom(self.k3, stride, pad, True)
             self.wp = self.wpd = self.dwp = None
 
     @property
@@ -71,7 +81,7 @@ class SNLayer(object):
         if self.is_fc:
             return
         w = self.m.params[self.wname]
-        kk = (self.k,) * 3
+        kk = self.k3
         self.wp, self.n_pad, self.kc = L.pack_weights(w, kk, self.cin_ref, self.co, L.WKIND_PLAIN, L.WLAYOUT_FWD,
                                                       ci_int=self.cin_int, cmap=self.cmap, inv_scale=self.sigma, out=self.wp)
         self.wpd, self.n_pad_d, self.kc_d = L.pack_weights(w, kk, self.cin_ref, self.co, L.WKIND_PLAIN, L.WLAYOUT_DGRAD,
@@ -82,7 +92,7 @@ class SNLayer(object):
             self.wpd_lo, _, _ = L.pack_weights(w, kk, self.cin_ref, self.co, L.WKIND_PLAIN, L.WLAYOUT_DGRAD | L.WLAYOUT_RESIDUAL,
                                                ci_int=self.cin_int, cmap=self.cmap, inv_scale=self.sigma, out=getattr(self, 'wpd_lo', None))
         if self.dwp is None:
-            self.dwp = torch.zeros(self.k ** 3 * self.n_pad * self.kc * 32, device=w.device)
+            self.dwp = torch.zeros(int(np.prod(self.k3)) * self.n_pad * self.kc * 32, device=w.device)
 
     @property
     def cuda_core(self):
@@ -91,7 +101,7 @@ class SNLayer(object):
         44.0 ms/step against 40.2 ms/step with these kernels (VP_D0_CUDA_CORE=0 selects the engine for comparison)."""
         if os.environ.get('VP_D0_CUDA_CORE', '1') != '1':
             return False
-        return (not self.is_fc) and self.k == 3 and tuple(self.stride) == (1, 1, 1) and self.cin_ref <= 3 and self.co == 32
+        return (not self.is_fc) and not self.two_d and self.k == 3 and tuple(self.stride) == (1, 1, 1) and self.cin_ref <= 3 and self.co == 32
 
     def fwd(self, x, out):
         # the first layer's FORWARD runs on the tensor-core engine: halo mode loads one activation tile per 9 taps, which
@@ -141,7 +151,7 @@ class SNLayer(object):
             L.conv_wgrad(L.tensor_view(L.tf32_residual(x.contiguous()), self.cin_int), dyv, self.geom, self.dwp, self.n_pad, self.kc, split_k=0)
             L.conv_wgrad(xv, L.tensor_view(L.tf32_residual(dy.contiguous()), self.co), self.geom, self.dwp, self.n_pad, self.kc, split_k=0)
         self.gwbar.zero_()
-        L.unpack_wgrad(self.dwp, (self.k,) * 3, self.cin_ref, self.co, L.WKIND_PLAIN, self.gwbar, self.n_pad, self.kc,
+        L.unpack_wgrad(self.dwp, self.k3, self.cin_ref, self.co, L.WKIND_PLAIN, self.gwbar, self.n_pad, self.kc,
                        ci_int=self.cin_int, cmap=self.cmap)
         self.sn_backward()
 
@@ -153,36 +163,54 @@ class SNLayer(object):
 
 class TrainMixin(object):
     # ------------------------------------------------------------------ parameter specs
-    def _d_scopes(self):
+    def _d_towers(self):
+        """Discriminator towers of discriminator_fn / discriminator_given_video_fn (savp_model.py:88-166): per enabled kind
+        (image: one sampled frame, networks.py:35-69; video: a clip_length clip, networks.py:72-108) one tower in the root
+        scope (real / fake = prior-unroll images) and, with nz > 0, one with separate weights under encoder/ (enc_real /
+        enc_fake = posterior-unroll images; use_same_discriminator=False).  `images_sn_*` (per-frame discriminator over the
+        whole clip) is refused in _check_supported."""
         hp = self.hparams
-        scopes = []
-        if hp.video_sn_gan_weight or hp.video_sn_vae_gan_weight:
-            if hp.nz:
-                scopes.append('discriminator/encoder/video')
-            scopes.append('discriminator/video')
-        return scopes
+        towers = []
+        for kind, w_gan, w_vae in (('image', hp.image_sn_gan_weight, hp.image_sn_vae_gan_weight),
+                                   ('video', hp.video_sn_gan_weight, hp.video_sn_vae_gan_weight)):
+            if w_gan or w_vae:
+                if hp.nz:
+                    towers.append(dict(scope='discriminator/encoder/' + kind, kind=kind, enc=True, weight=w_vae,
+                                       cdist=hp.vae_gan_feature_cdist_weight if w_vae else 0.0, keys=('enc_real', 'enc_fake')))
+                towers.append(dict(scope='discriminator/' + kind, kind=kind, enc=False, weight=w_gan,
+                                   cdist=hp.gan_feature_cdist_weight if w_gan else 0.0, keys=('real', 'fake')))
+        return towers
 
-    def _d_shapes(self):
-        """Output dims (T',H',W',C') of the 7 conv3d layers for clips [clip_length,H,W,C]."""
+    def _d_scopes(self):
+        return [t['scope'] for t in self._d_towers()]
+
+    def _d_shapes(self, kind='video'):
+        """Output dims (T',H',W',C') of the 7 conv layers for clips [clip,H,W,C] (image towers: clip = 1, no temporal taps)."""
         hp = self.hparams
-        dims = (hp.clip_length, self.H, self.W)
+        layers = VIDEO_D_LAYERS if kind == 'video' else IMAGE_D_LAYERS
+        dims = (hp.clip_length if kind == 'video' else 1, self.H, self.W)
         out = []
-        for name, mult, k, st in VIDEO_D_LAYERS:
-            dims = tuple((d + 2 - k) // s + 1 for d, s in zip(dims, st))
+        for name, mult, k, st in layers:
+            kk, pad = ((k, k, k), (1, 1, 1)) if kind == 'video' else ((1, k, k), (0, 1, 1))
+            dims = tuple((d + 2 * p - q) // s + 1 for d, p, q, s in zip(dims, pad, kk, st))
             out.append(dims + (hp.ndf * mult,))
         return out
 
     def _discriminator_param_specs(self):
         hp = self.hparams
         specs = OrderedDict()
-        shapes = self._d_shapes()
-        for scope in self._d_scopes():
+        for tw in self._d_towers():
+            scope, kind = tw['scope'], tw['kind']
+            shapes = self._d_shapes(kind)
+            layers = VIDEO_D_LAYERS if kind == 'video' else IMAGE_D_LAYERS
+            sub = 'conv3d' if kind == 'video' else 'conv2d'
             cin = self.C
-            for (name, mult, k, st), shp in zip(VIDEO_D_LAYERS, shapes):
+            for (name, mult, k, st), shp in zip(layers, shapes):
                 co = hp.ndf * mult
-                specs['%s/%s/conv3d/kernel' % (scope, name)] = ((k, k, k, cin, co), 'kernel')
-                specs['%s/%s/conv3d/u' % (scope, name)] = ((1, co), 'u')
-                specs['%s/%s/conv3d/bias' % (scope, name)] = ((co,), 'zeros')
+                kshape = (k, k, k, cin, co) if kind == 'video' else (k, k, cin, co)
+                specs['%s/%s/%s/kernel' % (scope, name, sub)] = (kshape, 'kernel')
+                specs['%s/%s/%s/u' % (scope, name, sub)] = ((1, co), 'u')
+                specs['%s/%s/%s/bias' % (scope, name, sub)] = ((co,), 'zeros')
                 cin = co
             f = int(np.prod(shapes[-1]))
             specs['%s/sn_fc4/dense/kernel' % scope] = ((f, 1), 'kernel')
@@ -195,17 +223,20 @@ class TrainMixin(object):
         hp = self.hparams
         B, H, W, C = self.B, self.H, self.W, self.C
         z = self._z
-        shapes = self._d_shapes()
         self.dnets = OrderedDict()
-        for scope in self._d_scopes():
-            net = dict(scope=scope, layers=[], feat=[], dfeat=[], dcd=[])
+        for tw in self._d_towers():
+            scope, kind = tw['scope'], tw['kind']
+            shapes = self._d_shapes(kind)
+            layers = VIDEO_D_LAYERS if kind == 'video' else IMAGE_D_LAYERS
+            clip_len = hp.clip_length if kind == 'video' else 1
+            net = dict(tw, layers=[], feat=[], dfeat=[], dcd=[], clip_len=clip_len)
             cin_ref, cin_int, cmap = C, 4, list(range(C)) + [-1] * (4 - C)
             nb = 2 * B
-            net['clip'] = z(nb, hp.clip_length, H, W, 4)
-            net['dclip'] = z(nb, hp.clip_length, H, W, 4)
-            for (name, mult, k, st), shp in zip(VIDEO_D_LAYERS, shapes):
+            net['clip'] = z(nb, clip_len, H, W, 4)
+            net['dclip'] = z(nb, clip_len, H, W, 4)
+            for (name, mult, k, st), shp in zip(layers, shapes):
                 co = hp.ndf * mult
-                net['layers'].append(SNLayer(self, scope, name, k, st, cin_ref, cin_int, cmap, co))
+                net['layers'].append(SNLayer(self, scope, name, k, st, cin_ref, cin_int, cmap, co, two_d=(kind == 'image')))
                 net['feat'].append(z(nb, *shp))
                 net['dfeat'].append(z(nb, *shp))
                 net['dcd'].append(z(B, *shp))
@@ -285,8 +316,8 @@ class TrainMixin(object):
         B, NB, HW = self.B, self.NB, self.H * self.W
         Bf = self.Bf
         if rows_real:
-            L.gather_clip(Bf['x'][1:], t_real, net['clip'][:B], B, hp.clip_length, HW, NB, 0)
-        L.gather_clip(Bf['gen'], t_fake, net['clip'][B:], B, hp.clip_length, HW, NB, fake_off)
+            L.gather_clip(Bf['x'][1:], t_real, net['clip'][:B], B, net['clip_len'], HW, NB, 0)
+        L.gather_clip(Bf['gen'], t_fake, net['clip'][B:], B, net['clip_len'], HW, NB, fake_off)
 
     def _d_forward(self, net, r0, r1):
         """Runs the tower on clip rows [r0, r1)."""
@@ -528,16 +559,18 @@ class TrainMixin(object):
         return self.loss_vals[LOSS_SLOTS.index(name):LOSS_SLOTS.index(name) + 1]
 
     def _set_tstarts(self, noise):
-        hp = self.hparams
-        hi = self.S - hp.clip_length + 1
-        keys = {'discriminator/encoder/video': ('enc_real', 'enc_fake'), 'discriminator/video': ('real', 'fake')}
-        for scope, net in self.dnets.items():
+        """Clip offsets t_start[B] in [0, T-1-clip_length] (video towers) / frame indices t_sample[B] in [0, T-2] (image towers)
+        of the two discriminator_fn instantiations (pre / post D update; savp_model.py:93-98).  `noise[which][key]` (as the
+        oracle takes them: 'real', 'fake', 'enc_real', 'enc_fake' for video, 'image_*' for image towers) overrides the draw."""
+        for ti, (scope, net) in enumerate(self.dnets.items()):
+            hi = self.S - net['clip_len'] + 1
             for w, which in enumerate(('d_pre', 'd_post')):
-                for r, key in enumerate(keys[scope]):
-                    if noise is not None and which in noise:
-                        v = torch.as_tensor(noise[which][key]).to(torch.int32)
+                for r, key in enumerate(net['keys']):
+                    nkey = key if net['kind'] == 'video' else 'image_' + key
+                    if noise is not None and which in noise and nkey in noise[which]:
+                        v = torch.as_tensor(noise[which][nkey]).to(torch.int32)
                     else:
-                        g = torch.Generator().manual_seed(self._seed('clips', 8 * list(self.dnets).index(scope) + 2 * w + r))
+                        g = torch.Generator().manual_seed(self._seed('clips', 8 * ti + 2 * w + r))
                         v = torch.randint(0, hi, (self.B,), generator=g, dtype=torch.int32)
                     if 'ts' not in net:
                         net['ts'] = {(a, b): torch.zeros(self.B, dtype=torch.int32, device=self.device)
@@ -632,11 +665,12 @@ class TrainMixin(object):
         if has_d:
             self.d_grad.zero_()
             def d_step_tower(scope, net):
-                enc = scope.endswith('encoder/video')
-                w = hp.video_sn_vae_gan_weight if enc else hp.video_sn_gan_weight
+                enc, w, kind = net['enc'], net['weight'], net['kind']
+                if not w:
+                    return      # the reference builds the tower but no loss term reads it (base_model.py:831-852)
                 self._d_gather(net, 'pre', net['ts'][('d_pre', 0)], net['ts'][('d_pre', 1)], 0 if enc else (B if hp.nz else 0))
                 self._d_forward(net, 0, 2 * B)
-                slot = self._slot('discrim_video_sn_vae_gan_loss' if enc else 'discrim_video_sn_gan_loss')
+                slot = self._slot('discrim_%s_sn_%sgan_loss' % (kind, 'vae_' if enc else ''))
                 L.gan_loss(net['logits'][:B], 1.0, B, w, hp.gan_loss_type, net['dlogits'][:B], slot)
                 L.gan_loss(net['logits'][B:], 0.0, B, w, hp.gan_loss_type, net['dlogits'][B:], slot)
                 self._d_backward(net, 0, 2 * B, with_wgrad=True, to_clip=False)
@@ -666,30 +700,28 @@ class TrainMixin(object):
             L.kl_loss(Bf['zmu'], Bf['zlss'], S * B, hp.nz, self._slot('gen_kl_loss'))
         if has_d:
             def g_step_tower(scope, net):
-                enc = scope.endswith('encoder/video')
-                w = hp.video_sn_vae_gan_weight if enc else hp.video_sn_gan_weight
-                cd_w = hp.vae_gan_feature_cdist_weight if enc else hp.gan_feature_cdist_weight
+                enc, w, kind, cd_w = net['enc'], net['weight'], net['kind'], net['cdist']
+                if not w:
+                    return
                 foff = 0 if enc else (B if hp.nz else 0)
                 need_real = bool(cd_w)
                 self._d_gather(net, 'post', net['ts'][('d_post', 0)], net['ts'][('d_post', 1)], foff, rows_real=need_real)
                 self._d_forward(net, 0 if need_real else B, 2 * B)
-                if w:
-                    L.gan_loss(net['logits'][B:], 1.0, B, w, hp.gan_loss_type, net['dlogits'][B:],
-                               self._slot('gen_video_sn_vae_gan_loss' if enc else 'gen_video_sn_gan_loss'))
-                else:
-                    net['dlogits'][B:].zero_()
+                L.gan_loss(net['logits'][B:], 1.0, B, w, hp.gan_loss_type, net['dlogits'][B:],
+                           self._slot('gen_%s_sn_%sgan_loss' % (kind, 'vae_' if enc else '')))
                 dcd = None
                 if cd_w:
                     dcd = net['dcd']
-                    slot = self._slot('gen_video_sn_vae_gan_feature_cdist_loss' if enc else 'gen_video_sn_gan_feature_cdist_loss')
+                    slot = self._slot('gen_%s_sn_%sgan_feature_cdist_loss' % (kind, 'vae_' if enc else ''))
                     for l, feat in enumerate(net['feat']):
                         dcd[l].zero_()
                         co = feat.shape[-1]
                         rows = int(np.prod(feat.shape[1:-1])) * B
                         L.cosine_distance(feat[B:], feat[:B], dcd[l], rows, co, cd_w, slot)
                 self._d_backward(net, B, 2 * B, with_wgrad=False, to_clip=True, dcd=dcd)
-                # the towers scatter into disjoint sample rows of dgen (posterior rows [0, B), prior rows [B, 2B))
-                L.scatter_clip(net['dclip'][B:], net['ts'][('d_post', 1)], G['dgen'], B, hp.clip_length, HW, NB, foff)
+                # the towers scatter into disjoint sample rows of dgen per unroll; towers of different kinds on the same
+                # unroll accumulate (scatter_clip adds)
+                L.scatter_clip(net['dclip'][B:], net['ts'][('d_post', 1)], G['dgen'], B, net['clip_len'], HW, NB, foff)
             self._run_concurrent([(lambda sc=sc, nt=nt: g_step_tower(sc, nt)) for sc, nt in self.dnets.items()])
         # ---- BPTT
         for t in range(S - 1, -1, -1):
@@ -728,12 +760,16 @@ class TrainMixin(object):
         hp = self.hparams
         step = self._staged_step if step is None else step
         kl = (self.kl_weight_at(step) or 0.0) if (hp.kl_weight and hp.nz) else 0.0
-        return OrderedDict([
-            ('gen_l1_loss', hp.l1_weight), ('gen_l2_loss', hp.l2_weight), ('gen_kl_loss', kl),
-            ('gen_video_sn_gan_loss', hp.video_sn_gan_weight), ('gen_video_sn_vae_gan_loss', hp.video_sn_vae_gan_weight),
-            ('gen_video_sn_vae_gan_feature_cdist_loss', hp.vae_gan_feature_cdist_weight),
-            ('gen_video_sn_gan_feature_cdist_loss', hp.gan_feature_cdist_weight),
-            ('discrim_video_sn_gan_loss', hp.video_sn_gan_weight), ('discrim_video_sn_vae_gan_loss', hp.video_sn_vae_gan_weight)])
+        w = OrderedDict([('gen_l1_loss', hp.l1_weight), ('gen_l2_loss', hp.l2_weight), ('gen_kl_loss', kl)])
+        for kind, w_gan, w_vae in (('video', hp.video_sn_gan_weight, hp.video_sn_vae_gan_weight),
+                                   ('image', hp.image_sn_gan_weight, hp.image_sn_vae_gan_weight)):
+            w['gen_%s_sn_gan_loss' % kind] = w_gan
+            w['gen_%s_sn_vae_gan_loss' % kind] = w_vae if hp.nz else 0.0
+            w['gen_%s_sn_vae_gan_feature_cdist_loss' % kind] = hp.vae_gan_feature_cdist_weight if (w_vae and hp.nz) else 0.0
+            w['gen_%s_sn_gan_feature_cdist_loss' % kind] = hp.gan_feature_cdist_weight if w_gan else 0.0
+            w['discrim_%s_sn_gan_loss' % kind] = w_gan
+            w['discrim_%s_sn_vae_gan_loss' % kind] = w_vae if hp.nz else 0.0
+        return w
 
     @staticmethod
     def split_losses(vals, weights):
