@@ -58,3 +58,27 @@ def mean_scalars(t):
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         t /= dist.get_world_size()
     return t
+
+
+class GradientReducer(object):
+    """Bucketed, overlapped gradient all-reduce (sum) of a flat buffer.  `reduce_range(lo, hi)` enqueues the all-reduce of
+    flat[lo:hi] on ONE dedicated communication stream as soon as the producing stream has finished that range (an event), so
+    the exchange of one layer's gradients runs under the computation of the next; NCCL operations of a communicator must
+    not run concurrently, which the single stream guarantees (also inside a captured CUDA graph, where they become a chain of
+    nodes).  `join()` makes the current stream wait for everything enqueued.  The reference issues one nccl.all_sum per
+    variable after the whole backward pass (tf_utils.py:450-480); the sums are identical."""
+
+    def __init__(self, device):
+        self.stream = torch.cuda.Stream(device=device)
+
+    def reduce_range(self, flat, lo, hi):
+        if hi <= lo:
+            return
+        ev = torch.cuda.Event()
+        ev.record()                                  # on the producing (current) stream
+        self.stream.wait_event(ev)
+        with torch.cuda.stream(self.stream):
+            dist.all_reduce(flat[lo:hi], op=dist.ReduceOp.SUM)
+
+    def join(self):
+        torch.cuda.current_stream().wait_stream(self.stream)

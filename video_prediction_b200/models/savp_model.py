@@ -15,6 +15,7 @@ HBM-bound kernels (csrc/elementwise.cu).  PyTorch only owns memory and streams.
 from __future__ import annotations
 
 import itertools
+import os
 from collections import OrderedDict
 
 import numpy as np
@@ -389,6 +390,7 @@ class SAVPVideoPredictionModel(TrainMixin, VideoPredictionModel):
         if self.world_size > 1:     # replicas start from rank 0's variables (post_init_ops, base_model.py:640-646)
             dp.broadcast_state([self.g_flat, self.d_flat] + [v for k, v in self.params.items() if k.endswith('/u')])
         self._allreduce = dp.make_allreduce()
+        self._reducer = dp.GradientReducer(self.device) if (self.world_size > 1 and os.environ.get('VP_DP_BUCKETS', '1') == '1') else None
         self._build_generator()
         if self.mode == 'train':
             self._build_discriminator()
@@ -538,6 +540,16 @@ class SAVPVideoPredictionModel(TrainMixin, VideoPredictionModel):
                     if ('adam/' + nm) in data.files and data['adam/' + nm].shape == tuple(buf.shape):
                         buf.copy_(torch.from_numpy(data['adam/' + nm]).to(self.device))
                 self.g_adam_t, self.d_adam_t = [int(v) for v in data['adam/t']]
+
+    def _flat_range(self, flat, names):
+        """[lo, hi) element range of `flat` covered by the variables `names` (views of the flat buffer)."""
+        lo, hi = None, None
+        for n in names:
+            v = self.params[n]
+            o = (v.data_ptr() - flat.data_ptr()) // 4
+            lo = o if lo is None else min(lo, o)
+            hi = o + v.numel() if hi is None else max(hi, o + v.numel())
+        return (lo or 0), (hi or 0)
 
     def get_params(self):
         return OrderedDict((k, v.detach().cpu().numpy()) for k, v in self.params.items())
@@ -709,6 +721,7 @@ class SAVPVideoPredictionModel(TrainMixin, VideoPredictionModel):
         B, T, S, C = self.B, self.T, self.S, self.C
         if getattr(self, '_shard', None) is not None and int(inputs['images'].shape[0]) != B:
             inputs = {k: v[self._shard] for k, v in inputs.items()}
+            noise, sampling = self._shard_noise(noise), self._shard_cols(sampling)
         imgs = torch.as_tensor(inputs['images']).to(dev, torch.float32)[:, :T]
         x = imgs.permute(1, 0, 2, 3, 4)
         Bf['x'].zero_()
@@ -769,6 +782,27 @@ class SAVPVideoPredictionModel(TrainMixin, VideoPredictionModel):
                              z_prior=torch.randn(self.T - hp.context_frames, self.B, hp.nz, generator=g))
             Bf['eps'].copy_(torch.as_tensor(noise['eps']).to(self.device, torch.float32))
             Bf['zprior'].copy_(torch.as_tensor(noise['z_prior']).to(self.device, torch.float32))
+
+    def _shard_cols(self, t):
+        """A [.., global batch] tensor (time-major noise / masks) -> this rank's columns."""
+        if t is None or t is False or getattr(self, '_shard', None) is None:
+            return t
+        t = torch.as_tensor(t)
+        return t[:, self._shard] if t.dim() >= 2 and t.shape[1] == self.B * self.world_size else t
+
+    def _shard_noise(self, noise):
+        """Explicit noise given for the GLOBAL batch (num_gpus > 1): eps / z_prior [T', B_global, nz] and the discriminators'
+        offsets [B_global] are cut to this rank's shard like the inputs."""
+        if noise is None or getattr(self, '_shard', None) is None:
+            return noise
+        out = {}
+        for k, v in noise.items():
+            if isinstance(v, dict):
+                out[k] = {kk: (torch.as_tensor(vv)[self._shard] if torch.as_tensor(vv).shape[0] == self.B * self.world_size else vv)
+                          for kk, vv in v.items()}
+            else:
+                out[k] = self._shard_cols(v)
+        return out
 
     def _seed(self, what, extra=0):
         """Host RNG seeds: distinct per purpose, step, data-parallel rank and `extra` (e.g. discriminator scope)."""

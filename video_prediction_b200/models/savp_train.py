@@ -458,18 +458,35 @@ class TrainMixin(object):
             L.axpy_channels(G['dimg'][t].data_ptr(), 4, G['dgen'][t - 1].data_ptr(), 4, NB * HW, 4, row_mask=Bf['sel'][t],
                             rows_per_mask=HW)
 
-    def _gen_backward_params(self):
-        """Time-batched weight/bias gradients + the z path (dense LSTM on z, posterior encoder)."""
+    def _gen_backward_params(self, red=None):
+        """Time-batched weight/bias gradients + the z path (dense LSTM on z, posterior encoder).  With a GradientReducer
+        (data parallel) every generator layer's slice of the flat gradient buffer is all-reduced as soon as it is final, under
+        the weight-gradient GEMMs of the following layers; the remainder goes at the end."""
+        done = []                                    # [lo, hi) ranges already exchanged
+        self._gen_backward_params_body(red, done)
+        if red is not None:
+            pos = 0
+            for lo, hi in sorted(done) + [(self.g_flat.numel(), self.g_flat.numel())]:
+                red.reduce_range(self.g_grad, pos, lo)
+                pos = max(pos, hi)
+
+    def _gen_backward_params_body(self, red, done):
         hp = self.hparams
         Bf, G, P, Gp = self.Bf, self.Gb, self.params, self.grads
         S, NB, B, H, W, C = self.S, self.NB, self.B, self.H, self.W, self.C
         rows_top = S * NB * H * W
+        sc_cell = 'generator/rnn/savp_cell'
         for d in self.gl:
             li = d['li']
             d['conv'].wgrad(Bf['in%d' % li], G['dpre%d' % li])
             L.colsum(G['dpre%d' % li].data_ptr(), d['oc'], Gp[d['conv'].bname], 1, S * NB * d['h'] * d['w'], d['oc'])
             if d['use']:
                 d['rconv'].wgrad(Bf['rin%d' % li][:S], G['dgpre%d' % li])
+            if red is not None:
+                pre = ('%s/h%d/' % (sc_cell, li), '%s/lstm_h%d/' % (sc_cell, li))
+                lo, hi = self._flat_range(self.g_flat, [k for k in P if k.startswith(pre)])
+                red.reduce_range(self.g_grad, lo, hi)
+                done.append((lo, hi))
         top = Bf['out%d' % (self.nl - 1)]
         ngf = hp.ngf
         self.conv_scratch.wgrad(top, G['dspre'])
@@ -596,7 +613,7 @@ class TrainMixin(object):
         elif not staged:
             self.redraw_step_randomness(noise, sampling)      # resident inputs: fresh eps / z_prior / sampling mask per step
         if not staged:
-            self.stage_step(noise)
+            self.stage_step(self._shard_noise(noise))
         if self.use_cuda_graph and not staged and self._eager_steps >= 1 and not L.exact_mode():
             # the device part of the step (~1.5 k launches, no host sync) is captured once and replayed
             if self._graph is None:
@@ -651,6 +668,7 @@ class TrainMixin(object):
         self.loss_vals.zero_()
         has_d = bool(self.dnets)
         world = float(self.world_size)
+        red = getattr(self, '_reducer', None) if allreduce is not None else None     # bucketed, overlapped all-reduce (dp.py)
 
         def d_prepare(net):
             # spectral norm + weight packing of one tower (dozens of tiny dependent launches): independent of the generator
@@ -674,8 +692,13 @@ class TrainMixin(object):
                 L.gan_loss(net['logits'][:B], 1.0, B, w, hp.gan_loss_type, net['dlogits'][:B], slot)
                 L.gan_loss(net['logits'][B:], 0.0, B, w, hp.gan_loss_type, net['dlogits'][B:], slot)
                 self._d_backward(net, 0, 2 * B, with_wgrad=True, to_clip=False)
+                if red is not None:      # this tower's gradients are final: exchange them under the other towers' backward
+                    lo, hi = self._flat_range(self.d_flat, [k for k in self.params if k.startswith(scope + '/') and not k.endswith('/u')])
+                    red.reduce_range(self.d_grad, lo, hi)
             self._run_concurrent([(lambda sc=sc, nt=nt: d_step_tower(sc, nt)) for sc, nt in self.dnets.items()])
-            if allreduce is not None:
+            if red is not None:
+                red.join()
+            elif allreduce is not None:
                 allreduce(self.d_grad)
             L.adam(self.d_flat, self.d_grad, self.d_m, self.d_v, self.d_flat.numel(), self.step_scalars[0:1], hp.beta1, hp.beta2,
                    1.0 / world)
@@ -726,8 +749,10 @@ class TrainMixin(object):
         # ---- BPTT
         for t in range(S - 1, -1, -1):
             self._gen_backward_step(t)
-        self._gen_backward_params()
-        if allreduce is not None:
+        self._gen_backward_params(red)
+        if red is not None:
+            red.join()
+        elif allreduce is not None:
             allreduce(self.g_grad)
         L.adam(self.g_flat, self.g_grad, self.g_m, self.g_v, self.g_flat.numel(), self.step_scalars[1:2], hp.beta1, hp.beta2, 1.0 / world)
         if has_d:   # every forward of this step read the start-of-step u; store u' now
