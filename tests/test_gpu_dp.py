@@ -40,7 +40,8 @@ def _run(num_gpus):
     return model, lv
 
 
-def _worker(rank, world, port, q):
+def _worker(rank, world, port, q, env):
+    os.environ.update(env)
     os.environ.update(RANK=str(rank), LOCAL_RANK=str(rank), WORLD_SIZE=str(world), MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port),
                       CUDA_VISIBLE_DEVICES=','.join(str(i) for i in range(world)))
     sys.path.insert(0, ROOT)
@@ -53,14 +54,20 @@ def _worker(rank, world, port, q):
     dist.destroy_process_group()
 
 
-def test_two_ranks_equal_one_rank_on_the_global_batch():
+@pytest.mark.parametrize('mode,buckets,tol', [('exact', '0', 3e-3), ('tf32', '1', 2e-2)])
+def test_two_ranks_equal_one_rank_on_the_global_batch(mode, buckets, tol):
+    """exact: fp32-exact convolutions (VP_EXACT=1) -> the two runs differ by fp32 summation order only (3e-3, see
+    profiles/r02_parity_noise_floor.md).  tf32: product arithmetic, where different tile / split-K decisions at B/2 flip
+    operand truncations downstream (two correct TF32 runs differ by ~0.5 %); this variant also exercises the bucketed,
+    overlapped all-reduce (VP_DP_BUCKETS=1)."""
     if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
         pytest.skip('needs 2 GPUs')
     import torch.multiprocessing as mp
+    env = dict(VP_EXACT='1' if mode == 'exact' else '0', VP_DP_BUCKETS=buckets)
     ctx = mp.get_context('spawn')
     q = ctx.Queue()
-    port = 29600 + os.getpid() % 2000
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    port = 29600 + (os.getpid() + (7 if mode == 'exact' else 0)) % 2000
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q, env)) for r in range(2)]
     for p in procs:
         p.start()
     res = sorted((q.get(timeout=600) for _ in range(2)), key=lambda r: r[0])
@@ -72,10 +79,19 @@ def test_two_ranks_equal_one_rank_on_the_global_batch():
     assert l0 == l1                                            # losses() averages over the replicas (tf_utils.py:489-490)
     os.environ.pop('WORLD_SIZE', None)
     os.environ.pop('RANK', None)
-    ref, lref = _run(1)
+    old = {k: os.environ.get(k) for k in env}
+    os.environ.update(env)
+    try:
+        ref, lref = _run(1)
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
     for name, got, want in (('generator', gg0, ref.g_grad.cpu()), ('discriminator', dg0, ref.d_grad.cpu())):
         rel = ((got.double() - want.double()).norm() / want.double().norm()).item()
-        print('%s gradient: 2 ranks x B/2 vs 1 rank x B, relative L2 %.2e' % (name, rel))
-        assert rel <= 2e-3, (name, rel)                        # same operands, different fp32 summation order / split-K
+        print('[%s] %s gradient: 2 ranks x B/2 vs 1 rank x B, relative L2 %.2e' % (mode, name, rel))
+        assert rel <= tol, (name, rel)
     for k, v in lref.items():
-        assert abs(l0[k] - v) <= 2e-3 * abs(v) + 1e-6, (k, l0[k], v)
+        assert abs(l0[k] - v) <= 5e-3 * abs(v) + 1e-6, (k, l0[k], v)

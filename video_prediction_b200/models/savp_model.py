@@ -390,7 +390,10 @@ class SAVPVideoPredictionModel(TrainMixin, VideoPredictionModel):
         if self.world_size > 1:     # replicas start from rank 0's variables (post_init_ops, base_model.py:640-646)
             dp.broadcast_state([self.g_flat, self.d_flat] + [v for k, v in self.params.items() if k.endswith('/u')])
         self._allreduce = dp.make_allreduce()
-        self._reducer = dp.GradientReducer(self.device) if (self.world_size > 1 and os.environ.get('VP_DP_BUCKETS', '1') == '1') else None
+        # VP_DP_BUCKETS=1: per-tower / per-layer all-reduces overlapped with the backward pass (dp.GradientReducer).  Measured at
+        # 2 GPUs: 34.37 ms/step with buckets, 34.25 without (33.89 on one GPU) -- 18 extra NCCL launches cost what the overlap
+        # saves when two ~100 us all-reduces are all there is to hide, so the default stays two flat all-reduces
+        self._reducer = dp.GradientReducer(self.device) if (self.world_size > 1 and os.environ.get('VP_DP_BUCKETS', '0') == '1') else None
         self._build_generator()
         if self.mode == 'train':
             self._build_discriminator()
