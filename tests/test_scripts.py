@@ -9,6 +9,7 @@ import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, 'scripts'))
+sys.path.insert(0, os.path.join(ROOT, 'tests'))
 
 REFERENCE_TRAIN_FLAGS = ['--input_dir', '--val_input_dir', '--logs_dir', '--output_dir', '--output_dir_postfix', '--checkpoint',
                          '--resume', '--dataset', '--dataset_hparams', '--dataset_hparams_dict', '--model', '--model_hparams',
@@ -99,4 +100,23 @@ def test_train_three_steps_checkpoint_resume_and_generate(tmp_path):
     b = np.load(os.path.join(png_dir, 'gen_image_00000_01.npy'))
     assert a.shape == (6, 64, 64, 3) and a.dtype == np.uint8
     assert np.array_equal(a[:2], b[:2]) and not np.array_equal(a[2:], b[2:])    # same context, different noise draws
-    del w
+    # a TensorFlow-format checkpoint (tensor bundle) of the same variables, with the historical 'dna_cell' scope and Adam slots:
+    # restore() reads it through tf_checkpoint.py and the savp_cell -> dna_cell mapping (savp_model.py:848-855)
+    from test_tf_checkpoint import write_bundle
+    tensors = {k.replace('savp_cell', 'dna_cell'): v for k, v in model2.get_params().items()}
+    k0 = 'generator/rnn/savp_cell/h0/conv_pool2d/kernel'
+    tensors[k0.replace('savp_cell', 'dna_cell') + '/Adam'] = np.full(w.shape, 0.25, np.float32)
+    tensors['global_step'] = np.array(1234, np.int64)
+    tensors['beta1_power'] = np.array(0.5 ** 6, np.float32)
+    tf_dir = tmp_path / 'tf_ckpt'
+    tf_dir.mkdir()
+    write_bundle(str(tf_dir / 'model-1234'), tensors)
+    (tf_dir / 'checkpoint').write_text('model_checkpoint_path: "model-1234"\n')
+    from video_prediction_b200.models import get_model_class
+    m3 = get_model_class('savp')(mode='train', hparams_dict=model2.hparams.values())
+    m3.build_graph({'images': np.zeros((2, 6, 64, 64, 3), np.float32)})
+    m3.restore(None, str(tf_dir))
+    assert m3.global_step == 1234 and m3.g_adam_t == 5
+    for k, v in model2.get_params().items():
+        assert np.array_equal(m3.get_params()[k], v), k
+    assert float(m3._view_of(m3.g_m, m3.g_flat, k0).mean()) == 0.25

@@ -499,50 +499,91 @@ class SAVPVideoPredictionModel(TrainMixin, VideoPredictionModel):
 
     @staticmethod
     def latest_checkpoint(checkpoint):
-        """A checkpoint name, or a directory holding a `checkpoint` file (tf.train.latest_checkpoint)."""
+        """A checkpoint name, or a directory holding a `checkpoint` state file (tf.train.latest_checkpoint).  Both this
+        package's `.npz` checkpoints and TensorFlow bundles (`<prefix>.index` + `.data-*`) are resolved."""
         import os
+        from .. import tf_checkpoint as T
         if checkpoint and os.path.isdir(checkpoint):
             idx = os.path.join(checkpoint, 'checkpoint')
-            if not os.path.exists(idx):
-                return None
-            with open(idx) as f:
-                name = f.readline().split('"')[1]
-            return os.path.join(checkpoint, name)
+            if os.path.exists(idx):
+                with open(idx) as f:
+                    name = f.readline().split('"')[1]
+                path = name if os.path.isabs(name) else os.path.join(checkpoint, name)
+                if os.path.exists(path) or T.is_tf_checkpoint(path):
+                    return path
+            return T.latest_checkpoint(checkpoint)
         return checkpoint
 
+    @staticmethod
+    def restore_to_checkpoint_mapping(restore_name, checkpoint_var_names):
+        """savp_model.py:848-855: checkpoints written before the cell was renamed use the scope 'dna_cell'."""
+        restore_name = restore_name.split(':')[0]
+        if restore_name not in checkpoint_var_names:
+            restore_name = restore_name.replace('savp_cell', 'dna_cell')
+        return restore_name
+
+    def _view_of(self, flat_like, flat, name):
+        """The slice of a buffer parallel to `flat` (gradients, Adam slots) that belongs to variable `name`."""
+        v = self.params[name]
+        o = (v.data_ptr() - flat.data_ptr()) // 4
+        return flat_like[o:o + v.numel()].view(v.shape)
+
     def restore(self, sess=None, checkpoints=None, restore_to_checkpoint_mapping=None):
-        """base_model.py:229-246.  `sess` is accepted for call compatibility and ignored.  Restores every variable present
-        in both the model and the checkpoint(s) (tf_utils.get_checkpoint_restore_saver: variables missing from the
-        checkpoint are reported and skipped), global_step unless several checkpoints are given, and Adam slots."""
+        """base_model.py:229-246 + SAVP's name mapping (savp_model.py:848-855).  `sess` is accepted for call compatibility
+        and ignored.  Restores every variable present in both the model and the checkpoint(s) -- this package's .npz files or
+        TensorFlow checkpoints of the reference (tf_checkpoint.py) -- reports the rest as get_checkpoint_restore_saver does
+        (tf_utils.py:543-557), global_step unless several checkpoints are given, and the Adam slots."""
+        import math
         import os
         import sys
+        from .. import tf_checkpoint as T
         if not checkpoints:
             return
         if not isinstance(checkpoints, (list, tuple)):
             checkpoints = [checkpoints]
         skip_global_step = len(checkpoints) > 1
+        mapping = restore_to_checkpoint_mapping or self.restore_to_checkpoint_mapping
         for ck in checkpoints:
             path = self.latest_checkpoint(ck)
-            if path is None or not os.path.exists(path):
+            if path is None or not (os.path.exists(path) or T.is_tf_checkpoint(path)):
                 raise FileNotFoundError('no checkpoint found at %s' % ck)
-            data = np.load(path)
-            names = {k[4:]: k for k in data.files if k.startswith('var/')}
-            if restore_to_checkpoint_mapping is not None:
-                names = {k: names[restore_to_checkpoint_mapping(k, names)] for k in self.params
-                         if restore_to_checkpoint_mapping(k, names) in names}
-            vals = {k: data[f] for k, f in names.items() if k in self.params}
-            missing = [k for k in self.params if k not in vals]
+            slots, adam_t = None, None
+            if T.is_tf_checkpoint(path):
+                vals, missing, unused, extra = T.load_variables(path, list(self.params), mapping)
+                gstep, slots = extra['global_step'], extra['slots']
+                if extra['beta1_power'] and 0 < extra['beta1_power'] < 1 and 0 < self.hparams.beta1 < 1:
+                    t = int(round(math.log(extra['beta1_power']) / math.log(self.hparams.beta1))) - 1    # beta1_power = beta1^(t+1)
+                    adam_t = (t, t)
+            else:
+                data = np.load(path)
+                names = set(k[4:] for k in data.files if k.startswith('var/'))
+                vals = OrderedDict((k, data['var/' + mapping(k, names)]) for k in self.params if mapping(k, names) in names)
+                missing = [k for k in self.params if k not in vals]
+                unused = sorted(names - set(mapping(k, names) for k in vals))
+                gstep = int(data['global_step']) if 'global_step' in data.files else None
+                if self.mode == 'train' and 'adam/t' in data.files:
+                    for nm in ('g_m', 'g_v', 'd_m', 'd_v'):
+                        buf = getattr(self, nm)
+                        if ('adam/' + nm) in data.files and data['adam/' + nm].shape == tuple(buf.shape):
+                            buf.copy_(torch.from_numpy(data['adam/' + nm]).to(self.device))
+                    adam_t = tuple(int(v) for v in data['adam/t'])
             if missing:
-                sys.stderr.write('restore: %d variables are not in %s (kept): %s ...\n' % (len(missing), path, missing[:3]))
+                sys.stderr.write('global variables that were not restored because they are not in the checkpoint:\n' +
+                                 ''.join('     %s\n' % k for k in sorted(missing)))
+            if unused:
+                sys.stderr.write('checkpoint variables that were not used for restoring because they are not in the graph:\n' +
+                                 ''.join('     %s\n' % k for k in unused))
             self.set_params(vals)
-            if not skip_global_step and 'global_step' in data.files:
-                self.global_step = int(data['global_step'])
-            if self.mode == 'train' and 'adam/t' in data.files:
-                for nm in ('g_m', 'g_v', 'd_m', 'd_v'):
-                    buf = getattr(self, nm)
-                    if ('adam/' + nm) in data.files and data['adam/' + nm].shape == tuple(buf.shape):
-                        buf.copy_(torch.from_numpy(data['adam/' + nm]).to(self.device))
-                self.g_adam_t, self.d_adam_t = [int(v) for v in data['adam/t']]
+            if not skip_global_step and gstep is not None:
+                self.global_step = gstep
+            if self.mode == 'train' and slots is not None:
+                for slot, gbuf, dbuf in (('m', self.g_m, self.d_m), ('v', self.g_v, self.d_v)):
+                    for name, arr in slots[slot].items():
+                        flat, like = (self.g_flat, gbuf) if name.startswith('generator/') else (self.d_flat, dbuf)
+                        if not name.endswith('/u'):
+                            self._view_of(like, flat, name).copy_(torch.from_numpy(np.ascontiguousarray(arr)).to(self.device))
+            if self.mode == 'train' and adam_t is not None:
+                self.g_adam_t, self.d_adam_t = adam_t
 
     def _flat_range(self, flat, names):
         """[lo, hi) element range of `flat` covered by the variables `names` (views of the flat buffer)."""
