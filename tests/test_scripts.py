@@ -120,3 +120,15 @@ def test_train_three_steps_checkpoint_resume_and_generate(tmp_path):
     for k, v in model2.get_params().items():
         assert np.array_equal(m3.get_params()[k], v), k
     assert float(m3._view_of(m3.g_m, m3.g_flat, k0).mean()) == 0.25
+    # best-of-N evaluation (base_model.py:132-227): 3 stochastic samples, psnr / mse / ssim min / avg / max per video
+    m4 = get_model_class('savp')(mode='test', hparams_dict=model2.hparams.values())
+    from video_prediction_b200 import datasets
+    batch = datasets.get_dataset_class('synthetic')('none', mode='test', seed=5, hparams='sequence_length=6').make_batch(2)
+    m4.build_graph(batch)
+    m4.restore(None, out)
+    eo, em = m4.eval_outputs_and_metrics(batch, num_samples=3)
+    assert tuple(em['eval_psnr/max'].shape) == (2, 4) and tuple(eo['eval_gen_images_ssim/max'].shape) == (2, 5, 64, 64, 3)
+    for name in ('psnr', 'ssim'):
+        lo, av, hi = (em['eval_%s/%s' % (name, k)].mean(dim=1) for k in ('min', 'avg', 'max'))
+        assert bool((lo <= av + 1e-6).all()) and bool((av <= hi + 1e-6).all()) and bool((hi > lo).any())
+    assert bool((em['eval_mse/min'] >= 0).all()) and float(em['eval_ssim/max'].max()) <= 1.0

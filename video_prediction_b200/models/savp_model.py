@@ -1093,6 +1093,54 @@ class SAVPVideoPredictionModel(TrainMixin, VideoPredictionModel):
         self.generator_forward()
         return self.outputs['gen_images'].detach().cpu().numpy()
 
+    def eval_outputs_and_metrics(self, inputs, num_samples=None, noise_seed=0):
+        """base_model.py:132-227 (eval_outputs_and_metrics_fn) for mode 'test' / 'val': `num_samples` stochastic predictions of
+        the batch (a fresh prior draw each), per-(sample, future frame) psnr / mse / ssim, and for every metric the worst /
+        average / best prediction per video, chosen by the metric's mean over the future frames (sort_criterion, :168-169).
+        Deterministic models (nz = 0) are evaluated once.  Returns (eval_outputs, eval_metrics) with the reference's keys,
+        batch-major ([B, T-1, ...] images, [B, future] metrics); lpips / eval_diversity need downloaded weights and are absent."""
+        from .. import metrics as M
+        hp = self.hparams
+        num_samples = 1 if self.deterministic else (num_samples or self.eval_num_samples)
+        future = self.T - hp.context_frames
+        images = torch.as_tensor(inputs['images']).to(self.device, torch.float32)[:, :self.T]
+        target = images[:, -future:]
+        acc = {}
+        base_step = self.global_step
+        for si in range(num_samples):
+            self.global_step = noise_seed * 1000003 + si          # the host RNG seed of the prior draw mixes in global_step
+            self.set_inputs(inputs)
+            self.generator_forward()
+            gen = self.outputs['gen_images'].clone()              # [B, T-1, H, W, C]
+            pred = gen[:, -future:]
+            for name, fn in M.METRIC_FNS:
+                m = fn(target, pred)                              # [B, future]
+                if si == 0:
+                    acc[name] = dict(min=m.clone(), max=m.clone(), sum=m.clone(), gmin=gen.clone(), gmax=gen.clone(), gsum=gen.clone())
+                    continue
+                a = acc[name]
+                crit, cmin, cmax = m.mean(dim=1), a['min'].mean(dim=1), a['max'].mean(dim=1)
+                lo, hi = crit < cmin, crit > cmax
+                a['min'][lo], a['gmin'][lo] = m[lo], gen[lo]
+                a['max'][hi], a['gmax'][hi] = m[hi], gen[hi]
+                a['sum'] += m
+                a['gsum'] += gen
+        self.global_step = base_step
+        eval_outputs, eval_metrics = OrderedDict(eval_images=images), OrderedDict()
+        for name, _ in M.METRIC_FNS:
+            a = acc[name]
+            if self.deterministic:
+                eval_outputs['eval_gen_images'] = a['gmax']
+            else:
+                eval_outputs['eval_gen_images_%s/min' % name] = a['gmin']
+                eval_outputs['eval_gen_images_%s/avg' % name] = a['gsum'] / float(num_samples)
+                eval_outputs['eval_gen_images_%s/max' % name] = a['gmax']
+            eval_metrics['eval_%s/min' % name] = a['min']
+            eval_metrics['eval_%s/avg' % name] = a['sum'] / float(num_samples)
+            eval_metrics['eval_%s/max' % name] = a['max']
+        self.eval_outputs, self.eval_metrics = eval_outputs, eval_metrics
+        return eval_outputs, eval_metrics
+
     def outputs_time_major(self, key):
         """One generator output straight from the device buffers, time-major as generator_fn returns it (no copy)."""
         B, C, Bf = self.B, self.C, self.Bf
