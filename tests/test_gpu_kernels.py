@@ -382,3 +382,56 @@ def test_flow_apply_fwd_bwd(L):
     gi, gf = torch.autograd.grad(loss, (imd, fd))
     close(dimg[..., :3], gi, 2e-5, 'flow dimage')
     close(dfl, gf, 2e-5, 'dflows')
+
+
+# ------------------------------------------------------------------ slab-mapped plane kernels (csrc/planes.cu)
+@pytest.mark.parametrize('N,P,C', [(3, 64, 32), (2, 256, 64), (32, 1024, 32), (4, 4096, 32), (2, 16, 256), (5, 1024, 128)])
+def test_slab_instance_norm_fwd_bwd(L, N, P, C):
+    """Shapes of the model's instance norms (32-channel 64x64 / 32x32 planes ... 256-channel 4x4) on the cluster / DSMEM kernels:
+    an input with a large mean (5 sigma) checks the shifted one-pass variance; two gradient sources, strided destination."""
+    x, g, b, dy = rnd(N, P, C) * 0.7 + 3.5, rnd(C, seed=1) * 0.3 + 1, rnd(C, seed=2), rnd(N, P, C, seed=3)
+    ys = C + 8
+    y = torch.zeros(N, P, ys, device='cuda')
+    st = torch.zeros(N, C, 2, device='cuda')
+    L.inorm_act(x.data_ptr(), C, y.data_ptr() + 16, ys, N, P, C, g, b, L.ACT_RELU, 0.0, st)
+    xr = x.double().requires_grad_(True)
+    gr, br = g.double().requires_grad_(True), b.double().requires_grad_(True)
+    ref = torch.relu(O.instance_norm(xr, gr, br))
+    close(y[..., 4:4 + C], ref, 1e-5, 'slab inorm fwd')
+    assert float(y[..., :4].abs().max()) == 0 and float(y[..., 4 + C:].abs().max()) == 0       # neighbours of the slice untouched
+    gx, gg, gb = torch.autograd.grad(ref, (xr, gr, br), dy.double())
+    dx, dg, db = torch.zeros_like(x), torch.zeros(C, device='cuda'), torch.zeros(C, device='cuda')
+    half = dy * 0.5
+    L.inorm_act_bwd(x.data_ptr(), C, [(half.data_ptr(), C), (half.data_ptr(), C)], dx.data_ptr(), C, N, P, C, g, b, st, L.ACT_RELU, 0.0,
+                    dg, db)
+    close(dx, gx, 3e-5, 'slab inorm dx')
+    close(dg, gg, 3e-5, 'slab inorm dgamma')
+    close(db, gb, 3e-5, 'slab inorm dbeta')
+
+
+@pytest.mark.parametrize('N,P,Fl', [(32, 1024, 32), (6, 256, 64), (5, 64, 128), (2, 1024, 64), (3, 16, 256)])
+def test_slab_lstm_gates_fwd_bwd(L, N, P, Fl):
+    pre, c0 = rnd(N, P, 4 * Fl) + 0.8, rnd(N, P, Fl, seed=1)
+    g1, b1, g2, b2 = rnd(4 * Fl, seed=2) * 0.3 + 1, rnd(4 * Fl, seed=3) * 0.1, rnd(Fl, seed=4) * 0.3 + 1, rnd(Fl, seed=5) * 0.1
+    hs = Fl + 8
+    c1, h, h2 = torch.zeros(N, P, Fl, device='cuda'), torch.zeros(N, P, hs, device='cuda'), torch.zeros(N, P, Fl, device='cuda')
+    s1, s2 = torch.zeros(N, 4 * Fl, 2, device='cuda'), torch.zeros(N, Fl, 2, device='cuda')
+    L.lstm_gates_fwd(pre, N, P, Fl, c0, g1, b1, g2, b2, c1, [(h.data_ptr() + 16, hs), (h2.data_ptr(), Fl)], s1, s2)
+    prd, c0d = pre.double().requires_grad_(True), c0.double().requires_grad_(True)
+    ps = [t.double().requires_grad_(True) for t in (g1, b1, g2, b2)]
+    cat = O.instance_norm(prd, ps[0], ps[1])
+    i, j, f, o = torch.split(cat, Fl, dim=-1)
+    nc = O.instance_norm(c0d * torch.sigmoid(f + 1.0) + torch.sigmoid(i) * torch.tanh(j), ps[2], ps[3])
+    nh = torch.tanh(nc) * torch.sigmoid(o)
+    close(c1, nc, 1e-5, 'slab gates c')
+    close(h[..., 4:4 + Fl], nh, 1e-5, 'slab gates h')
+    close(h2, nh, 1e-5, 'slab gates h (2nd destination)')
+    dh, dc = rnd(N, P, Fl, seed=6), rnd(N, P, Fl, seed=7)
+    grads = torch.autograd.grad((nh * dh.double()).sum() + (nc * dc.double()).sum(), [prd, c0d] + ps)
+    dpre, dc0 = torch.zeros_like(pre), torch.zeros_like(c0)
+    dgs = [torch.zeros_like(t) for t in (g1, b1, g2, b2)]
+    L.lstm_gates_bwd(pre, N, P, Fl, c0, g1, b1, g2, b2, s1, s2, [(dh.data_ptr(), Fl)], dc, dpre, dc0, dgs[0], dgs[1], dgs[2], dgs[3])
+    close(dpre, grads[0], 5e-5, 'slab gates dpre')
+    close(dc0, grads[1], 5e-5, 'slab gates dc_prev')
+    for a, b_, nm in zip(dgs, grads[2:], ('dg1', 'db1', 'dg2', 'db2')):
+        close(a, b_, 5e-5, 'slab gates ' + nm)

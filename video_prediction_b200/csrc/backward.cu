@@ -753,6 +753,11 @@ extern "C" int vp_inorm_act_bwd(const float* x, int x_cstride, const float* cons
                                 const float* stats, int act, float alpha, float* dgamma, float* dbeta, vp_stream_t stream) {
   if (!x || !dy || !dx || !stats || !gamma || !beta || !dgamma || !dbeta) return set_error("vp_inorm_act_bwd: null pointer");
   if (c % 4 || num_dy < 1 || num_dy > 4) return set_error("vp_inorm_act_bwd: bad channel count / source count");
+  {
+    const int rc = slab_inorm_act_bwd(x, x_cstride, dy, dy_cstride, num_dy, dx, dx_cstride, n, positions, c, gamma, beta, stats, act, alpha,
+                                      dgamma, dbeta, stream);
+    if (rc <= 0) return rc;
+  }
   dim3 grid(c / 4, n);
   const int staged = positions <= 4096 ? 1 : 0;
   static bool attr_set = false;
@@ -773,6 +778,11 @@ extern "C" int vp_lstm_gates_bwd(const float* pre, int n, int positions, int fil
                                  float* dgamma2, float* dbeta2, vp_stream_t stream) {
   if (positions > 1024) return set_error("vp_lstm_gates_bwd: plane too large");
   if (filters % 4 || num_dh < 1 || num_dh > 4) return set_error("vp_lstm_gates_bwd: bad filters / source count");
+  {
+    const int rc = slab_gates_bwd(pre, n, positions, filters, c_prev, gamma1, beta1, gamma2, beta2, stats1, stats2, forget_bias, dh, dh_cstride,
+                                  num_dh, dc_next, dpre, dc_prev, dgamma1, dbeta1, dgamma2, dbeta2, stream);
+    if (rc <= 0) return rc;
+  }
   const size_t smem = static_cast<size_t>(positions) * 40 * sizeof(float);
   static bool attr_set = false;
   if (!attr_set) {

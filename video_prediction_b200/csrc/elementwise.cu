@@ -444,6 +444,10 @@ extern "C" int vp_inorm_act(const float* x, int x_cstride, float* y, int y_cstri
                             vp_stream_t stream) {
   if (!x || !y) return set_error("vp_inorm_act: null pointer");
   if (c % 4 || x_cstride % 4 || y_cstride % 4) return set_error("vp_inorm_act: channels/strides must be multiples of 4");
+  {
+    const int rc = slab_inorm_act(x, x_cstride, y, y_cstride, n, positions, c, gamma, beta, eps, act, alpha, stats, stream);
+    if (rc <= 0) return rc;
+  }
   dim3 grid(c / 4, n);
   const int staged = positions <= 4096 ? 1 : 0;
   const size_t smem = staged ? static_cast<size_t>(positions) * 16 : 0;
@@ -464,6 +468,11 @@ extern "C" int vp_lstm_gates_fwd(const float* pre, int n, int positions, int fil
   if (!pre || !c_prev || !c_new || !h_dst) return set_error("vp_lstm_gates_fwd: null pointer");
   if (positions > kGatesMaxP) return set_error("vp_lstm_gates_fwd: plane of %d positions exceeds %d", positions, kGatesMaxP);
   if (filters % 4 || num_h_dst < 1 || num_h_dst > 3) return set_error("vp_lstm_gates_fwd: bad filters / destination count");
+  {
+    const int rc = slab_gates_fwd(pre, n, positions, filters, c_prev, gamma1, beta1, gamma2, beta2, forget_bias, eps, c_new, h_dst, h_cstride,
+                                  num_h_dst, stats1, stats2, stream);
+    if (rc <= 0) return rc;
+  }
   GateDst d;
   d.count = num_h_dst;
   for (int i = 0; i < 3; ++i) { d.ptr[i] = i < num_h_dst ? h_dst[i] : nullptr; d.stride[i] = i < num_h_dst ? h_cstride[i] : 0; }
