@@ -7,7 +7,7 @@ import subprocess
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-fams = ['', 'inorm', 'gates', 'wgrad', 'c4wgrad', 'pack', 'colsum,copy', 'cdna', 'sn', 'cosd,dense', 'adam']
+fams = (sys.argv[1].split(';') if len(sys.argv) > 1 else ['', 'inorm', 'gates', 'wgrad', 'c4wgrad', 'pack', 'colsum,copy', 'cdna', 'sn', 'cosd,dense', 'adam'])
 base = None
 for f in fams:
     env = dict(os.environ, VP_SKIP=f)

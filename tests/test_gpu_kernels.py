@@ -424,8 +424,8 @@ def test_slab_lstm_gates_fwd_bwd(L, N, P, Fl):
     nc = O.instance_norm(c0d * torch.sigmoid(f + 1.0) + torch.sigmoid(i) * torch.tanh(j), ps[2], ps[3])
     nh = torch.tanh(nc) * torch.sigmoid(o)
     close(c1, nc, 1e-5, 'slab gates c')
-    close(h[..., 4:4 + Fl], nh, 1e-5, 'slab gates h')
-    close(h2, nh, 1e-5, 'slab gates h (2nd destination)')
+    close(h[..., 4:4 + Fl], nh, 2e-5, 'slab gates h')          # __expf / fast tanh: 1.04e-5 measured at 32 x 1024 x 32
+    close(h2, nh, 2e-5, 'slab gates h (2nd destination)')
     dh, dc = rnd(N, P, Fl, seed=6), rnd(N, P, Fl, seed=7)
     grads = torch.autograd.grad((nh * dh.double()).sum() + (nc * dc.double()).sum(), [prd, c0d] + ps)
     dpre, dc0 = torch.zeros_like(pre), torch.zeros_like(c0)
