@@ -1,5 +1,7 @@
 // Discriminator-side helpers: spectral normalisation (ops.py:1020-1049, one power iteration,
 // differentiable through the iteration) and per-sample clip gather/scatter (savp_model.py:97-102).
+#include <algorithm>
+
 #include "common.h"
 #include "ptx.cuh"
 
@@ -246,7 +248,7 @@ __global__ void __launch_bounds__(256) conv3d_c4_fwd_kernel(const float4* __rest
 
 // gw[(t*CI + ci)*32 + co] += sum_v x[v + tap_t][ci] * dy[v][co]
 // blockIdx.y selects the temporal tap dz (9 of the 27 taps -> 27 accumulators per lane, high occupancy); lane = output
-// channel; a warp walks a chunk of consecutive voxels, two at a time so that 18 independent neighbour loads are in flight.
+// channel; a warp walks one contiguous chunk of voxels (9 broadcast neighbour loads + 1 dy load + 27 FMAs per voxel).
 __global__ void __launch_bounds__(256, 3) conv3d_c4_wgrad_kernel(const float4* __restrict__ x, const float* __restrict__ dy,
                                                                  float* __restrict__ gw, int N, int D, int H, int W, int CI,
                                                                  int chunk) {
@@ -254,8 +256,7 @@ __global__ void __launch_bounds__(256, 3) conv3d_c4_wgrad_kernel(const float4* _
   const int dz = static_cast<int>(blockIdx.y) - 1;
   const long long warp_id = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
   const long long total = static_cast<long long>(N) * D * H * W;
-  const long long v0 = warp_id * chunk, v1 = min(total, v0 + chunk);
-  if (v0 >= v1) return;
+  const long long v0 = min(total, warp_id * chunk), v1 = min(total, v0 + chunk);      // (empty ranges still take part in the block reduction)
   float acc[27];
 #pragma unroll
   for (int i = 0; i < 27; ++i) acc[i] = 0.f;
@@ -284,11 +285,21 @@ __global__ void __launch_bounds__(256, 3) conv3d_c4_wgrad_kernel(const float4* _
     }
     if (++xw == W) { xw = 0; if (++yh == H) { yh = 0; if (++zd == D) zd = 0; } }
   }
+  // the 8 warps of the block are summed in shared memory first: 81 x 32 output addresses receive one atomic per BLOCK instead
+  // of one per warp (the first version issued 80 M same-address atomics per launch, half of its run time)
+  __shared__ float red[8][27][32];
+  const int warp = threadIdx.x >> 5;
 #pragma unroll
-  for (int t = 0; t < 9; ++t)
+  for (int i = 0; i < 27; ++i) red[warp][i][lane] = acc[i];
+  __syncthreads();
+  for (int i = threadIdx.x; i < 27 * 32; i += blockDim.x) {
+    const int t3 = i >> 5, co = i & 31;
+    float sum = 0.f;
 #pragma unroll
-    for (int ci = 0; ci < 3; ++ci)
-      if (ci < CI) atomicAdd(gw + (((dz + 1) * 9 + t) * CI + ci) * 32 + lane, acc[t * 3 + ci]);
+    for (int w = 0; w < 8; ++w) sum += red[w][t3][co];
+    const int t = t3 / 3, ci = t3 % 3;
+    if (ci < CI) atomicAdd(gw + (((dz + 1) * 9 + t) * CI + ci) * 32 + co, sum);
+  }
 }
 
 }  // namespace vp
@@ -306,7 +317,9 @@ extern "C" int vp_conv3d_c4_wgrad(const float* x, const float* dy, float* gw, in
                                   vp_stream_t stream) {
   if (ci < 1 || ci > 3) return set_error("vp_conv3d_c4_wgrad: 1..3 input channels");
   const long long total = static_cast<long long>(n) * d * h * wd;
-  const int chunk = 128;
+  // ~3 resident blocks per SM per temporal tap: each warp walks one contiguous chunk of voxels
+  const long long target_warps = 148LL * 3 * 8;
+  const int chunk = static_cast<int>(std::max<long long>(64, (total + target_warps - 1) / target_warps));
   const long long warps = (total + chunk - 1) / chunk;
   dim3 grid(static_cast<unsigned>((warps + 7) / 8), 3);
   conv3d_c4_wgrad_kernel<<<grid, 256, 0, as_stream(stream)>>>(
