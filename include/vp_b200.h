@@ -86,16 +86,6 @@ int vp_conv_igemm_actgrad(const vp_tensor* in, const vp_conv_geom* g, const floa
  * does not read.  conv(x, W) + conv(lo, W) + conv(x, W_residual) is the fp32-exact ("3xTF32") debug mode. */
 int vp_tf32_residual(const float* x, float* lo, long long n, vp_stream_t stream);
 
-/* Halo-resident variant of vp_conv_igemm for 2-D stride-1 convolutions (the ConvLSTM gate convolutions,
- * rnn_ops.py:121, and their input gradients).  `in` is a zero-padded FLATTENED plane stack: dims (n, 1, Hp, P) with
- * the valid valid_h x valid_w region in the top-left corner of each plane and zeros elsewhere; the gaps Hp - valid_h
- * and P - valid_w must be >= the filter reach.  `out` is a dense (n, 1, valid_h, valid_w) view.  One halo tile per
- * 32-channel chunk stays resident in shared memory and every filter tap is a shifted UMMA descriptor on it.
- * desc_mode: 0 = descriptor base_offset 0 (swizzle keyed on the absolute address), 1 = base_offset from the address. */
-int vp_conv_flat(const vp_tensor* in, int valid_h, int valid_w, const vp_conv_geom* g, const float* wpacked, int n_pad,
-                 int kc, const vp_tensor* out, const float* bias, int act, float alpha, int split_k, int accumulate,
-                 int desc_mode, vp_stream_t stream);
-
 /* Weight gradient of the same convolution: dwpacked[tap][co][ci] += sum_o  dy.. * x..
  * (layout VP_WLAYOUT_FWD: rows = channels of dy (n_pad rows), cols = kc*32 channels of x).
  * Always accumulates atomically: caller zero-fills before the first call of a step. */
@@ -264,11 +254,20 @@ int vp_spectral_norm_bwd(const float* w, const float* u, const float* g_wbar, in
 int vp_conv3d_c4_fwd(const float* x, const float* w, const float* inv_scale, const float* bias, float* out, int n, int d,
                      int h, int wd, int ci, float lrelu_alpha, vp_stream_t stream);
 int vp_conv3d_c4_wgrad(const float* x, const float* dy, float* gw, int n, int d, int h, int wd, int ci, vp_stream_t stream);
+/* The same weight gradient on the tensor cores (TF32 operands, fp32 accumulate): halo rows of float4 voxels are the
+ * un-swizzled MN-major UMMA operand as they are, three MMAs (one per dx) per 8 voxels.  Needs wd % 64 == 0. */
+int vp_conv3d_c4_wgrad_tc(const float* x, const float* dy, float* gw, int n, int d, int h, int wd, int ci, vp_stream_t stream);
 /* savp_model.py:97-102: clip[b][j][p] = video[t_start[b]+j][batch_offset+b][p]; pixels = H*W (4 floats each) */
 int vp_gather_clip(const float* video, const int32_t* t_start, float* clip, int clips, int clip_len, long long pixels,
                    int video_batch, int batch_offset, vp_stream_t stream);
 int vp_scatter_clip(const float* dclip, const int32_t* t_start, float* dvideo, int clips, int clip_len, long long pixels,
                     int video_batch, int batch_offset, vp_stream_t stream);
+
+/* Debug: one tcgen05.mma kind::tf32 (M = 128, N = n, K = 8) on caller-supplied shared-memory images and descriptor fields
+ * (start offset, LBO, SBO in bytes; layout type 0 none, 1 = 128B/32B-atom, 2 = 128B; major 0 = K, 1 = MN).  out = [128][n]. */
+int vp_debug_umma_probe(const void* a_img, int a_bytes, const void* b_img, int b_bytes, unsigned a_start, unsigned a_lbo,
+                        unsigned a_sbo, unsigned a_layout, int a_mn_major, unsigned b_start, unsigned b_lbo, unsigned b_sbo,
+                        unsigned b_layout, int b_mn_major, int n, float* out, vp_stream_t stream);
 
 #ifdef __cplusplus
 }

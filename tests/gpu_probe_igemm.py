@@ -11,8 +11,7 @@ sys.path.insert(0, ROOT)
 
 CASES = ['conv3x3', 'conv5x5_lstm0', 'conv5x5_lstm2', 'pooled6x6', 'enc4x4s2', 'upsample', 'conv3d_k3',
          'conv3d_k4s122', 'conv3d_k4s222', 'slice_bias_act', 'splitk', 'dgrad_s1', 'dgrad_s2', 'dgrad_up',
-         'wgrad_s1', 'wgrad_pooled', 'wgrad_up', 'wgrad_3d', 'smallN',
-         'flat_h0_m0', 'flat_h0_m1', 'flat_h2_m0', 'flat_h2_m1', 'flat_h1_split', 'flat_dgrad']
+         'wgrad_s1', 'wgrad_pooled', 'wgrad_up', 'wgrad_3d', 'smallN']
 
 
 def run_case(name):
@@ -133,46 +132,6 @@ def run_case(name):
         x, w = rnd(2, 64, 64, 56), rnd(3, 3, 53, 7) * 0.1
         y = run_fwd(x, 53, w, (1, 3, 3), (1, 1, 1), (0, 1, 1), None, out=torch.zeros(2, 64, 64, 8, device=dev))
         return report(y[..., :7], conv_ref(tf32(x)[..., :53], tf32(w), (1, 1), (1, 1), out_hw=(64, 64)))
-
-    if name.startswith('flat_'):
-        import time
-        cfg = {'flat_h0': (8, 32, 72, 128), 'flat_h2': (6, 8, 264, 512), 'flat_h1': (4, 16, 136, 256), 'flat_dg': (4, 16, 256, 136)}[name[:7]]
-        B, H, Cin, Cout = cfg
-        mode = 1 if name.endswith('m1') else 0
-        split = 3 if name.endswith('split') else 1
-        transposed = name == 'flat_dgrad'
-        Hp, P = H + 2, H + 2
-        xs = rnd(B, H, H, Cin)
-        xp = torch.zeros(B, Hp, P, Cin, device=dev)
-        xp[:, :H, :H] = xs
-        w = rnd(5, 5, Cin, Cout) * 0.03
-        if not transposed:
-            wp, n_pad, kc = L.pack_weights(w.contiguous(), (1, 5, 5), Cin, Cout, L.WKIND_PLAIN, L.WLAYOUT_FWD)
-            ref = conv_ref(tf32(xs), tf32(w), (1, 1), (2, 2), out_hw=(H, H))
-            co = Cout
-        else:   # input-gradient of a 5x5 SAME conv with Cout_fwd = Cin (dy has Cin channels here), result has Cout channels
-            wf = rnd(5, 5, Cout, Cin) * 0.03          # forward kernel [5,5,ci=Cout,co=Cin]
-            wp, n_pad, kc = L.pack_weights(wf.contiguous(), (1, 5, 5), Cout, Cin, L.WKIND_PLAIN, L.WLAYOUT_DGRAD)
-            xin = torch.zeros(B, H, H, Cout, device=dev, dtype=torch.float64, requires_grad=True)
-            y = O.conv2d_tf(xin, tf32(wf).double(), padding='SAME')
-            (ref,) = torch.autograd.grad(y, xin, tf32(xs).double())
-            co = Cout
-        out = torch.zeros(B, H, H, co, device=dev)
-        g = L.geom((1, 5, 5), (1, 1, 1), (0, 2, 2), transposed)
-        L.conv_flat(L.tensor_view(xp, Cin), H, H, g, wp, n_pad, kc, L.tensor_view(out, co), None, L.ACT_NONE, 0.0, split, 0, mode)
-        torch.cuda.synchronize()
-        r = report(out, ref)
-        if r < 2e-3:
-            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            xv, ov = L.tensor_view(xp, Cin), L.tensor_view(out, co)
-            ev0.record()
-            for _ in range(20):
-                L.conv_flat(xv, H, H, g, wp, n_pad, kc, ov, None, L.ACT_NONE, 0.0, split, 0, mode)
-            ev1.record()
-            torch.cuda.synchronize()
-            ms = ev0.elapsed_time(ev1) / 20
-            print('INFO flat %s: %.1f us, %.0f TFLOP/s (algorithmic, warm L2)' % (name, ms * 1e3, 2.0 * B * H * H * co * 25 * Cin / ms / 1e9))
-        return r
 
     # ---------------- dgrad: dx = engine(dy, W packed DGRAD, geometry transposed-flag flipped)
     def run_dgrad(dy, w_ref, k, s, p, x_shape, c_int, kind=L.WKIND_PLAIN, fwd_transposed=False):

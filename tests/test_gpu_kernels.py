@@ -322,17 +322,29 @@ def test_conv3d_c4_cuda_core_first_discriminator_layer(L):
     close(g.view(3, 3, 3, C, 32), gw, 2e-5, 'conv3d_c4 wgrad')
 
 
-@pytest.mark.parametrize('B,H,Cin,Cout,split', [(5, 32, 72, 128, 1), (6, 8, 264, 512, 3), (4, 16, 136, 256, 1)])
-def test_halo_resident_flat_conv_matches_box_engine(L, B, H, Cin, Cout, split):
-    """vp_conv_flat (shifted UMMA descriptors on a resident halo tile) against the fp64 reference."""
-    xs, w = rnd(B, H, H, Cin), rnd(5, 5, Cin, Cout, seed=1, scale=0.03)
-    xp = torch.zeros(B, H + 2, H + 2, Cin, device='cuda')
-    xp[:, :H, :H] = xs
-    wp, n_pad, kc = L.pack_weights(w, (1, 5, 5), Cin, Cout, L.WKIND_PLAIN, L.WLAYOUT_FWD)
-    out = torch.zeros(B, H, H, Cout, device='cuda')
-    L.conv_flat(L.tensor_view(xp, Cin), H, H, L.geom((1, 5, 5), (1, 1, 1), (0, 2, 2), False), wp, n_pad, kc, L.tensor_view(out, Cout),
-                None, L.ACT_NONE, 0.0, split, 0, 0)
-    close(out, O.conv2d_tf(tf32(xs).double(), tf32(w).double(), padding='SAME'), 2e-3, 'flat conv')
+@pytest.mark.parametrize('N,D,H,W,C', [(2, 3, 5, 64, 3), (1, 2, 3, 128, 1), (3, 10, 64, 64, 3)])
+def test_conv3d_c4_wgrad_tensor_cores(L, N, D, H, W, C):
+    """vp_conv3d_c4_wgrad_tc (float4 voxel rows as the un-swizzled MN-major UMMA operand, one MMA per dx) against the fp64
+    weight gradient of the operands the tensor core reads (fp32 truncated to TF32), and against the CUDA-core kernel."""
+    def trunc(t):
+        return (t.contiguous().view(torch.int32) & ~0x1FFF).view(torch.float32)
+    x = torch.zeros(N, D, H, W, 4, device='cuda')
+    x[..., :C] = torch.rand(N, D, H, W, C, device='cuda') - 0.3
+    x[..., C:] = 7.0                                           # padding channels must not leak into real taps
+    dy = rnd(N, D, H, W, 32, seed=3)
+    wz = torch.zeros(3, 3, 3, C, 32, device='cuda', dtype=torch.float64, requires_grad=True)
+    xp = F.pad(trunc(x)[..., :C].double(), (0, 0, 1, 1, 1, 1, 1, 1))
+    pre = O.conv3d_tf_valid(xp, wz, (1, 1, 1), None)
+    (gw,) = torch.autograd.grad(pre, wz, trunc(dy).double())
+    g = torch.full((27 * C * 32,), 0.5, device='cuda')         # accumulates
+    L.check(L.lib().vp_conv3d_c4_wgrad_tc(L.ptr(x), L.ptr(dy), L.ptr(g), N, D, H, W, C, L.stream_ptr()))
+    torch.cuda.synchronize()
+    err = (g.view(3, 3, 3, C, 32).double() - 0.5 - gw).norm() / gw.norm()
+    assert err < 2e-4, 'tensor-core first-layer wgrad: rel L2 %g' % err.item()
+    g2 = torch.zeros(27 * C * 32, device='cuda')
+    L.check(L.lib().vp_conv3d_c4_wgrad(L.ptr(x), L.ptr(dy), L.ptr(g2), N, D, H, W, C, L.stream_ptr()))
+    err2 = (g - 0.5 - g2).norm() / g2.norm()
+    assert err2 < 3e-3, 'tensor cores vs CUDA cores: rel L2 %g' % err2.item()
 
 
 def test_image_warp_fwd_bwd(L):

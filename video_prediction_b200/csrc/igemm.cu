@@ -23,6 +23,7 @@
 
 #include "common.h"
 #include "ptx.cuh"
+#include "tensormap.h"
 
 namespace vp {
 
@@ -990,23 +991,6 @@ __global__ void __launch_bounds__(192, 1) igemm_wgrad_row_kernel(const __grid_co
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn get_encode() {
-  static EncodeTiledFn fn = nullptr;
-  if (!fn) {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
-        q != cudaDriverEntryPointSuccess)
-      return nullptr;
-    fn = reinterpret_cast<EncodeTiledFn>(p);
-  }
-  return fn;
-}
-
 static int floor_pow2(int v) { int p = 1; while (p * 2 <= v) p *= 2; return p; }
 static int ceil_div(int a, int b) { return (a + b - 1) / b; }
 static int pos_mod(int a, int b) { int r = a % b; return r < 0 ? r + b : r; }

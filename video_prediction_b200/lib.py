@@ -205,12 +205,6 @@ def engine_choices():
     return dict(_ENGINE_CHOICE)
 
 
-def conv_flat(x_view, valid_h, valid_w, g, wpacked, n_pad, kc, out_view, bias=None, act=ACT_NONE, alpha=0.0, split_k=1,
-              accumulate=0, desc_mode=0):
-    check(lib().vp_conv_flat(C.byref(x_view), valid_h, valid_w, C.byref(g), ptr(wpacked), n_pad, kc, C.byref(out_view), ptr(bias),
-                             act, C.c_float(alpha), split_k, int(accumulate), desc_mode, stream_ptr()))
-
-
 def conv_wgrad(x_view, dy_view, g, dwpacked, n_pad, kc, split_k=1):
     if 'wgrad' in _SKIP:
         return
@@ -509,6 +503,10 @@ def conv3d_c4_fwd(x, w, inv_scale, bias, out, n, d, h, wd, ci, alpha):
 
 def conv3d_c4_wgrad(x, dy, gw, n, d, h, wd, ci):
     if 'c4wgrad' in _SKIP:
+        return
+    # tensor cores unless the fp32-exact mode is on (the CUDA-core kernel is exact) or the width does not tile by 64
+    if wd % 64 == 0 and not exact_mode() and os.environ.get('VP_D0_WGRAD_CUDA_CORE', '0') != '1':
+        check(lib().vp_conv3d_c4_wgrad_tc(ptr(x), ptr(dy), ptr(gw), n, d, h, wd, ci, stream_ptr()))
         return
     check(lib().vp_conv3d_c4_wgrad(ptr(x), ptr(dy), ptr(gw), n, d, h, wd, ci, stream_ptr()))
 

@@ -106,7 +106,8 @@ class SNLayer(object):
     def fwd(self, x, out):
         # the first layer's FORWARD runs on the tensor-core engine: halo mode loads one activation tile per 9 taps, which
         # the box mode of round 1 could not (1070 us box / 417 us CUDA cores / 250 us halo per 32 clips); its weight
-        # gradient stays on the CUDA-core kernel (4 input channels = 3 % MMA efficiency as a GEMM over pixels)
+        # gradient has its own tensor-core kernel (csrc/d0_wgrad.cu: float4 voxel rows are the MN-major operand as they
+        # lie, ~80 us against 900 us on the CUDA cores), the CUDA-core kernel remains for the fp32-exact mode
         if self.cuda_core and os.environ.get('VP_D0_FWD_CUDA_CORE', '0') == '1':
             P = self.m.params
             n, d, h, w = x.shape[:4]
