@@ -105,6 +105,19 @@ int vp_conv_wgrad(const vp_tensor* x, const vp_tensor* dy, const vp_conv_geom* g
 int vp_pack_weights(const float* w, int kd, int kh, int kw, int ci_ref, int co, int kind, int layout,
                     const int32_t* cmap, int ci_int, const float* inv_scale, float* wpacked, int n_pad, int kc,
                     vp_stream_t stream);
+/* The same for a whole table of tensors in one launch.  `jobs_device` is a DEVICE array; job i owns the 256-thread blocks
+ * [block_begin_i, block_begin_{i+1}) with block_begin_0 = 0 and ceil(taps * n_pad * kc * 32 / 256) blocks per job;
+ * total_blocks = the sum.  Fields as the arguments of vp_pack_weights. */
+typedef struct {
+  const float* w;
+  float* wpacked;
+  const int32_t* cmap;
+  const float* inv_scale;
+  int kd, kh, kw, ci_ref, co, kind, layout, ci_int, n_pad, kc;
+  int block_begin;
+  int reserved;
+} vp_pack_job;
+int vp_pack_weights_batch(const vp_pack_job* jobs_device, int njobs, int total_blocks, vp_stream_t stream);
 /* Adjoint of vp_pack_weights(layout FWD): dw[...] += L^T(dwpacked) (no scale applied). */
 int vp_unpack_wgrad(const float* dwpacked, int kd, int kh, int kw, int ci_ref, int co, int kind,
                     const int32_t* cmap, int ci_int, float* dw, int n_pad, int kc, vp_stream_t stream);
@@ -254,8 +267,12 @@ int vp_spectral_norm_bwd(const float* w, const float* u, const float* g_wbar, in
 int vp_conv3d_c4_fwd(const float* x, const float* w, const float* inv_scale, const float* bias, float* out, int n, int d,
                      int h, int wd, int ci, float lrelu_alpha, vp_stream_t stream);
 int vp_conv3d_c4_wgrad(const float* x, const float* dy, float* gw, int n, int d, int h, int wd, int ci, vp_stream_t stream);
-/* The same weight gradient on the tensor cores (TF32 operands, fp32 accumulate): halo rows of float4 voxels are the
- * un-swizzled MN-major UMMA operand as they are, three MMAs (one per dx) per 8 voxels.  Needs wd % 64 == 0. */
+/* The same layer on the tensor cores (TF32 operands, fp32 accumulate), without repacking x (csrc/d0_layer.cu):
+ *  fwd:   a flat halo tile of float4 voxels is the un-swizzled K-major operand; the next-voxel leading offset (LBO = 16 B)
+ *         turns x[v-1 .. v+2] into the K = 16 operand of one kernel row.  Needs h % 4 == 0 and a tile that fits (64^2, 128^2 do).
+ *  wgrad: rows of float4 voxels are the 32-byte-atom MN-major operand, dy arrives phase-major.  Needs wd % 64 == 0. */
+int vp_conv3d_c4_fwd_tc(const float* x, const float* w, const float* inv_scale, const float* bias, float* out, int n, int d, int h,
+                        int wd, int ci, float lrelu_alpha, vp_stream_t stream);
 int vp_conv3d_c4_wgrad_tc(const float* x, const float* dy, float* gw, int n, int d, int h, int wd, int ci, vp_stream_t stream);
 /* savp_model.py:97-102: clip[b][j][p] = video[t_start[b]+j][batch_offset+b][p]; pixels = H*W (4 floats each) */
 int vp_gather_clip(const float* video, const int32_t* t_start, float* clip, int clips, int clip_len, long long pixels,

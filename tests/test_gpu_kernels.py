@@ -233,7 +233,7 @@ def test_dense_and_small_lstm_fwd_bwd(L):
 
 def test_wide_dense_tiled_kernels(L):
     """The CDNA-kernel dense layer shapes (K >= 1024, J <= 128) take the tiled kernels; dW is called once over all time steps."""
-    for B, K, J in [(32, 2048, 100), (70, 1100, 36)]:
+    for B, K, J in [(32, 2048, 100), (70, 1100, 36), (16, 4096, 1), (5, 1030, 7)]:
         x, w, b, dy = rnd(B, K), rnd(K, J, seed=1, scale=0.05), rnd(J, seed=2), rnd(B, J, seed=3)
         sig = torch.tensor([1.7], device='cuda')
         y = torch.zeros(B, J, device='cuda')
@@ -345,6 +345,50 @@ def test_conv3d_c4_wgrad_tensor_cores(L, N, D, H, W, C):
     L.check(L.lib().vp_conv3d_c4_wgrad(L.ptr(x), L.ptr(dy), L.ptr(g2), N, D, H, W, C, L.stream_ptr()))
     err2 = (g - 0.5 - g2).norm() / g2.norm()
     assert err2 < 3e-3, 'tensor cores vs CUDA cores: rel L2 %g' % err2.item()
+
+
+@pytest.mark.parametrize('N,D,H,W,C', [(2, 3, 16, 64, 3), (1, 2, 8, 128, 1), (3, 4, 64, 64, 3), (1, 2, 12, 20, 2)])
+def test_conv3d_c4_fwd_tensor_cores(L, N, D, H, W, C):
+    """vp_conv3d_c4_fwd_tc (flat halo tile of float4 voxels as the un-swizzled K-major operand, LBO = one voxel) against the
+    fp64 convolution of the operands the tensor core sees (x truncated to TF32, w / sigma rounded to TF32) and the CUDA-core kernel."""
+    def trunc(t):
+        return (t.contiguous().view(torch.int32) & ~0x1FFF).view(torch.float32)
+    x = torch.zeros(N, D, H, W, 4, device='cuda')
+    x[..., :C] = torch.rand(N, D, H, W, C, device='cuda') - 0.3
+    x[..., C:] = 5.0                                           # padding channels must meet zero weights
+    w, b = rnd(3, 3, 3, C, 32, seed=1, scale=0.2), rnd(32, seed=2)
+    sigma = torch.tensor([1.7], device='cuda')
+    out = torch.full((N, D, H, W, 32), -3.0, device='cuda')
+    L.conv3d_c4_fwd_tc(x, w, sigma, b, out, N, D, H, W, C, 0.1)
+    xp = F.pad(trunc(x)[..., :C].double(), (0, 0, 1, 1, 1, 1, 1, 1))
+    ref = O.lrelu(O.conv3d_tf_valid(xp, tf32(w / sigma).double(), (1, 1, 1), b.double()), 0.1)
+    close(out, ref, 2e-5, 'first layer forward on the tensor cores')
+    out2 = torch.zeros_like(out)
+    L.conv3d_c4_fwd(x, w, sigma, b, out2, N, D, H, W, C, 0.1)
+    close(out, out2, 3e-3, 'tensor cores vs CUDA cores')
+
+
+def test_pack_weights_batch_equals_per_tensor_packs(L):
+    """vp_pack_weights_batch (one table-driven launch) writes exactly what the per-tensor launches write."""
+    cases = [((1, 5, 5), 72, 128, L.WKIND_PLAIN), ((1, 3, 3), 40, 32, L.WKIND_POOLED), ((1, 3, 3), 64, 16, L.WKIND_UPSAMPLED),
+             ((3, 3, 3), 3, 32, L.WKIND_PLAIN), ((1, 4, 4), 136, 264, L.WKIND_PLAIN)]
+    entries, refs = [], []
+    for i, (k, ci, co, kind) in enumerate(cases):
+        w = rnd(*k, ci, co, seed=i, scale=0.1)
+        ci_int = ((ci + 3) // 4) * 4 + 4
+        cmap = torch.arange(ci_int, dtype=torch.int32, device='cuda')
+        cmap[ci:] = -1
+        sigma = torch.tensor([1.3 + i], device='cuda') if i % 2 else None
+        for layout in (L.WLAYOUT_FWD, L.WLAYOUT_DGRAD):
+            ref, n_pad, kc = L.pack_weights(w, k, ci, co, kind, layout, ci_int=ci_int, cmap=cmap, inv_scale=sigma)
+            out = torch.full_like(ref, -7.0)
+            entries.append((w, k, ci, co, kind, layout, ci_int, cmap, sigma, out))
+            refs.append(ref)
+    plan = L.PackPlan(entries)
+    plan.run()
+    torch.cuda.synchronize()
+    for e, ref in zip(entries, refs):
+        assert torch.equal(e[-1], ref)
 
 
 def test_image_warp_fwd_bwd(L):

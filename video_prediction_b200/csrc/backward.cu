@@ -427,55 +427,81 @@ __global__ void dense_bwd_dw_kernel(const float* __restrict__ x, int xs, const f
 }
 
 
-// Tiled versions for the wide CDNA-kernel dense layer (K = 8192 flattened lstm_h2 features -> J = 100, B = 2*batch rows):
-// dx: one CTA per 32 k; W tile and dy staged in shared memory (coalesced global reads, W read exactly once).
-// dW: one CTA per 32 k over ALL rows (the time-batched call passes B = (T-1)*NB rows); thread <-> (k, j mod 8).
+// Tiled versions for the wide CDNA-kernel dense layer (K = 8192 flattened lstm_h2 features -> J = 100, B = 2*batch rows),
+// Both keep a 4 x 4 register tile per thread fed by two 16-byte shared loads per reduction step.
+// dx: one CTA per 64 k; W tile (transposed, k contiguous) and dy (transposed, b contiguous) staged in shared memory.
+// dW: one CTA per 32 k over ALL rows (the time-batched call passes B = (T-1)*NB rows), rows staged 32 at a time.
 constexpr int kDenseJMax = 128;
+constexpr int kDxK = 64, kDxPitch = kDxK + 4;
 __global__ void __launch_bounds__(256) dense_bwd_dx_tiled_kernel(const float* __restrict__ dy, int dys, const float* __restrict__ W,
                                                                  const float* __restrict__ inv_scale, float* __restrict__ dx, int dxs,
                                                                  int B, int K, int J, int accumulate) {
-  extern __shared__ float dsm[];
-  float* Ws = dsm;                    // [32][J + 1]
-  float* dys_s = dsm + 32 * (J + 1);  // [B][J]
-  const int k0 = blockIdx.x * 32;
-  for (int i = threadIdx.x; i < 32 * J; i += blockDim.x) {
+  extern __shared__ __align__(16) float dsm[];
+  const int BP = (B + 3) & ~3;
+  float* Wt = dsm;                      // [J][kDxPitch]   Wt[j][kk] = W[k0 + kk][j]
+  float* dyT = dsm + J * kDxPitch;      // [J][BP]         dyT[j][b] = dy[b][j]
+  const int k0 = blockIdx.x * kDxK;
+  for (int i = threadIdx.x; i < kDxK * J; i += blockDim.x) {
     const int kk = i / J, j = i - kk * J;
-    Ws[kk * (J + 1) + j] = (k0 + kk < K) ? W[static_cast<long long>(k0 + kk) * J + j] : 0.f;
+    Wt[j * kDxPitch + kk] = (k0 + kk < K) ? W[static_cast<long long>(k0 + kk) * J + j] : 0.f;
   }
-  for (int i = threadIdx.x; i < B * J; i += blockDim.x) {
+  for (int i = threadIdx.x; i < BP * J; i += blockDim.x) {
     const int b = i / J, j = i - b * J;
-    dys_s[i] = dy[static_cast<long long>(b) * dys + j];
+    dyT[j * BP + b] = b < B ? dy[static_cast<long long>(b) * dys + j] : 0.f;
   }
   __syncthreads();
   const float sc = inv_scale ? 1.f / __ldg(inv_scale) : 1.f;
-  for (int i = threadIdx.x; i < 32 * B; i += blockDim.x) {
-    const int kk = i & 31, b = i >> 5;
-    if (k0 + kk >= K) continue;
-    const float* wr = Ws + kk * (J + 1);
-    const float* dr = dys_s + b * J;
-    float s0 = 0.f, s1 = 0.f;
-    int j = 0;
-    for (; j + 1 < J; j += 2) { s0 += dr[j] * wr[j]; s1 += dr[j + 1] * wr[j + 1]; }
-    if (j < J) s0 += dr[j] * wr[j];
-    const float s = (s0 + s1) * sc;
-    float* o = dx + static_cast<long long>(b) * dxs + k0 + kk;
-    *o = accumulate ? *o + s : s;
+  const int BT = BP >> 2;
+  for (int t = threadIdx.x; t < BT * (kDxK / 4); t += blockDim.x) {
+    const int kt = t % (kDxK / 4), bt = t / (kDxK / 4);
+    float acc[4][4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[r][c] = 0.f;
+#pragma unroll 4
+    for (int j = 0; j < J; ++j) {
+      const float4 dv = *reinterpret_cast<const float4*>(dyT + j * BP + 4 * bt);
+      const float4 wv = *reinterpret_cast<const float4*>(Wt + j * kDxPitch + 4 * kt);
+      const float dr[4] = {dv.x, dv.y, dv.z, dv.w}, wc[4] = {wv.x, wv.y, wv.z, wv.w};
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[r][c] += dr[r] * wc[c];
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int b = 4 * bt + r;
+      if (b >= B) continue;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int k = k0 + 4 * kt + c;
+        if (k >= K) continue;
+        float* o = dx + static_cast<long long>(b) * dxs + k;
+        const float v = acc[r][c] * sc;
+        *o = accumulate ? *o + v : v;
+      }
+    }
   }
 }
 
 __global__ void __launch_bounds__(256) dense_bwd_dw_tiled_kernel(const float* __restrict__ x, int xs, const float* __restrict__ dy,
                                                                  int dys, const float* __restrict__ inv_scale,
                                                                  float* __restrict__ dW, float* __restrict__ db, int B, int K, int J) {
-  __shared__ float xsm[32][33];
-  __shared__ float dsm2[32][kDenseJMax];
+  __shared__ __align__(16) float xsm[32][32];               // [row][k]
+  __shared__ __align__(16) float dsm2[32][kDenseJMax];      // [row][j]
   const int k0 = blockIdx.x * 32;
-  const int kk = threadIdx.x & 31, jg = threadIdx.x >> 5;   // 8 j-groups: j = jg + 8 i
-  float acc[kDenseJMax / 8];
-#pragma unroll
-  for (int i = 0; i < kDenseJMax / 8; ++i) acc[i] = 0.f;
-  float bsum = 0.f;                                          // CTA 0: thread t < J sums dy[:, t]
+  const int J4 = (J + 3) >> 2;
+  const int kt = threadIdx.x & 7, jt = threadIdx.x >> 3;     // tile: k = 4 kt .. +3, j = 4 jt .. +3 (jt < J4 <= 32)
+  const bool active = jt < J4;
   for (int i = threadIdx.x; i < 32 * kDenseJMax; i += blockDim.x) dsm2[i / kDenseJMax][i % kDenseJMax] = 0.f;   // columns >= J stay zero
   __syncthreads();
+  float acc[4][4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) acc[r][c] = 0.f;
+  float bsum = 0.f;                                          // CTA 0: thread t < J sums dy[:, t]
   for (int b0 = 0; b0 < B; b0 += 32) {
     const int nb = min(32, B - b0);
     for (int i = threadIdx.x; i < 32 * 32; i += blockDim.x) {
@@ -487,21 +513,31 @@ __global__ void __launch_bounds__(256) dense_bwd_dw_tiled_kernel(const float* __
       dsm2[bb][j] = bb < nb ? dy[static_cast<long long>(b0 + bb) * dys + j] : 0.f;
     }
     __syncthreads();
-    for (int bb = 0; bb < nb; ++bb) {
-      const float xv = xsm[bb][kk];
+    if (active) {
+#pragma unroll 8
+      for (int bb = 0; bb < 32; ++bb) {                      // rows >= nb are zero
+        const float4 xv = *reinterpret_cast<const float4*>(&xsm[bb][4 * kt]);
+        const float4 dv = *reinterpret_cast<const float4*>(&dsm2[bb][4 * jt]);
+        const float xr[4] = {xv.x, xv.y, xv.z, xv.w}, dc[4] = {dv.x, dv.y, dv.z, dv.w};
 #pragma unroll
-      for (int i = 0; i < kDenseJMax / 8; ++i) acc[i] += xv * dsm2[bb][jg + 8 * i];
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) acc[r][c] += xr[r] * dc[c];
+      }
     }
     if (db && blockIdx.x == 0 && threadIdx.x < J)
       for (int bb = 0; bb < nb; ++bb) bsum += dsm2[bb][threadIdx.x];
     __syncthreads();
   }
   const float sc = inv_scale ? 1.f / __ldg(inv_scale) : 1.f;
-  if (k0 + kk < K) {
+  if (active) {
 #pragma unroll
-    for (int i = 0; i < kDenseJMax / 8; ++i) {
-      const int j = jg + 8 * i;
-      if (j < J) dW[static_cast<long long>(k0 + kk) * J + j] += acc[i] * sc;
+    for (int r = 0; r < 4; ++r) {
+      const int k = k0 + 4 * kt + r;
+      if (k >= K) continue;
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        if (4 * jt + c < J) dW[static_cast<long long>(k) * J + 4 * jt + c] += acc[r][c] * sc;
     }
   }
   if (db && blockIdx.x == 0 && threadIdx.x < J) db[threadIdx.x] += bsum;
@@ -827,10 +863,10 @@ extern "C" int vp_dense_bwd(const float* x, int x_stride, const float* w, const 
                             vp_stream_t stream) {
   const bool wide = k >= 1024 && j <= kDenseJMax;
   if (dx) {
-    const size_t smem = (32 * static_cast<size_t>(j + 1) + static_cast<size_t>(b) * j) * sizeof(float);
+    const size_t smem = (static_cast<size_t>(j) * kDxPitch + static_cast<size_t>((b + 3) & ~3) * j) * sizeof(float);
     if (wide && smem <= 48 * 1024) {
-      dense_bwd_dx_tiled_kernel<<<(k + 31) / 32, 256, smem, as_stream(stream)>>>(dy, dy_stride, w, inv_scale, dx, dx_stride, b, k, j,
-                                                                                 dx_accumulate);
+      dense_bwd_dx_tiled_kernel<<<(k + kDxK - 1) / kDxK, 256, smem, as_stream(stream)>>>(dy, dy_stride, w, inv_scale, dx, dx_stride, b, k,
+                                                                                         j, dx_accumulate);
       if (check_launch("dense_bwd_dx_tiled_kernel")) return -1;
     } else {
       dense_bwd_dx_kernel<<<grid_for(static_cast<long long>(b) * k, 256), 256, 0, as_stream(stream)>>>(dy, dy_stride, w, inv_scale, dx,

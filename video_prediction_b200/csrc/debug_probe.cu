@@ -1,6 +1,6 @@
 // Debug tool: ONE tcgen05.mma (kind::tf32, cta_group::1) on caller-supplied shared-memory images and descriptor fields, with
 // the full accumulator returned.  Used by tests/gpu_probe_umma.py to read off which shared-memory word the tensor core
-// fetches for operand element (row, k) under a given layout type / LBO / SBO -- the layouts of d0_wgrad.cu and of the halo
+// fetches for operand element (row, k) under a given layout type / LBO / SBO -- the layouts of d0_layer.cu and of the halo
 // engine were pinned this way, not from documentation.
 #include <cstdint>
 

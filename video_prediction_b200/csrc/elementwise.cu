@@ -284,38 +284,66 @@ __global__ void __launch_bounds__(256) dense_fwd_kernel(const float* __restrict_
 
 
 // Tiled forward for the wide CDNA-kernel dense layer (K = 8192 -> J = 100, B <= 64 rows): one CTA per 64 k, W tile and
-// the x slab staged in shared memory, partial [B, J] products reduced into the zero-filled y with atomics.
+// the transposed x slab staged in shared memory; every thread owns a 4 (rows) x 4 (outputs) register tile fed by two
+// 16-byte shared loads per k; partial [B, J] products are reduced into the zero-filled y with atomics.
 __global__ void __launch_bounds__(256) dense_fwd_tiled_kernel(const float* __restrict__ x, int xs, const float* __restrict__ W,
                                                               const float* __restrict__ bias, const float* __restrict__ inv_scale,
                                                               float* __restrict__ y, int ys, int B, int K, int J) {
-  extern __shared__ float fsm[];
-  float* Ws = fsm;              // [64][J]
-  float* xT = fsm + 64 * J;     // [64][B + 1]  (k-major so that lanes = consecutive rows b)
+  extern __shared__ __align__(16) float fsm[];
+  const int BP = (B + 3) & ~3, JP = (J + 3) & ~3;
+  float* Ws = fsm;              // [64][JP]
+  float* xT = fsm + 64 * JP;    // [64][BP]  (k-major: a thread's four rows are one float4)
   const int k0 = blockIdx.x * 64;
-  for (int i = threadIdx.x; i < 64 * J; i += blockDim.x) {
-    const int kk = i / J;
-    Ws[i] = (k0 + kk < K) ? W[static_cast<long long>(k0) * J + i] : 0.f;
+  const int J4 = JP >> 2;
+  if (J == JP && (reinterpret_cast<uintptr_t>(W) & 15) == 0) {
+    for (int i = threadIdx.x; i < 64 * J4; i += blockDim.x) {
+      const int kk = i / J4;
+      reinterpret_cast<float4*>(Ws)[i] = (k0 + kk < K) ? reinterpret_cast<const float4*>(W + static_cast<long long>(k0) * J)[i]
+                                                       : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  } else {
+    for (int i = threadIdx.x; i < 64 * JP; i += blockDim.x) {
+      const int kk = i / JP, j = i - kk * JP;
+      Ws[i] = (j < J && k0 + kk < K) ? W[static_cast<long long>(k0 + kk) * J + j] : 0.f;
+    }
   }
-  for (int i = threadIdx.x; i < 64 * B; i += blockDim.x) {
+  for (int i = threadIdx.x; i < 64 * BP; i += blockDim.x) {
     const int b = i >> 6, kk = i & 63;
-    xT[kk * (B + 1) + b] = (k0 + kk < K) ? x[static_cast<long long>(b) * xs + k0 + kk] : 0.f;
+    xT[kk * BP + b] = (b < B && k0 + kk < K) ? x[static_cast<long long>(b) * xs + k0 + kk] : 0.f;
   }
   __syncthreads();
   const float sc = inv_scale ? 1.f / __ldg(inv_scale) : 1.f;
-  // outputs (b, j): lanes run over b, warps over j
-  for (int o = threadIdx.x; o < ((B + 31) / 32) * 32 * J; o += blockDim.x) {
-    const int bt = (B + 31) / 32 * 32;
-    const int b = o % bt, j = o / bt;
-    if (b >= B) continue;
-    float s0 = 0.f, s1 = 0.f;
+  const int BT = BP >> 2;
+  for (int t = threadIdx.x; t < BT * J4; t += blockDim.x) {
+    const int bt = t % BT, jt = t / BT;
+    float acc[4][4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[r][c] = 0.f;
 #pragma unroll 8
-    for (int kk = 0; kk < 64; kk += 2) {
-      s0 += xT[kk * (B + 1) + b] * Ws[kk * J + j];
-      s1 += xT[(kk + 1) * (B + 1) + b] * Ws[(kk + 1) * J + j];
+    for (int kk = 0; kk < 64; ++kk) {
+      const float4 xv = *reinterpret_cast<const float4*>(xT + kk * BP + 4 * bt);
+      const float4 wv = *reinterpret_cast<const float4*>(Ws + kk * JP + 4 * jt);
+      const float xr[4] = {xv.x, xv.y, xv.z, xv.w}, wc[4] = {wv.x, wv.y, wv.z, wv.w};
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[r][c] += xr[r] * wc[c];
     }
-    float t = (s0 + s1) * sc;
-    if (bias && blockIdx.x == 0) t += bias[j];
-    atomicAdd(y + static_cast<long long>(b) * ys + j, t);
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int b = 4 * bt + r;
+      if (b >= B) continue;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int j = 4 * jt + c;
+        if (j >= J) continue;
+        float v = acc[r][c] * sc;
+        if (bias && blockIdx.x == 0) v += bias[j];
+        atomicAdd(y + static_cast<long long>(b) * ys + j, v);
+      }
+    }
   }
 }
 
@@ -525,7 +553,7 @@ extern "C" int vp_dense_fwd(const float* x, int x_stride, const float* w, const 
                             float* y, int y_stride, int b, int k, int j, int k_splits, vp_stream_t stream) {
   if (!x || !w || !y) return set_error("vp_dense_fwd: null pointer");
   // wide layers called with k_splits > 1 (y zero-filled by the caller): tiled kernel
-  const size_t tsm = (64 * static_cast<size_t>(j) + 64 * static_cast<size_t>(b + 1)) * sizeof(float);
+  const size_t tsm = (64 * static_cast<size_t>((j + 3) & ~3) + 64 * static_cast<size_t>((b + 3) & ~3)) * sizeof(float);
   if (k_splits > 1 && k >= 1024 && j <= 128 && tsm <= 48 * 1024) {
     dense_fwd_tiled_kernel<<<(k + 63) / 64, 256, tsm, as_stream(stream)>>>(x, x_stride, w, bias, inv_scale, y, y_stride, b, k, j);
     return check_launch("dense_fwd_tiled_kernel");

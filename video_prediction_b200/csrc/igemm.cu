@@ -1484,7 +1484,8 @@ extern "C" int vp_conv_wgrad(const vp_tensor* x, const vp_tensor* dy, const vp_c
     const bool enabled = !(env && atoi(env) == 0);
     // (kc == 4 with kw = 5 would need two 64-column N tiles that re-read dy; the tap-group kernel is faster there)
     const bool narrow_tiles = kc > 512 / (32 * g->kw) && kc % ceil_div(kc, 512 / (32 * g->kw)) == 0 && kc / ceil_div(kc, 512 / (32 * g->kw)) < 3;
-    if (enabled && unit && g->kw >= 4 && g->kw <= 8 && A.bw % 8 == 0 && g->kw * 32 <= 512 && !narrow_tiles) {
+    static const int min_kw = getenv("VP_WGRAD_ROW_MINKW") ? atoi(getenv("VP_WGRAD_ROW_MINKW")) : 4;
+    if (enabled && unit && g->kw >= min_kw && g->kw <= 8 && A.bw % 8 == 0 && g->kw * 32 <= 512 && !narrow_tiles) {
       const int halo_w = A.bw + g->kw - 1;
       const int lines = kWgPix / A.bw;
       const int hbox[4] = {halo_w, A.bh, A.bd, A.bn};

@@ -51,13 +51,9 @@ __device__ __forceinline__ float keff(const float* __restrict__ w, int kind, int
   }
 }
 
-__global__ void pack_weights_kernel(const float* __restrict__ w, int kd, int kh, int kw, int ci_ref, int co_n,
-                                    int kind, int layout, const int32_t* __restrict__ cmap, int ci_int,
-                                    const float* __restrict__ inv_scale, float* __restrict__ wp, int taps, int n_pad,
-                                    int kpad) {
-  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  const long long total = static_cast<long long>(taps) * n_pad * kpad;
-  if (idx >= total) return;
+__device__ __forceinline__ void pack_element(const float* __restrict__ w, int kd, int kh, int kw, int ci_ref, int co_n, int kind, int layout,
+                                             const int32_t* __restrict__ cmap, int ci_int, const float* __restrict__ inv_scale,
+                                             float* __restrict__ wp, int n_pad, int kpad, long long idx) {
   const int k = static_cast<int>(idx % kpad);
   const int n = static_cast<int>((idx / kpad) % n_pad);
   const int tap = static_cast<int>(idx / (static_cast<long long>(kpad) * n_pad));
@@ -73,6 +69,33 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, int kd, int kh,
   }
   // VP_WLAYOUT_RESIDUAL: the part of the weight the TF32 rounding dropped (the "lo" term of the fp32-exact 3xTF32 mode)
   wp[idx] = (layout & VP_WLAYOUT_RESIDUAL) ? round_tf32(v - round_tf32(v)) : round_tf32(v);
+}
+
+__global__ void pack_weights_kernel(const float* __restrict__ w, int kd, int kh, int kw, int ci_ref, int co_n,
+                                    int kind, int layout, const int32_t* __restrict__ cmap, int ci_int,
+                                    const float* __restrict__ inv_scale, float* __restrict__ wp, int taps, int n_pad,
+                                    int kpad) {
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long total = static_cast<long long>(taps) * n_pad * kpad;
+  if (idx >= total) return;
+  pack_element(w, kd, kh, kw, ci_ref, co_n, kind, layout, cmap, ci_int, inv_scale, wp, n_pad, kpad, idx);
+}
+
+// All weight tensors of an optimizer in ONE launch (the generator repacks ~60 small tensors after every Adam step: 60
+// launches of a few microseconds each): a device table of jobs, each owning the blocks [block_begin, next block_begin).
+__global__ void pack_weights_batch_kernel(const vp_pack_job* __restrict__ jobs, int njobs) {
+  int lo = 0, hi = njobs - 1;
+  const int b = static_cast<int>(blockIdx.x);
+  while (lo < hi) {                                              // last job with block_begin <= b
+    const int mid = (lo + hi + 1) >> 1;
+    if (jobs[mid].block_begin <= b) lo = mid; else hi = mid - 1;
+  }
+  const vp_pack_job j = jobs[lo];
+  const long long idx = static_cast<long long>(b - j.block_begin) * blockDim.x + threadIdx.x;
+  const int kpad = j.kc * 32;
+  const int taps = j.kind == VP_WKIND_POOLED ? (j.kh + 1) * (j.kw + 1) : (j.kind == VP_WKIND_UPSAMPLED ? (j.kh + 3) * (j.kw + 3) : j.kd * j.kh * j.kw);
+  if (idx >= static_cast<long long>(taps) * j.n_pad * kpad) return;
+  pack_element(j.w, j.kd, j.kh, j.kw, j.ci_ref, j.co, j.kind, j.layout, j.cmap, j.ci_int, j.inv_scale, j.wpacked, j.n_pad, kpad, idx);
 }
 
 // lo = x - tf32_truncate(x): what the tensor core does not see of an fp32 activation (it reads the top 19 bits)
@@ -143,6 +166,12 @@ extern "C" int vp_pack_weights(const float* w, int kd, int kh, int kw, int ci_re
   pack_weights_kernel<<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(w, kd, kh, kw, ci_ref, co, kind, layout, cmap,
                                                                          ci_int, inv_scale, wpacked, taps, n_pad, kpad);
   return check_launch("pack_weights_kernel");
+}
+
+extern "C" int vp_pack_weights_batch(const vp_pack_job* jobs_device, int njobs, int total_blocks, vp_stream_t stream) {
+  if (!jobs_device || njobs < 1 || total_blocks < 1) return set_error("vp_pack_weights_batch: empty job table");
+  pack_weights_batch_kernel<<<total_blocks, 256, 0, as_stream(stream)>>>(jobs_device, njobs);
+  return check_launch("pack_weights_batch_kernel");
 }
 
 extern "C" int vp_unpack_wgrad(const float* dwpacked, int kd, int kh, int kw, int ci_ref, int co, int kind,

@@ -82,21 +82,28 @@ _ENGINE_CHOICE = {}     # geometry signature -> 0 (box) / 1 (halo), measured onc
 _PROFILE = None         # list of (kind, algorithmic flops, start event, end event) while profile_engine(True) is active
 
 
-def profile_engine(on):
-    """Starts / stops recording every tensor-core engine call (CUDA events on the launching stream + algorithmic FLOPs).
-    Stopping returns {'igemm' | 'wgrad': dict(calls, flops, ms)} for the whole-engine roofline of bench.py."""
-    global _PROFILE
+_PROFILE_REPLAY = False
+
+
+def profile_engine(on, by_geometry=False, replay=False):
+    """Starts / stops recording every tensor-core engine call (algorithmic FLOPs + GPU time).  Stopping returns
+    {'igemm' | 'wgrad': dict(calls, flops, ms)} for the whole-engine roofline of bench.py, or with by_geometry the same sums
+    per (kind, geometry key, engine).  Timing: CUDA events around the eager call on its launching stream, which for kernels
+    shorter than a launch costs on the host (ctypes + tensor-map encoding, ~25 us) measures the HOST, not the GPU; with
+    replay=True every call is additionally captured four times into a CUDA graph and the replay is timed (GPU time only,
+    operands L2-warm; calls that accumulate into their output are repeated too, so the step's numbers are garbage)."""
+    global _PROFILE, _PROFILE_REPLAY
     if on:
-        _PROFILE = []
+        _PROFILE, _PROFILE_REPLAY = [], bool(replay)
         return None
     rec, _PROFILE = _PROFILE or [], None
     torch.cuda.synchronize()
     out = {}
-    for kind, flops, e0, e1 in rec:
-        d = out.setdefault(kind, dict(calls=0, flops=0.0, ms=0.0))
+    for kind, flops, e0, e1, key, reps in rec:
+        d = out.setdefault((kind, key) if by_geometry else kind, dict(calls=0, flops=0.0, ms=0.0))
         d['calls'] += 1
         d['flops'] += flops
-        d['ms'] += e0.elapsed_time(e1)
+        d['ms'] += e0.elapsed_time(e1) / reps
     return out
 
 
@@ -109,14 +116,29 @@ def _conv_flops(x_view, g, out_view):
     return 2.0 * out_view.n * out_view.d * out_view.h * out_view.w * out_view.c * x_view.c * taps
 
 
-def _profiled(kind, flops, call):
+def _profiled(kind, flops, call, key=None):
     if _PROFILE is None:
         return call()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if _PROFILE_REPLAY and not torch.cuda.is_current_stream_capturing():
+        call()
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            for _ in range(4):
+                call()
+        g.replay()
+        e0.record()
+        g.replay()
+        e1.record()
+        e1.synchronize()
+        _PROFILE.append((kind, flops, e0, e1, key, 4))
+        del g
+        return
     e0.record()
     call()
     e1.record()
-    _PROFILE.append((kind, flops, e0, e1))
+    _PROFILE.append((kind, flops, e0, e1, key, 1))
 
 
 def _conv_key(x_view, g, n_pad, kc, out_view, act, extra):
@@ -163,25 +185,33 @@ def _pick_engine(key, call, idempotent):
 
 
 def conv_igemm(x_view, g, wpacked, n_pad, kc, out_view, bias=None, act=ACT_NONE, alpha=0.0, split_k=1, accumulate=0):
+    if 'igemm' in _SKIP:
+        return
+
     def call():
         check(lib().vp_conv_igemm(C.byref(x_view), C.byref(g), ptr(wpacked), n_pad, kc, C.byref(out_view), ptr(bias),
                                   act, C.c_float(alpha), split_k, int(accumulate), stream_ptr()))
     # an explicit split_k > 1 adds atomically into a caller-cleared output: repeating the call (timing) would change it
-    eng = _pick_engine(_conv_key(x_view, g, n_pad, kc, out_view, act, ('fwd', split_k)), call, not accumulate and split_k <= 1)
+    key = _conv_key(x_view, g, n_pad, kc, out_view, act, ('fwd', split_k))
+    eng = _pick_engine(key, call, not accumulate and split_k <= 1)
     check(lib().vp_conv_set_engine(eng))
-    _profiled('igemm', _conv_flops(x_view, g, out_view), call)
+    _profiled('igemm', _conv_flops(x_view, g, out_view), call, (key, eng))
     if eng >= 0:
         check(lib().vp_conv_set_engine(-1))
 
 
 def conv_igemm_actgrad(x_view, g, wpacked, n_pad, kc, out_view, act_output_addr, addend_addr, act, alpha=0.0, accumulate=0):
+    if 'igemm' in _SKIP:
+        return
+
     def call():
         check(lib().vp_conv_igemm_actgrad(C.byref(x_view), C.byref(g), ptr(wpacked), n_pad, kc, C.byref(out_view),
                                           C.c_void_p(act_output_addr), C.c_void_p(addend_addr or 0), act, C.c_float(alpha),
                                           int(accumulate), stream_ptr()))
-    eng = _pick_engine(_conv_key(x_view, g, n_pad, kc, out_view, act, ('actgrad', bool(addend_addr))), call, not accumulate)
+    key = _conv_key(x_view, g, n_pad, kc, out_view, act, ('actgrad', bool(addend_addr)))
+    eng = _pick_engine(key, call, not accumulate)
     check(lib().vp_conv_set_engine(eng))
-    _profiled('igemm', _conv_flops(x_view, g, out_view), call)
+    _profiled('igemm', _conv_flops(x_view, g, out_view), call, (key, eng))
     if eng >= 0:
         check(lib().vp_conv_set_engine(-1))
 
@@ -211,7 +241,8 @@ def conv_wgrad(x_view, dy_view, g, dwpacked, n_pad, kc, split_k=1):
     taps = g.kd * g.kh * g.kw / (float(g.sd * g.sh * g.sw) if g.transposed else 1.0)
     flops = 2.0 * dy_view.n * dy_view.d * dy_view.h * dy_view.w * dy_view.c * x_view.c * taps
     _profiled('wgrad', flops, lambda: check(lib().vp_conv_wgrad(C.byref(x_view), C.byref(dy_view), C.byref(g), ptr(dwpacked), n_pad, kc,
-                                                               split_k, stream_ptr())))
+                                                               split_k, stream_ptr())),
+              (_conv_key(x_view, g, n_pad, kc, dy_view, 0, ('wgrad', split_k)), -1))
 
 
 def eff_taps(k, kind):
@@ -249,6 +280,45 @@ def pack_weights(w, k, ci_ref, co, kind, layout, ci_int=None, cmap=None, inv_sca
     check(lib().vp_pack_weights(ptr(w), k[0], k[1], k[2], ci_ref, co, kind, layout, ptr(cmap), ci_int,
                                 ptr(inv_scale), ptr(out), n_pad, kc, stream_ptr()))
     return out, n_pad, kc
+
+
+class PackJob(C.Structure):
+    """vp_pack_job (include/vp_b200.h)."""
+    _fields_ = [('w', C.c_void_p), ('wpacked', C.c_void_p), ('cmap', C.c_void_p), ('inv_scale', C.c_void_p),
+                ('kd', C.c_int), ('kh', C.c_int), ('kw', C.c_int), ('ci_ref', C.c_int), ('co', C.c_int), ('kind', C.c_int),
+                ('layout', C.c_int), ('ci_int', C.c_int), ('n_pad', C.c_int), ('kc', C.c_int), ('block_begin', C.c_int),
+                ('reserved', C.c_int)]
+
+
+class PackPlan(object):
+    """A fixed set of weight tensors repacked by ONE launch (vp_pack_weights_batch).  Every entry is the argument list of a
+    pack_weights call whose output buffer already exists: (w, k, ci_ref, co, kind, layout, ci_int, cmap, inv_scale, out)."""
+
+    def __init__(self, entries):
+        import numpy as np
+        jobs = (PackJob * len(entries))()
+        blocks = 0
+        self.keep = entries                                   # the table holds raw pointers: keep the tensors alive
+        for j, (w, k, ci_ref, co, kind, layout, ci_int, cmap, inv_scale, out) in zip(jobs, entries):
+            ci_int = ci_ref if ci_int is None else ci_int
+            rows, cols = (co, ci_int) if (layout & 3) == WLAYOUT_FWD else (ci_int, co)
+            n_pad, kc = choose_n_pad(rows), pad_to(cols, 32) // 32
+            total = eff_taps(k, kind) * n_pad * kc * 32
+            assert out.numel() == total and w.is_contiguous()
+            j.w, j.wpacked = w.data_ptr(), out.data_ptr()
+            j.cmap = cmap.data_ptr() if cmap is not None else None
+            j.inv_scale = inv_scale.data_ptr() if inv_scale is not None else None
+            j.kd, j.kh, j.kw, j.ci_ref, j.co, j.kind, j.layout, j.ci_int = k[0], k[1], k[2], ci_ref, co, kind, layout, ci_int
+            j.n_pad, j.kc, j.block_begin = n_pad, kc, blocks
+            blocks += -(-total // 256)
+        self.njobs, self.blocks = len(entries), blocks
+        raw = np.frombuffer(bytes(jobs), dtype=np.uint8).copy()
+        self.table = torch.from_numpy(raw).to(entries[0][0].device)
+
+    def run(self):
+        if 'pack' in _SKIP:
+            return
+        check(lib().vp_pack_weights_batch(ptr(self.table), self.njobs, self.blocks, stream_ptr()))
 
 
 def unpack_wgrad(dwpacked, k, ci_ref, co, kind, dw, n_pad, kc, ci_int=None, cmap=None):
@@ -499,6 +569,17 @@ def conv3d_c4_fwd(x, w, inv_scale, bias, out, n, d, h, wd, ci, alpha):
     if 'c4fwd' in _SKIP:
         return
     check(lib().vp_conv3d_c4_fwd(ptr(x), ptr(w), ptr(inv_scale), ptr(bias), ptr(out), n, d, h, wd, ci, _f(alpha), stream_ptr()))
+
+
+def conv3d_c4_fwd_tc_ok(h, wd):
+    """Shapes vp_conv3d_c4_fwd_tc tiles: L in {16, 8, 4} lines with h % L == 0 and three (L+2) x (wd+2) float4 planes <= 90 KB."""
+    return wd + 2 <= 256 and any(h % L == 0 and 3 * (L + 2) * (wd + 2) * 16 <= 90 * 1024 for L in (16, 8, 4))
+
+
+def conv3d_c4_fwd_tc(x, w, inv_scale, bias, out, n, d, h, wd, ci, alpha):
+    if 'c4fwd' in _SKIP:
+        return
+    check(lib().vp_conv3d_c4_fwd_tc(ptr(x), ptr(w), ptr(inv_scale), ptr(bias), ptr(out), n, d, h, wd, ci, _f(alpha), stream_ptr()))
 
 
 def conv3d_c4_wgrad(x, dy, gw, n, d, h, wd, ci):

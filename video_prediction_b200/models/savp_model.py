@@ -748,10 +748,23 @@ class SAVPVideoPredictionModel(TrainMixin, VideoPredictionModel):
         Bf['zprior'] = self._z(self.T - hp.context_frames, B, hp.nz)
 
     def _pack_all(self):
+        """Repacks every generator / encoder convolution weight after an optimizer step: one table-driven launch once all
+        packed buffers exist (the first call creates them layer by layer), per-layer calls in the fp32-exact mode."""
+        plan = getattr(self, '_pack_plan', None)
+        if plan is not None:
+            plan.run()
+            return
         for c in self.convs:
             c.pack()
             if getattr(c, 'wpd', None) is not None:
                 c.pack_bwd()
+        if not L.exact_mode() and os.environ.get('VP_PACK_BATCH', '1') == '1' and all(getattr(c, 'wpd', None) is not None for c in self.convs):
+            entries = []
+            for c in self.convs:
+                w = self.params[c.wname]
+                entries.append((w, c.k, c.ci_ref, c.co, c.kind, L.WLAYOUT_FWD, c.ci_int, c.cmap, None, c.wp))
+                entries.append((w, c.k, c.ci_ref, c.co, c.kind, L.WLAYOUT_DGRAD, c.ci_int, c.cmap, None, c.wpd))
+            self._pack_plan = L.PackPlan(entries)
 
     # ------------------------------------------------------------------ inputs
     def set_inputs(self, inputs, noise=None, sampling=None):

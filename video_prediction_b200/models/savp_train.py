@@ -104,15 +104,19 @@ class SNLayer(object):
         return (not self.is_fc) and not self.two_d and self.k == 3 and tuple(self.stride) == (1, 1, 1) and self.cin_ref <= 3 and self.co == 32
 
     def fwd(self, x, out):
-        # the first layer's FORWARD runs on the tensor-core engine: halo mode loads one activation tile per 9 taps, which
-        # the box mode of round 1 could not (1070 us box / 417 us CUDA cores / 250 us halo per 32 clips); its weight
-        # gradient has its own tensor-core kernel (csrc/d0_wgrad.cu: float4 voxel rows are the MN-major operand as they
-        # lie, ~80 us against 900 us on the CUDA cores), the CUDA-core kernel remains for the fp32-exact mode
-        if self.cuda_core and os.environ.get('VP_D0_FWD_CUDA_CORE', '0') == '1':
+        # the first layer has its own tensor-core kernels (csrc/d0_layer.cu): float4 voxel rows are UMMA operands as they lie
+        # -- forward: overlapping rows x[v-1 .. v+2] = the K = 16 operand of a kernel row, 18 MMAs per 128 voxels against
+        # 108 on the generic engine (270 us -> ~40 us per 32 clips); weight gradient: ~80 us against 900 us on the CUDA cores.
+        # The fp32-exact mode runs the generic engine (3xTF32) and the exact CUDA-core weight gradient.
+        if self.cuda_core and not L.exact_mode():
             P = self.m.params
             n, d, h, w = x.shape[:4]
-            L.conv3d_c4_fwd(x, P[self.wname], self.sigma, P[self.bname], out, n, d, h, w, self.cin_ref, 0.1)
-            return
+            if os.environ.get('VP_D0_FWD_CUDA_CORE', '0') == '1':
+                L.conv3d_c4_fwd(x, P[self.wname], self.sigma, P[self.bname], out, n, d, h, w, self.cin_ref, 0.1)
+                return
+            if os.environ.get('VP_D0_FWD_ENGINE', '0') != '1' and L.conv3d_c4_fwd_tc_ok(h, w):
+                L.conv3d_c4_fwd_tc(x, P[self.wname], self.sigma, P[self.bname], out, n, d, h, w, self.cin_ref, 0.1)
+                return
         if L.exact_mode():
             from .savp_model import conv3x
             conv3x(x, self.cin_int, self.geom, self.wp, self.wp_lo, self.n_pad, self.kc, L.tensor_view(out, self.co),
