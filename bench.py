@@ -234,6 +234,32 @@ def time_gate_kernels(model, iters=3):
     return flops, ms, per_layer
 
 
+def engine_in_graph_ms(model, one_step, steps):
+    """The engine's cost INSIDE the captured step: the step is re-captured without the tensor-core engine calls
+    (results are garbage by design) and timed; full step - this = what the engine costs on the critical path, with the
+    overlap of the parallel graph branches and warm caches that the per-call timings cannot see."""
+    import torch
+    from video_prediction_b200 import lib as L
+    saved = set(L._SKIP)
+    try:
+        L._SKIP.update(('igemm', 'wgrad'))
+        model._graph, model._eager_steps = None, 0
+        for _ in range(4):
+            one_step()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            one_step()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / steps
+    finally:
+        L._SKIP.clear()
+        L._SKIP.update(saved)
+        model._graph, model._eager_steps = None, 0
+
+
 def engine_profile(model, batch):
     """Whole-engine roofline: ONE eager training step with every tensor-core engine call (forward + dgrad = `igemm`, weight
     gradients = `wgrad`) bracketed by CUDA events on its launching stream; algorithmic FLOPs as SURVEY.md 8(d) counts them
@@ -246,7 +272,9 @@ def engine_profile(model, batch):
     try:
         model.stage_step()
         torch.cuda.synchronize()
-        L.profile_engine(True)
+        # replay=True: every call is re-captured into a CUDA graph and the replay is timed -- an eager event pair around a
+        # kernel of a few microseconds measures the host's launch path (ctypes + tensor-map encoding), not the GPU
+        L.profile_engine(True, replay=True)
         model._step_device(getattr(model, '_allreduce', None))
         model.global_step += 1
         return L.profile_engine(False)
@@ -345,6 +373,10 @@ def run_ours(args):
     finite = all(v == v for v in losses.values())
 
     # ---------------- rooflines + CPU baseline (rank 0; the CPU leg at N = 1 only)
+    no_engine_ms = None
+    if not args.no_roofline and world == 1 and graph is not None:
+        no_engine_ms = engine_in_graph_ms(model, one_step, max(5, min(args.steps, 10)))
+        log('step without the engine: %.2f ms' % no_engine_ms)
     prof = None if args.no_roofline else engine_profile(model, batches[0])     # every rank runs the same (collective-bearing) step
     if rank == 0:
         peaks = load_peaks()
@@ -363,13 +395,19 @@ def run_ours(args):
             sustained = (peaks.get('bf16_sustained') or peaks['bf16']) / 2
             roof['whole_engine'] = dict(
                 what='every tensor-core engine call of ONE training step (forward + dgrad + wgrad of all convolutions), '
-                     'algorithmic FLOPs / summed CUDA-event time of the calls (eager step, towers sequential)',
+                     'algorithmic FLOPs / summed GPU time of the calls, each call timed as a CUDA-graph replay of 4 repeats '
+                     '(CUDA events; eager event pairs around kernels of a few microseconds time the host launch path)',
                 tflop_per_step=tot_f / 1e12, engine_ms_per_step=tot_ms, achieved=tot_f / tot_ms / 1e9, unit='TFLOP/s',
                 peak_tf32_equiv_sustained=sustained, frac_of_tf32_peak_sustained=tot_f / tot_ms / 1e9 / sustained,
                 frac_of_bf16_peak_sustained=tot_f / tot_ms / 1e9 / (2 * sustained),
                 by_kind={k: dict(calls=d['calls'], tflop=d['flops'] / 1e12, ms=d['ms'], tflops=d['flops'] / d['ms'] / 1e9)
                          for k, d in prof.items()},
                 whole_step_tflops=tot_f / ms / 1e9)
+            if no_engine_ms is not None:
+                roof['whole_engine']['in_graph'] = dict(
+                    what='captured step re-timed without the engine calls: full - without = the engine on the critical path',
+                    step_ms=ms, step_without_engine_ms=no_engine_ms, engine_ms=ms - no_engine_ms,
+                    achieved=tot_f / (ms - no_engine_ms) / 1e9, frac_of_tf32_peak_sustained=tot_f / (ms - no_engine_ms) / 1e9 / sustained)
         cpu = None
         if world == 1 and not args.no_cpu:
             sb = cpu_sample_batch()
