@@ -16,6 +16,8 @@
 #include <cooperative_groups.h>
 
 #include <cstdlib>
+#include <map>
+#include <tuple>
 
 #include "common.h"
 #include "ptx.cuh"
@@ -204,8 +206,8 @@ __global__ void __launch_bounds__(512) slab_inorm_act_bwd_kernel(const float* __
 
 // ------------------------------------------------------------------------------------------------ ConvLSTM gates forward
 // pre [N,P,4F] (i,j,f,o); i,j,f,o = IN(pre)*g1+b1 ; c' = c*sig(f+fb) + sig(i)*tanh(j) ; cn = IN(c')*g2+b2 ; h = tanh(cn)*sig(o)
-template <int ITERS>
-__global__ void __launch_bounds__(256) slab_gates_fwd_kernel(const float* __restrict__ pre, int P, int F, const float* __restrict__ c_prev,
+template <int ITERS, int THREADS = 256>
+__global__ void __launch_bounds__(THREADS) slab_gates_fwd_kernel(const float* __restrict__ pre, int P, int F, const float* __restrict__ c_prev,
                                                              const float* __restrict__ g1, const float* __restrict__ b1,
                                                              const float* __restrict__ g2, const float* __restrict__ b2, float forget_bias,
                                                              float eps, float* __restrict__ c_new, SlabDsts hdst, float* __restrict__ stats1,
@@ -325,11 +327,12 @@ __global__ void __launch_bounds__(512) slab_gates_bwd_kernel(
     const float* __restrict__ g2, const float* __restrict__ b2, const float* __restrict__ stats1, const float* __restrict__ stats2,
     float forget_bias, SlabSrcs dh_srcs, const float* __restrict__ dc_next, float* __restrict__ dpre, float* __restrict__ dc_prev,
     float* __restrict__ dg1, float* __restrict__ db1, float* __restrict__ dg2, float* __restrict__ db2, int cs, int ppc) {
-  extern __shared__ float4 sm4[];   // [4][ppc*8] staged pre-activations, [4][ppc*8] gate gradients, [ppc*8] dcn, [ppc*8] chat
+  extern __shared__ float4 sm4[];   // ([4][ppc*8] staged pre-activations if ppc <= 128,) [4][ppc*8] gate gradients, [ppc*8] dcn, [ppc*8] chat
   __shared__ float s_warp[kSlabMaxWarps * 8 * 32], s_partA[8 * 8], s_partB[8 * 32], s_tot[8 * 32];
   const int items = ppc * 8;
+  const bool stage_pre = ppc <= 128;   // larger CTAs re-read the pre-activations from global memory (L2) in passes B and C
   float4* spre = sm4;
-  float4* sdg = spre + 4 * items;
+  float4* sdg = stage_pre ? spre + 4 * items : sm4;
   float4* sdc = sdg + 4 * items;
   float4* sch = sdc + items;
   const int q = threadIdx.x & 7, pl = threadIdx.x >> 3, lanes = blockDim.x >> 3;
@@ -372,7 +375,7 @@ __global__ void __launch_bounds__(512) slab_gates_bwd_kernel(
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
       pv[g] = *reinterpret_cast<const float4*>(pp + p * 4 * F + g * F);
-      spre[g * items + si] = pv[g];
+      if (stage_pre) spre[g * items + si] = pv[g];
     }
     float gi[4], gj[4], gf[4], go[4];
     gate(pv[0], 0, gi); gate(pv[1], 1, gj); gate(pv[2], 2, gf); gate(pv[3], 3, go);
@@ -418,7 +421,14 @@ __global__ void __launch_bounds__(512) slab_gates_bwd_kernel(
   for (int l = pl; l < ppc; l += lanes) {
     const long long p = p0 + l;
     const int si = l * 8 + q;
-    const float4 pv0 = spre[si], pv1 = spre[items + si], pv2 = spre[2 * items + si], pv3 = spre[3 * items + si];
+    float4 pv0, pv1, pv2, pv3;
+    if (stage_pre) {
+      pv0 = spre[si]; pv1 = spre[items + si]; pv2 = spre[2 * items + si]; pv3 = spre[3 * items + si];
+    } else {
+      const float* g = pp + p * 4 * F;
+      pv0 = *reinterpret_cast<const float4*>(g); pv1 = *reinterpret_cast<const float4*>(g + F);
+      pv2 = *reinterpret_cast<const float4*>(g + 2 * F); pv3 = *reinterpret_cast<const float4*>(g + 3 * F);
+    }
     float gi[4], gj[4], gf[4];
     gate(pv0, 0, gi); gate(pv1, 1, gj); gate(pv2, 2, gf);
     const float4 c4 = *reinterpret_cast<const float4*>(cp + p * F);
@@ -470,7 +480,7 @@ __global__ void __launch_bounds__(512) slab_gates_bwd_kernel(
     const int si = l * 8 + q;
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
-      const float4 v = spre[g * items + si];
+      const float4 v = stage_pre ? spre[g * items + si] : *reinterpret_cast<const float4*>(pp + p * 4 * F + g * F);
       const float4 d4 = sdg[g * items + si];
       const float xv[4] = {v.x, v.y, v.z, v.w}, dv[4] = {d4.x, d4.y, d4.z, d4.w};
       float o[4];
@@ -494,18 +504,61 @@ static bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
 
 // Decomposition of a plane of P positions for `units` = slabs * samples independent (sample, slab) units:
 // cluster size cs (1..8), positions per CTA ppc = P / cs, and for the register-resident kernels lanes * iters = ppc.
+//
+// The candidates are ranked by how many ROUNDS of resident clusters the launch needs: these kernels hold one CTA per SM
+// (registers or 160-200 KB of staging), and a cluster of 8 is placed inside a GPC, so only 15 clusters of 8 (120 CTAs) are
+// co-resident on the 148 SMs -- the first version launched 32 clusters of 8 for the 32x32 planes and ran three rounds of a
+// latency-bound kernel (ncu: launch__cluster_max_active 15, SMs active 53 % of the time).  cudaOccupancyMaxActiveClusters
+// gives the resident cluster count of each candidate; cost = rounds * (1 + ppc / ppc_ref): a round is a fixed latency chain
+// (loads, two cluster-wide reductions, stores) plus a part that grows with the positions a CTA walks.
 struct SlabPlan { int cs, ppc, lanes, iters; };
-static bool plan_slab(int P, long long units, int max_iters, int max_lanes, SlabPlan* pl) {
+
+static int max_active_clusters(const void* kernel, int cs, int threads, size_t smem) {
+  static std::map<std::tuple<const void*, int, int, size_t>, int> cache;
+  const auto key = std::make_tuple(kernel, cs, threads, smem);
+  auto it = cache.find(key);
+  if (it != cache.end()) return it->second;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(cs * 64);
+  cfg.blockDim = dim3(threads);
+  cfg.dynamicSmemBytes = smem;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cs;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, kernel, &cfg) != cudaSuccess || n < 1) {
+    cudaGetLastError();
+    n = std::max(1, 148 / cs);
+  }
+  cache[key] = n;
+  return n;
+}
+
+// `describe(ppc, lanes, iters, &kernel, &threads, &smem)` returns false when the kernel family has no variant for that shape.
+template <typename Describe>
+static bool plan_slab(int P, long long units, int max_lanes, double ppc_ref, Describe describe, SlabPlan* best) {
   if (!is_pow2(P) || P < 8) return false;
-  int cs = 1;
-  while (cs < 8 && units * cs * 2 <= 148 * 2 && P / (cs * 2) >= 32) cs *= 2;     // spread over the SMs, >= 32 positions per CTA
-  while (cs < 8 && P / cs > max_iters * max_lanes) cs *= 2;                        // the register-resident kernels need ppc <= iters*lanes
-  const int ppc = P / cs;
-  if (ppc > max_iters * max_lanes) return false;
-  int lanes = ppc < max_lanes ? ppc : max_lanes;
-  if (lanes < 4) return false;                                                     // block of at least 32 threads
-  pl->cs = cs; pl->ppc = ppc; pl->lanes = lanes; pl->iters = ppc / lanes;
-  return true;
+  double best_cost = 1e30;
+  for (int cs = 1; cs <= 8; cs *= 2) {
+    if (P % cs) continue;
+    const int ppc = P / cs;
+    const int lanes = ppc < max_lanes ? ppc : max_lanes;
+    if (lanes < 4) continue;                                                       // block of at least 32 threads
+    const int iters = ppc / lanes;
+    const void* kernel = nullptr;
+    int threads = 0;
+    size_t smem = 0;
+    if (!describe(ppc, lanes, iters, &kernel, &threads, &smem)) continue;
+    const long long resident = max_active_clusters(kernel, cs, threads, smem);
+    const long long rounds = (units + resident - 1) / resident;
+    const double cost = static_cast<double>(rounds) * (1.0 + ppc / ppc_ref);
+    if (cost < best_cost - 1e-9) { best_cost = cost; best->cs = cs; best->ppc = ppc; best->lanes = lanes; best->iters = iters; }
+  }
+  return best_cost < 1e29;
 }
 
 template <typename... Args>
@@ -531,19 +584,26 @@ static int launch_cluster(void (*kernel)(Args...), dim3 grid, int threads, size_
 int slab_inorm_act(const float* x, int xs, float* y, int ys, int n, int P, int C, const float* gamma, const float* beta, float eps, int act,
                    float alpha, float* stats, vp_stream_t stream) {
   if (!slab_enabled() || C % 32 || (xs & 3) || (ys & 3)) return 1;
-  SlabPlan pl;
-  if (!plan_slab(P, static_cast<long long>(C / 32) * n, 16, 64, &pl)) return 1;
-  dim3 grid(pl.cs, C / 32, n);
   typedef void (*K)(const float*, int, float*, int, int, int, const float*, const float*, float, int, float, float*, int);
-  K k = nullptr;
-  switch (pl.iters) {
-    case 1: k = slab_inorm_act_kernel<1>; break;
-    case 2: k = slab_inorm_act_kernel<2>; break;
-    case 4: k = slab_inorm_act_kernel<4>; break;
-    case 8: k = slab_inorm_act_kernel<8>; break;
-    case 16: k = slab_inorm_act_kernel<16>; break;
-    default: return 1;
-  }
+  auto pick = [](int iters) -> K {
+    switch (iters) {
+      case 1: return slab_inorm_act_kernel<1>;
+      case 2: return slab_inorm_act_kernel<2>;
+      case 4: return slab_inorm_act_kernel<4>;
+      case 8: return slab_inorm_act_kernel<8>;
+      case 16: return slab_inorm_act_kernel<16>;
+      default: return nullptr;
+    }
+  };
+  SlabPlan pl;
+  if (!plan_slab(P, static_cast<long long>(C / 32) * n, 64, 2048.0,
+                 [&](int, int lanes, int iters, const void** kern, int* threads, size_t* smem) {
+                   K kk = pick(iters);
+                   *kern = reinterpret_cast<const void*>(kk); *threads = lanes * 8; *smem = 0;
+                   return kk != nullptr;
+                 }, &pl)) return 1;
+  dim3 grid(pl.cs, C / 32, n);
+  K k = pick(pl.iters);
   return launch_cluster(k, grid, pl.lanes * 8, 0, pl.cs, as_stream(stream), x, xs, y, ys, P, C, gamma, beta, eps, act, alpha, stats, pl.cs);
 }
 
@@ -551,21 +611,28 @@ int slab_inorm_act_bwd(const float* x, int xs, const float* const* dy, const int
                        const float* gamma, const float* beta, const float* stats, int act, float alpha, float* dgamma, float* dbeta,
                        vp_stream_t stream) {
   if (!slab_enabled() || C % 32 || (xs & 3) || (dxs & 3)) return 1;
+  typedef void (*K)(const float*, int, SlabSrcs, float*, int, int, int, const float*, const float*, const float*, int, float, float*, float*, int);
+  auto pick = [](int iters) -> K {
+    switch (iters) {
+      case 1: return slab_inorm_act_bwd_kernel<1>;
+      case 2: return slab_inorm_act_bwd_kernel<2>;
+      case 4: return slab_inorm_act_bwd_kernel<4>;
+      case 8: return slab_inorm_act_bwd_kernel<8>;
+      default: return nullptr;
+    }
+  };
   SlabPlan pl;
-  if (!plan_slab(P, static_cast<long long>(C / 32) * n, 8, 64, &pl)) return 1;
+  if (!plan_slab(P, static_cast<long long>(C / 32) * n, 64, 1024.0,
+                 [&](int, int lanes, int iters, const void** kern, int* threads, size_t* smem) {
+                   K kk = pick(iters);
+                   *kern = reinterpret_cast<const void*>(kk); *threads = lanes * 8; *smem = 0;
+                   return kk != nullptr;
+                 }, &pl)) return 1;
   SlabSrcs s;
   s.count = num_dy;
   for (int i = 0; i < 4; ++i) { s.ptr[i] = i < num_dy ? dy[i] : nullptr; s.stride[i] = i < num_dy ? dy_cs[i] : 0; }
   dim3 grid(pl.cs, C / 32, n);
-  typedef void (*K)(const float*, int, SlabSrcs, float*, int, int, int, const float*, const float*, const float*, int, float, float*, float*, int);
-  K k = nullptr;
-  switch (pl.iters) {
-    case 1: k = slab_inorm_act_bwd_kernel<1>; break;
-    case 2: k = slab_inorm_act_bwd_kernel<2>; break;
-    case 4: k = slab_inorm_act_bwd_kernel<4>; break;
-    case 8: k = slab_inorm_act_bwd_kernel<8>; break;
-    default: return 1;
-  }
+  K k = pick(pl.iters);
   return launch_cluster(k, grid, pl.lanes * 8, 0, pl.cs, as_stream(stream), x, xs, s, dx, dxs, P, C, gamma, beta, stats, act, alpha, dgamma,
                         dbeta, pl.cs);
 }
@@ -575,22 +642,30 @@ int slab_gates_fwd(const float* pre, int n, int P, int F, const float* c_prev, c
                    float* stats2, vp_stream_t stream) {
   if (!slab_enabled() || F % 32) return 1;
   for (int i = 0; i < num_h; ++i) if (h_cs[i] & 3) return 1;
+  typedef void (*K)(const float*, int, int, const float*, const float*, const float*, const float*, const float*, float, float, float*, SlabDsts,
+                    float*, float*, int);
+  auto pick = [](int iters) -> K {                                                   // 256 threads x <= 4 positions: operands stay in registers
+    switch (iters) {
+      case 1: return slab_gates_fwd_kernel<1>;
+      case 2: return slab_gates_fwd_kernel<2>;
+      case 4: return slab_gates_fwd_kernel<4>;
+      case 8: return slab_gates_fwd_kernel<4, 512>;                                  // lanes = 64: 512 threads x 4 positions
+      default: return nullptr;
+    }
+  };
   SlabPlan pl;
-  if (!plan_slab(P, static_cast<long long>(F / 32) * n, 4, 32, &pl)) return 1;      // 256 threads x <= 4 positions: operands stay in registers
+  if (!plan_slab(P, static_cast<long long>(F / 32) * n, 32, 256.0,
+                 [&](int, int lanes, int iters, const void** kern, int* threads, size_t* smem) {
+                   K kk = pick(iters);
+                   *kern = reinterpret_cast<const void*>(kk); *threads = iters == 8 ? 512 : lanes * 8; *smem = 0;
+                   return kk != nullptr;
+                 }, &pl)) return 1;
   SlabDsts d;
   d.count = num_h;
   for (int i = 0; i < 3; ++i) { d.ptr[i] = i < num_h ? h_dst[i] : nullptr; d.stride[i] = i < num_h ? h_cs[i] : 0; }
   dim3 grid(pl.cs, F / 32, n);
-  typedef void (*K)(const float*, int, int, const float*, const float*, const float*, const float*, const float*, float, float, float*, SlabDsts,
-                    float*, float*, int);
-  K k = nullptr;
-  switch (pl.iters) {
-    case 1: k = slab_gates_fwd_kernel<1>; break;
-    case 2: k = slab_gates_fwd_kernel<2>; break;
-    case 4: k = slab_gates_fwd_kernel<4>; break;
-    default: return 1;
-  }
-  return launch_cluster(k, grid, pl.lanes * 8, 0, pl.cs, as_stream(stream), pre, P, F, c_prev, g1, b1, g2, b2, forget_bias, eps, c_new, d,
+  K k = pick(pl.iters);
+  return launch_cluster(k, grid, pl.iters == 8 ? 512 : pl.lanes * 8, 0, pl.cs, as_stream(stream), pre, P, F, c_prev, g1, b1, g2, b2, forget_bias, eps, c_new, d,
                         stats1, stats2, pl.cs);
 }
 
@@ -600,21 +675,27 @@ int slab_gates_bwd(const float* pre, int n, int P, int F, const float* c_prev, c
                    vp_stream_t stream) {
   if (!slab_enabled() || F % 32) return 1;
   for (int i = 0; i < num_dh; ++i) if (dh_cs[i] & 3) return 1;
-  SlabPlan pl;
-  if (!plan_slab(P, static_cast<long long>(F / 32) * n, 2, 64, &pl)) return 1;      // ppc <= 128: 160 KB of staging per CTA
-  SlabSrcs s;
-  s.count = num_dh;
-  for (int i = 0; i < 4; ++i) { s.ptr[i] = i < num_dh ? dh[i] : nullptr; s.stride[i] = i < num_dh ? dh_cs[i] : 0; }
-  const size_t smem = static_cast<size_t>(pl.ppc) * 8 * 10 * sizeof(float4);
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(slab_gates_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 8 * 10 * 16) != cudaSuccess)
+    if (cudaFuncSetAttribute(slab_gates_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * 8 * 6 * 16) != cudaSuccess)
       return set_error("cudaFuncSetAttribute(slab_gates_bwd_kernel) failed");
     attr_set = true;
   }
+  // ppc <= 128: pre-activations staged too (10 float4 per position and quad = 160 KB); ppc = 256: they are re-read from
+  // global memory (L2) in the second and third pass and only the six derived float4 are staged (192 KB)
+  auto staging = [](int ppc) { return static_cast<size_t>(ppc) * 8 * (ppc <= 128 ? 10 : 6) * sizeof(float4); };
+  SlabPlan pl;
+  if (!plan_slab(P, static_cast<long long>(F / 32) * n, 64, 256.0,
+                 [&](int ppc, int lanes, int, const void** kern, int* threads, size_t* smem) {
+                   *kern = reinterpret_cast<const void*>(slab_gates_bwd_kernel); *threads = lanes * 8; *smem = staging(ppc);
+                   return ppc <= 256;
+                 }, &pl)) return 1;
+  SlabSrcs s;
+  s.count = num_dh;
+  for (int i = 0; i < 4; ++i) { s.ptr[i] = i < num_dh ? dh[i] : nullptr; s.stride[i] = i < num_dh ? dh_cs[i] : 0; }
   dim3 grid(pl.cs, F / 32, n);
-  return launch_cluster(slab_gates_bwd_kernel, grid, pl.lanes * 8, smem, pl.cs, as_stream(stream), pre, P, F, c_prev, g1, b1, g2, b2, stats1,
-                        stats2, forget_bias, s, dc_next, dpre, dc_prev, dg1, db1, dg2, db2, pl.cs, pl.ppc);
+  return launch_cluster(slab_gates_bwd_kernel, grid, pl.lanes * 8, staging(pl.ppc), pl.cs, as_stream(stream), pre, P, F, c_prev, g1, b1, g2, b2,
+                        stats1, stats2, forget_bias, s, dc_next, dpre, dc_prev, dg1, db1, dg2, db2, pl.cs, pl.ppc);
 }
 
 }  // namespace vp
