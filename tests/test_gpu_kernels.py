@@ -441,7 +441,7 @@ def test_flow_apply_fwd_bwd(L):
 
 
 # ------------------------------------------------------------------ slab-mapped plane kernels (csrc/planes.cu)
-@pytest.mark.parametrize('N,P,C', [(3, 64, 32), (2, 256, 64), (32, 1024, 32), (4, 4096, 32), (2, 16, 256), (5, 1024, 128)])
+@pytest.mark.parametrize('N,P,C', [(3, 64, 32), (2, 256, 64), (32, 1024, 32), (4, 4096, 32), (32, 4096, 32), (2, 16, 256), (5, 1024, 128)])
 def test_slab_instance_norm_fwd_bwd(L, N, P, C):
     """Shapes of the model's instance norms (32-channel 64x64 / 32x32 planes ... 256-channel 4x4) on the cluster / DSMEM kernels:
     an input with a large mean (5 sigma) checks the shifted one-pass variance; two gradient sources, strided destination."""
@@ -465,7 +465,7 @@ def test_slab_instance_norm_fwd_bwd(L, N, P, C):
     close(db, gb, 3e-5, 'slab inorm dbeta')
 
 
-@pytest.mark.parametrize('N,P,Fl', [(32, 1024, 32), (6, 256, 64), (5, 64, 128), (2, 1024, 64), (3, 16, 256)])
+@pytest.mark.parametrize('N,P,Fl', [(32, 1024, 32), (6, 256, 64), (32, 256, 64), (5, 64, 128), (32, 64, 128), (2, 1024, 64), (3, 16, 256)])
 def test_slab_lstm_gates_fwd_bwd(L, N, P, Fl):
     pre, c0 = rnd(N, P, 4 * Fl) + 0.8, rnd(N, P, Fl, seed=1)
     g1, b1, g2, b2 = rnd(4 * Fl, seed=2) * 0.3 + 1, rnd(4 * Fl, seed=3) * 0.1, rnd(Fl, seed=4) * 0.3 + 1, rnd(Fl, seed=5) * 0.1

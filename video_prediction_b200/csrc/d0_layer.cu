@@ -188,6 +188,7 @@ __global__ void __launch_bounds__(192, 1) d0_fwd_kernel(const __grid_constant__ 
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   __shared__ uint64_t full_bar[2], empty_bar[2], acc_full[kF0Acc], acc_empty[kF0Acc];
   __shared__ uint32_t tmem_base_smem;
+  __shared__ __align__(16) float stage[4][32][36];                  // epilogue transpose tiles (one per epilogue warp)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr int kWBytes = 18 * 1024;                                  // B operand: [row 9][k-step 2][32 n x 8 k = 1 KB]
   if (static_cast<int>(blockIdx.x) >= a.items) return;
@@ -293,18 +294,26 @@ __global__ void __launch_bounds__(192, 1) d0_fwd_kernel(const __grid_constant__ 
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&acc_empty[acc]);
-        const int p = tile * 128 + q * 32 + lane;
-        const int line = p / a.pitch, i = p - line * a.pitch;
-        if (line < a.L && i < a.W) {
-          float4* o = reinterpret_cast<float4*>(obase + (static_cast<long long>(line) * a.W + i) * 32);
+        // bias + leaky relu, then through a per-warp shared tile so that every store instruction writes 512 contiguous bytes
+        // (a lane owns one voxel = 128 B; storing straight from the registers touches 32 different lines per instruction)
+        float (*st)[36] = stage[q];
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            float r4[4];
+        for (int j = 0; j < 32; j += 4) {
+          float r4[4];
 #pragma unroll
-            for (int c = 0; c < 4; ++c) { const float u = v[j + c] + bv[j + c]; r4[c] = fmaxf(u, a.alpha * u); }
-            o[j >> 2] = make_float4(r4[0], r4[1], r4[2], r4[3]);
-          }
+          for (int c = 0; c < 4; ++c) { const float u = v[j + c] + bv[j + c]; r4[c] = fmaxf(u, a.alpha * u); }
+          *reinterpret_cast<float4*>(&st[lane][j]) = make_float4(r4[0], r4[1], r4[2], r4[3]);
         }
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int row = j * 4 + (lane >> 3), quad = lane & 7;
+          const int p = tile * 128 + q * 32 + row;
+          const int line = p / a.pitch, i = p - line * a.pitch;
+          if (line < a.L && i < a.W)
+            *reinterpret_cast<float4*>(obase + (static_cast<long long>(line) * a.W + i) * 32 + quad * 4) = *reinterpret_cast<const float4*>(&st[row][quad * 4]);
+        }
+        __syncwarp();
       }
     }
   }
@@ -405,7 +414,7 @@ extern "C" int vp_conv3d_c4_fwd_tc(const float* x, const float* w, const float* 
   }
   // tail: the last M tile's junk rows read up to 128 + 2 * pitch + 4 voxels past the third plane
   const size_t smem = 18 * 1024 + 2 * static_cast<size_t>(A.stage_bytes) + (128 + 2 * A.pitch + 8) * 16 + 1024;
-  if (smem > 227 * 1024) return set_error("vp_conv3d_c4_fwd_tc: tile does not fit in shared memory");
+  if (smem + 20 * 1024 > 227 * 1024) return set_error("vp_conv3d_c4_fwd_tc: tile does not fit in shared memory");
   static size_t configured = 0;
   if (smem > configured) {
     if (cudaFuncSetAttribute(d0_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess)
