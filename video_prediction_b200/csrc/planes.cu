@@ -204,6 +204,69 @@ __global__ void __launch_bounds__(512) slab_inorm_act_bwd_kernel(const float* __
   if (cs > 1) cg::this_cluster().sync();
 }
 
+// The same for CTAs that walk more positions than fit in registers (64x64 planes in clusters of 4 = 1024 positions per CTA, so
+// that all 128 CTAs of a 32-sample launch are resident at once): two passes over x and dy, the second one served by the L2.
+__global__ void __launch_bounds__(512) slab_inorm_act_bwd_loop_kernel(const float* __restrict__ x, int xs, SlabSrcs srcs, float* __restrict__ dx,
+                                                                      int dxs, int P, int C, const float* __restrict__ gamma,
+                                                                      const float* __restrict__ beta, const float* __restrict__ stats, int act,
+                                                                      float alpha, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                                                      int cs, int ppc) {
+  __shared__ float s_warp[kSlabMaxWarps * 8 * 8], s_part[8 * 8], s_tot[8 * 8];
+  const int q = threadIdx.x & 7, pl = threadIdx.x >> 3, lanes = blockDim.x >> 3;
+  const int n = blockIdx.z, c0 = blockIdx.y * 32 + q * 4;
+  const int p0 = blockIdx.x * ppc;
+  const float* xp = x + static_cast<long long>(n) * P * xs + c0;
+  float m[4], r[4], g[4], b[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    m[i] = stats[(static_cast<long long>(n) * C + c0 + i) * 2];
+    r[i] = stats[(static_cast<long long>(n) * C + c0 + i) * 2 + 1];
+    g[i] = gamma[c0 + i];
+    b[i] = beta[c0 + i];
+  }
+  auto load = [&](long long p, float* xh, float* dyp) {
+    const float4 xv = *reinterpret_cast<const float4*>(xp + p * xs);
+    float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int sI = 0; sI < srcs.count; ++sI) {
+      const float4 t = *reinterpret_cast<const float4*>(srcs.ptr[sI] + (static_cast<long long>(n) * P + p) * srcs.stride[sI] + c0);
+      d.x += t.x; d.y += t.y; d.z += t.z; d.w += t.w;
+    }
+    const float xv4[4] = {xv.x, xv.y, xv.z, xv.w}, dv[4] = {d.x, d.y, d.z, d.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      xh[i] = (xv4[i] - m[i]) * r[i];
+      dyp[i] = dv[i] * p_act_grad(g[i] * xh[i] + b[i], act, alpha);
+    }
+  };
+  float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
+  for (int l = pl; l < ppc; l += lanes) {
+    float xh[4], dyp[4];
+    load(p0 + l, xh, dyp);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { s[i] += dyp[i]; s[4 + i] += dyp[i] * xh[i]; }
+  }
+  slab_reduce<8>(s, s_warp, s_part, s_tot, cs);
+  if (blockIdx.x == 0 && pl == 0) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      atomicAdd(dbeta + c0 + i, s[i]);
+      atomicAdd(dgamma + c0 + i, s[4 + i]);
+    }
+  }
+  const float inv = 1.f / P;
+  float* dp = dx + static_cast<long long>(n) * P * dxs + c0;
+#pragma unroll 4
+  for (int l = pl; l < ppc; l += lanes) {
+    float xh[4], dyp[4], o[4];
+    load(p0 + l, xh, dyp);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) o[i] = r[i] * g[i] * (dyp[i] - s[i] * inv - xh[i] * s[4 + i] * inv);
+    *reinterpret_cast<float4*>(dp + static_cast<long long>(p0 + l) * dxs) = make_float4(o[0], o[1], o[2], o[3]);
+  }
+  if (cs > 1) cg::this_cluster().sync();
+}
+
 // ------------------------------------------------------------------------------------------------ ConvLSTM gates forward
 // pre [N,P,4F] (i,j,f,o); i,j,f,o = IN(pre)*g1+b1 ; c' = c*sig(f+fb) + sig(i)*tanh(j) ; cn = IN(c')*g2+b2 ; h = tanh(cn)*sig(o)
 template <int ITERS, int THREADS = 256>
@@ -621,18 +684,26 @@ int slab_inorm_act_bwd(const float* x, int xs, const float* const* dy, const int
       default: return nullptr;
     }
   };
+  // dx may alias one of the gradient sources only in the register-resident kernels (everything is read before anything is written)
+  bool aliased = false;
+  for (int i = 0; i < num_dy; ++i) aliased = aliased || dy[i] == dx;
   SlabPlan pl;
   if (!plan_slab(P, static_cast<long long>(C / 32) * n, 64, 1024.0,
-                 [&](int, int lanes, int iters, const void** kern, int* threads, size_t* smem) {
+                 [&](int ppc, int lanes, int iters, const void** kern, int* threads, size_t* smem) {
                    K kk = pick(iters);
-                   *kern = reinterpret_cast<const void*>(kk); *threads = lanes * 8; *smem = 0;
-                   return kk != nullptr;
+                   *threads = lanes * 8; *smem = 0;
+                   if (kk) { *kern = reinterpret_cast<const void*>(kk); return true; }
+                   *kern = reinterpret_cast<const void*>(slab_inorm_act_bwd_loop_kernel);
+                   return !aliased && ppc <= 2048;
                  }, &pl)) return 1;
   SlabSrcs s;
   s.count = num_dy;
   for (int i = 0; i < 4; ++i) { s.ptr[i] = i < num_dy ? dy[i] : nullptr; s.stride[i] = i < num_dy ? dy_cs[i] : 0; }
   dim3 grid(pl.cs, C / 32, n);
   K k = pick(pl.iters);
+  if (!k)
+    return launch_cluster(slab_inorm_act_bwd_loop_kernel, grid, pl.lanes * 8, 0, pl.cs, as_stream(stream), x, xs, s, dx, dxs, P, C, gamma, beta,
+                          stats, act, alpha, dgamma, dbeta, pl.cs, pl.ppc);
   return launch_cluster(k, grid, pl.lanes * 8, 0, pl.cs, as_stream(stream), x, xs, s, dx, dxs, P, C, gamma, beta, stats, act, alpha, dgamma,
                         dbeta, pl.cs);
 }
