@@ -304,6 +304,19 @@ def test_clip_gather_scatter(L):
     assert torch.equal(dv[1:4, 2], video[1:4, 2]) and float(dv[:, :2].abs().sum()) == 0.0
 
 
+@pytest.mark.parametrize('rows,C', [(1000, 32), (77, 64), (513, 128), (9, 256)])
+def test_cosine_distance_vectorised_shapes(L, rows, C):
+    """The discriminator feature widths: 32 / 64 / 128 channels take the float4 kernel (8 / 16 / 32 lanes per row), 256 the generic one."""
+    a, b = rnd(rows, C), rnd(rows, C, seed=1)
+    da = torch.full_like(a, 0.25)                                # accumulates
+    out = torch.zeros(1, device='cuda')
+    L.cosine_distance(a, b, da, rows, C, 3.0, out)
+    ad = a.double().requires_grad_(True)
+    ref = O.cosine_distance(ad, b.double())
+    close(out, ref.reshape(1), 1e-5, 'cosine distance')
+    close(da - 0.25, torch.autograd.grad(3.0 * ref, ad)[0], 1e-6, 'cosine distance grad')
+
+
 def test_conv3d_c4_cuda_core_first_discriminator_layer(L):
     N, D, H, W, C = 2, 5, 16, 12, 3
     x = torch.zeros(N, D, H, W, 4, device='cuda')

@@ -2,6 +2,8 @@
 // small LSTM, pooling) + losses + fused TF-Adam.  Same layout conventions as elementwise.cu.
 // Parameter gradients are accumulated with atomics into zero-initialised flat gradient buffers
 // (BPTT sums over timesteps, savp_model.py unrolls share variables).
+#include <cstdint>
+
 #include "common.h"
 #include "ptx.cuh"
 
@@ -755,6 +757,59 @@ __global__ void __launch_bounds__(256) cosine_distance_kernel(const float* __res
   }
 }
 
+// The same with LPR lanes per row holding one float4 each (C = 4 * LPR <= 128): a and b are read once, every access is 16 bytes.
+template <int LPR>
+__global__ void __launch_bounds__(256) cosine_distance_vec_kernel(const float* __restrict__ a, const float* __restrict__ b,
+                                                                  float* __restrict__ da, long long rows, float inv_rows, float gscale,
+                                                                  float* __restrict__ out) {
+  constexpr int C = 4 * LPR;
+  const int sub = threadIdx.x % LPR;
+  const long long row = (static_cast<long long>(blockIdx.x) * 256 + threadIdx.x) / LPR;
+  const bool live = row < rows;
+  float4 av = make_float4(0.f, 0.f, 0.f, 0.f), bv = av;
+  if (live) {
+    av = *reinterpret_cast<const float4*>(a + row * C + 4 * sub);
+    bv = *reinterpret_cast<const float4*>(b + row * C + 4 * sub);
+  }
+  float na = av.x * av.x + av.y * av.y + av.z * av.z + av.w * av.w;
+  float nb = bv.x * bv.x + bv.y * bv.y + bv.z * bv.z + bv.w * bv.w;
+#pragma unroll
+  for (int o = LPR / 2; o > 0; o >>= 1) {
+    na += __shfl_xor_sync(0xffffffffu, na, o);
+    nb += __shfl_xor_sync(0xffffffffu, nb, o);
+  }
+  na = sqrtf(na); nb = sqrtf(nb);
+  const float ia = 1.f / (na + 1e-10f), ib = 1.f / (nb + 1e-10f);
+  const float d[4] = {av.x * ia - bv.x * ib, av.y * ia - bv.y * ib, av.z * ia - bv.z * ib, av.w * ia - bv.w * ib};
+  float s = d[0] * d[0] + d[1] * d[1] + d[2] * d[2] + d[3] * d[3];
+  float dotad = av.x * d[0] + av.y * d[1] + av.z * d[2] + av.w * d[3];
+#pragma unroll
+  for (int o = LPR / 2; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    dotad += __shfl_xor_sync(0xffffffffu, dotad, o);
+  }
+  if (live && da) {
+    const float coef = (na > 0.f) ? dotad * ia * ia / na : 0.f;
+    const float k = gscale * inv_rows;
+    float4* dp = reinterpret_cast<float4*>(da + row * C + 4 * sub);
+    float4 o = *dp;
+    o.x += k * (d[0] * ia - coef * av.x); o.y += k * (d[1] * ia - coef * av.y);
+    o.z += k * (d[2] * ia - coef * av.z); o.w += k * (d[3] * ia - coef * av.w);
+    *dp = o;
+  }
+  float acc = (live && sub == 0) ? 0.5f * s * inv_rows : 0.f;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  __shared__ float red[8];
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < 8; ++i) t += red[i];
+    atomicAdd(out, t);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // fused TF-Adam over a flat parameter buffer (tf.train.AdamOptimizer, epsilon-hat form):
 //   lr_t = lr*sqrt(1-b2^t)/(1-b1^t) ; m = b1 m + (1-b1) g ; v = b2 v + (1-b2) g^2 ; p -= lr_t m/(sqrt(v)+eps)
@@ -963,6 +1018,15 @@ extern "C" int vp_kl_loss(const float* mu, const float* lss, int rows, int nz, f
 
 extern "C" int vp_cosine_distance(const float* a, const float* b, float* da, long long rows, int c, float grad_scale, float* out,
                                   vp_stream_t stream) {
+  const bool aligned = ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(da)) & 15) == 0;
+  if (aligned && (c == 32 || c == 64 || c == 128)) {
+    const int lpr = c / 4;
+    const unsigned blocks = static_cast<unsigned>((rows * lpr + 255) / 256);
+    if (lpr == 8) cosine_distance_vec_kernel<8><<<blocks, 256, 0, as_stream(stream)>>>(a, b, da, rows, 1.f / rows, grad_scale, out);
+    else if (lpr == 16) cosine_distance_vec_kernel<16><<<blocks, 256, 0, as_stream(stream)>>>(a, b, da, rows, 1.f / rows, grad_scale, out);
+    else cosine_distance_vec_kernel<32><<<blocks, 256, 0, as_stream(stream)>>>(a, b, da, rows, 1.f / rows, grad_scale, out);
+    return check_launch("cosine_distance_vec_kernel");
+  }
   cosine_distance_kernel<<<static_cast<unsigned>((rows + 7) / 8), 256, 0, as_stream(stream)>>>(a, b, da, rows, c, 1.f / rows,
                                                                                               grad_scale, out);
   return check_launch("cosine_distance_kernel");

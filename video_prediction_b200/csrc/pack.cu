@@ -84,13 +84,17 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, int kd, int kh,
 // All weight tensors of an optimizer in ONE launch (the generator repacks ~60 small tensors after every Adam step: 60
 // launches of a few microseconds each): a device table of jobs, each owning the blocks [block_begin, next block_begin).
 __global__ void pack_weights_batch_kernel(const vp_pack_job* __restrict__ jobs, int njobs) {
-  int lo = 0, hi = njobs - 1;
+  __shared__ vp_pack_job j;                                      // one table lookup per block, not per thread
   const int b = static_cast<int>(blockIdx.x);
-  while (lo < hi) {                                              // last job with block_begin <= b
-    const int mid = (lo + hi + 1) >> 1;
-    if (jobs[mid].block_begin <= b) lo = mid; else hi = mid - 1;
+  if (threadIdx.x == 0) {
+    int lo = 0, hi = njobs - 1;
+    while (lo < hi) {                                            // last job with block_begin <= b
+      const int mid = (lo + hi + 1) >> 1;
+      if (jobs[mid].block_begin <= b) lo = mid; else hi = mid - 1;
+    }
+    j = jobs[lo];
   }
-  const vp_pack_job j = jobs[lo];
+  __syncthreads();
   const long long idx = static_cast<long long>(b - j.block_begin) * blockDim.x + threadIdx.x;
   const int kpad = j.kc * 32;
   const int taps = j.kind == VP_WKIND_POOLED ? (j.kh + 1) * (j.kw + 1) : (j.kind == VP_WKIND_UPSAMPLED ? (j.kh + 3) * (j.kw + 3) : j.kd * j.kh * j.kw);
