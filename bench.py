@@ -183,20 +183,25 @@ def run_reference(args):
 
 def ncu_traffic():
     """DRAM traffic of the dominant kernel per launch (dram__bytes_read.sum + dram__bytes_write.sum) from the committed
-    `ncu --set full` capture of the lstm_h0 gate convolution (profiles/r01_ncu_full_final_summary.json), next to the
-    algorithmic bytes of that launch (input + packed weights read, gate pre-activations written)."""
+    `ncu --set full` capture of the lstm_h0 gate convolution (profiles/r02_ncu_full_summary.json, tests/ncu_capture_r02.sh),
+    next to the algorithmic bytes of that launch (input + packed weights read, gate pre-activations written)."""
     out = dict(traffic=None)
-    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'profiles', 'r01_ncu_full_final_summary.json')
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'profiles', 'r02_ncu_full_summary.json')
+
+    def mb(v):
+        num, unit = v.split()[:2]
+        return float(num) * {'byte': 1.0, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}[unit]
     try:
         with open(path) as f:
-            caps = json.load(f)['captures']['gate_r01b']
-        c = [x for x in caps if x.get('grid') == '148'][0]      # lstm_h0: 256 pixel tiles on a persistent grid of 148
-        out['traffic'] = (float(c['dram_bytes_read']) + float(c['dram_bytes_write'])) * 1e6
-        out['traffic_unit'] = 'bytes per launch (lstm_h0 gate conv, ncu --set full)'
+            caps = json.load(f)['captures']['r02_engine_kernels.ncu-rep']
+        c = [x for x in caps if 'igemm_halo' in x['kernel'] and x['grid'].startswith('(128,')][0]   # lstm_h0: 128 M = 256 tiles
+        out['traffic'] = mb(c['dram_bytes_read']) + mb(c['dram_bytes_write'])
+        out['traffic_unit'] = 'bytes per launch (lstm_h0 gate conv, halo mode, ncu --set full)'
         out['traffic_algorithmic'] = 32 * 1024 * 72 * 4 + 25 * 128 * 96 * 4 + 32 * 1024 * 128 * 4
         out['traffic_note'] = ('reads = input + weights once (no re-reads from HBM); the 16.8 MB of gate pre-activations stay in the '
                                '126 MB L2 for the gate kernel that follows, so almost nothing is written back')
-        out['tensor_pipe_active_pct'] = float(c['tensor_pipe_active_pct_of_active'])
+        out['tensor_pipe_active_pct'] = float(c['tensor_pipe_active_pct_of_active'].split()[0])
+        out['l2_to_sm_bytes'] = mb(c['l1tex__m_xbar2l1tex_read_bytes.sum'])
     except Exception:       # noqa: BLE001  (profile summary absent: leave traffic null)
         pass
     return out

@@ -113,9 +113,11 @@ def set_tf32_emulation(mode, exempt=(), weight_mode='rna'):
     tensor core reads raw from fp32 memory: None | 'trunc' (drop the low 13 mantissa bits) | 'rna' (round to nearest,
     ties away).  weight_mode: quantisation of the filter operand of forward and dgrad -- the CUDA path rounds weights
     with cvt.rna.tf32.f32 when it packs them (csrc/pack.cu), independent of what the tensor core does.
+    'bf16' (round to nearest even at 8 significant bits) is not a mode of the CUDA path: it is what kind::f16 operands would
+    see, used by tests/measure_bf16_tolerance.py to show why the engine multiplies in TF32.
     exempt: iterable of substrings; a conv called with a `tag` containing one of them stays exact
     (layers the CUDA path runs on fp32 CUDA cores)."""
-    assert mode in (None, 'trunc', 'rna') and weight_mode in ('trunc', 'rna')
+    assert mode in (None, 'trunc', 'rna', 'bf16') and weight_mode in ('trunc', 'rna', 'bf16')
     _TF32['mode'] = mode
     _TF32['exempt'] = tuple(exempt)
     _TF32['weight_mode'] = weight_mode
@@ -127,6 +129,8 @@ def tf32_quantize(x, mode=None):
         return x
     x32 = x.detach().to(torch.float32).contiguous()
     xi = x32.view(torch.int32)
+    if mode == 'bf16':
+        return x32.to(torch.bfloat16).to(torch.float32).to(x.dtype)
     if mode == 'rna':
         xi = (xi + 0x1000) & ~0x1FFF
     else:
