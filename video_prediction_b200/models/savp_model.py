@@ -455,7 +455,7 @@ class SAVPVideoPredictionModel(TrainMixin, VideoPredictionModel):
         for name, v in values.items():
             if name not in self.params:
                 continue        # e.g. discriminator variables offered to a test-mode model
-            t = torch.as_tensor(np.array(v.detach().cpu() if torch.is_tensor(v) else v, dtype=np.float32))
+            t = v.detach().to(dtype=torch.float32, device='cpu').clone() if torch.is_tensor(v) else torch.from_numpy(np.array(v, dtype=np.float32))
             if tuple(t.shape) != tuple(self.params[name].shape):
                 raise ValueError('shape mismatch for %s: %s vs %s' % (name, tuple(t.shape), tuple(self.params[name].shape)))
             self.params[name].copy_(t.to(self.device))
