@@ -76,4 +76,55 @@ L.lstm_gates_bwd(pre, N, P, Fl, c0, g1, b1, g2, b2, s1, s2, [(h.data_ptr(), Fl)]
 torch.cuda.synchronize()
 print('slab gates fwd/bwd: finite %s' % bool(torch.isfinite(dpre).all() and torch.isfinite(h).all()))
 ok &= bool(torch.isfinite(dpre).all() and torch.isfinite(h).all())
+# full-batch plane shapes: the planner picks clusters of 4 with 256 / 1024 positions per CTA (gates backward re-reading its
+# pre-activations, 512-thread gates forward, two-pass instance-norm backward)
+N = 32
+pre, c0 = rnd(N, P, 4 * Fl), rnd(N, P, Fl, seed=3)
+c1, h = torch.zeros(N, P, Fl, device='cuda'), torch.zeros(N, P, Fl, device='cuda')
+s1, s2 = torch.zeros(N, 4 * Fl, 2, device='cuda'), torch.zeros(N, Fl, 2, device='cuda')
+L.lstm_gates_fwd(pre, N, P, Fl, c0, g1, b1, g2, b2, c1, [(h.data_ptr(), Fl)], s1, s2)
+dpre, dc0 = torch.zeros_like(pre), torch.zeros_like(c0)
+L.lstm_gates_bwd(pre, N, P, Fl, c0, g1, b1, g2, b2, s1, s2, [(h.data_ptr(), Fl)], None, dpre, dc0, dgs[0], dgs[1], dgs[2], dgs[3])
+x4, dy4 = rnd(N, 4096, C) + 1.0, rnd(N, 4096, C, seed=5)
+y4, st4, dx4 = torch.zeros_like(x4), torch.zeros(N, C, 2, device='cuda'), torch.zeros_like(x4)
+L.inorm_act(x4.data_ptr(), C, y4.data_ptr(), C, N, 4096, C, g, b, L.ACT_RELU, 0.0, st4)
+dg4, db4 = torch.zeros(C, device='cuda'), torch.zeros(C, device='cuda')
+L.inorm_act_bwd(x4.data_ptr(), C, [(dy4.data_ptr(), C)], dx4.data_ptr(), C, N, 4096, C, g, b, st4, L.ACT_RELU, 0.0, dg4, db4)
+torch.cuda.synchronize()
+fin = bool(torch.isfinite(dpre).all() and torch.isfinite(h).all() and torch.isfinite(dx4).all())
+print('full-batch slab kernels (gates fwd/bwd 32x1024x32, instance norm fwd/bwd 32x4096x32): finite %s' % fin)
+ok &= fin
+# first discriminator layer on the tensor cores (csrc/d0_layer.cu) against the CUDA-core kernels
+n, d, hh, ww, ci = 2, 3, 8, 64, 3
+xv = torch.zeros(n, d, hh, ww, 4, device='cuda')
+xv[..., :ci] = torch.rand(n, d, hh, ww, ci, device='cuda')
+wv, bv, sig = rnd(3, 3, 3, ci, 32, seed=7, scale=0.2), rnd(32, seed=8), torch.tensor([1.3], device='cuda')
+o1, o2 = torch.zeros(n, d, hh, ww, 32, device='cuda'), torch.zeros(n, d, hh, ww, 32, device='cuda')
+L.conv3d_c4_fwd_tc(xv, wv, sig, bv, o1, n, d, hh, ww, ci, 0.1)
+L.conv3d_c4_fwd(xv, wv, sig, bv, o2, n, d, hh, ww, ci, 0.1)
+gw1, gw2 = torch.zeros(27 * ci * 32, device='cuda'), torch.zeros(27 * ci * 32, device='cuda')
+L.check(L.lib().vp_conv3d_c4_wgrad_tc(L.ptr(xv), L.ptr(o2), L.ptr(gw1), n, d, hh, ww, ci, L.stream_ptr()))
+L.check(L.lib().vp_conv3d_c4_wgrad(L.ptr(xv), L.ptr(o2), L.ptr(gw2), n, d, hh, ww, ci, L.stream_ptr()))
+torch.cuda.synchronize()
+e1 = (o1 - o2).abs().max().item() / o2.abs().max().item()
+e2 = ((gw1 - gw2).norm() / gw2.norm()).item()
+print('first layer on tensor cores vs CUDA cores: forward rel %.1e, weight gradient rel L2 %.1e' % (e1, e2))
+ok &= e1 < 3e-3 and e2 < 3e-3
+# table-driven weight packing, register-tiled wide dense layer, float4 cosine distance
+wq = rnd(1, 5, 5, 72, 128, seed=9, scale=0.05)[0]
+ref, n_pad, kc = L.pack_weights(wq, (1, 5, 5), 72, 128, L.WKIND_PLAIN, L.WLAYOUT_FWD)
+outp = torch.zeros_like(ref)
+L.PackPlan([(wq, (1, 5, 5), 72, 128, L.WKIND_PLAIN, L.WLAYOUT_FWD, None, None, None, outp)]).run()
+xd_, wd_, bd_ = rnd(32, 2048), rnd(2048, 100, seed=1, scale=0.05), rnd(100, seed=2)
+yd = torch.zeros(32, 100, device='cuda')
+L.dense_fwd(xd_, 2048, wd_, bd_, yd, 100, 32, 2048, 100, k_splits=32)
+dxd, dwd, dbd = torch.zeros_like(xd_), torch.zeros_like(wd_), torch.zeros_like(bd_)
+L.dense_bwd(xd_, 2048, wd_, yd, 100, 32, 2048, 100, dx=dxd, dx_stride=2048, dw=dwd, dbias=dbd)
+ca, cb = rnd(1000, 32), rnd(1000, 32, seed=1)
+cda, cout_ = torch.zeros_like(ca), torch.zeros(1, device='cuda')
+L.cosine_distance(ca, cb, cda, 1000, 32, 1.0, cout_)
+torch.cuda.synchronize()
+e3 = (yd.double() - (xd_.double() @ wd_.double() + bd_.double())).abs().max().item()
+print('batched pack equal %s, wide dense max err %.1e, cosine distance finite %s' % (bool(torch.equal(outp, ref)), e3, bool(torch.isfinite(cda).all())))
+ok &= bool(torch.equal(outp, ref)) and e3 < 1e-3 and bool(torch.isfinite(cda).all())
 print('SANITIZE TARGET %s' % ('OK' if ok else 'MISMATCH'))

@@ -205,6 +205,11 @@ __global__ void __launch_bounds__(192, 1) d0_fwd_kernel(const __grid_constant__ 
       if (dx < 3 && ci < a.CI) v = round_tf32(__ldg(a.w + ((r * 3 + dx) * a.CI + ci) * 32 + n) / sigma);
       wb[blk * 256 + (n >> 3) * 64 + (kk >> 2) * 32 + (n & 7) * 4 + (kk & 3)] = v;
     }
+    // The zero-weight K column (dx = +2) of the LAST voxel of a plane reads one voxel past what TMA writes (alignment gap, the
+    // next stage before its first load, or the tail): 0 x garbage must not be 0 x NaN, so the tile area starts out as zeros.
+    float4* tiles = reinterpret_cast<float4*>(smem + kWBytes);
+    const int n16 = (2 * a.stage_bytes + (128 + 2 * a.pitch + 8) * 16) / 16;
+    for (int i = threadIdx.x; i < n16; i += blockDim.x) tiles[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     fence_proxy_async();
   }
   if (threadIdx.x == 0) {
