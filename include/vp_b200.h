@@ -237,7 +237,6 @@ int vp_flow_apply_bwd(const float* image, const float* flows, int flows_cstride,
 int vp_pixel_loss(const float* pred, int pred_cstride, const float* target, int target_cstride, float* dpred,
                   int dpred_cstride, long long rows, int c, int mode /*bit 0: 0 = L1, 1 = L2; bit 1: dpred += instead of =*/, long long mean_count,
                   float grad_scale, float* out, vp_stream_t stream);
-int vp_lsgan_loss(const float* logits, float label, int n, float grad_scale, float* dlogits, float* out, vp_stream_t stream);
 /* losses.gan_loss (losses.py:29-54) for labels in {0,1}: kind 0 LSGAN, 1 GAN (sigmoid cross-entropy), 2 SNGAN (softplus) */
 int vp_gan_loss(const float* logits, float label, int n, float grad_scale, int kind, float* dlogits, float* out,
                 vp_stream_t stream);

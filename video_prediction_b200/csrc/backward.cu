@@ -668,20 +668,6 @@ __global__ void __launch_bounds__(256) pixel_loss_kernel(const float* __restrict
   bsum<1>(s, scratch);
   if (threadIdx.x == 0) atomicAdd(out, s[0] * inv_count);
 }
-// LSGAN: mean (logit - label)^2 (losses.gan_loss), logits [n]; dlogits = gscale*2*(l-label)/n
-__global__ void lsgan_loss_kernel(const float* __restrict__ logits, float label, int n, float gscale, float* __restrict__ dlogits,
-                                  float* __restrict__ out) {
-  float s = 0.f;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    const float d = logits[i] - label;
-    s += d * d;
-    if (dlogits) dlogits[i] = gscale * 2.f * d / n;
-  }
-  __shared__ float scratch[32];
-  float v[1] = {s};
-  bsum<1>(v, scratch);
-  if (threadIdx.x == 0) atomicAdd(out, v[0] / n);
-}
 // losses.gan_loss for labels in {0, 1}: kind 0 = LSGAN mean (l - y)^2; kind 1 = GAN = mean sigmoid-cross-entropy(l, y);
 // kind 2 = SNGAN = mean softplus(l) (y = 0) / softplus(-l) (y = 1) -- numerically the same function as kind 1 for y in {0,1}.
 // dlogits = gscale * d value / d logits.
@@ -995,12 +981,6 @@ extern "C" int vp_pixel_loss(const float* pred, int pred_cstride, const float* t
   pixel_loss_kernel<<<blocks, 256, 0, as_stream(stream)>>>(pred, pred_cstride, target, target_cstride, dpred, dpred_cstride, rows, c,
                                                            mode, inv, grad_scale, out);
   return check_launch("pixel_loss_kernel");
-}
-
-extern "C" int vp_lsgan_loss(const float* logits, float label, int n, float grad_scale, float* dlogits, float* out,
-                             vp_stream_t stream) {
-  lsgan_loss_kernel<<<1, 256, 0, as_stream(stream)>>>(logits, label, n, grad_scale, dlogits, out);
-  return check_launch("lsgan_loss_kernel");
 }
 
 extern "C" int vp_gan_loss(const float* logits, float label, int n, float grad_scale, int kind, float* dlogits, float* out,

@@ -32,7 +32,6 @@ constexpr int kMaxMaps = 8;
 constexpr int kStagesFwd = 4;
 constexpr int kKsubMinIters = 48;  // k-iterations per CTA from which two k-chunks per stage pay off
 constexpr int kMaxStagesFwd = 6;
-constexpr int kStagesWg = 3;
 constexpr int kWgPix = 64;  // pixels (GEMM-K) per wgrad pipeline stage
 
 struct Tap {

@@ -230,11 +230,6 @@ def exact_mode():
     return os.environ.get('VP_EXACT', '0') == '1'
 
 
-def engine_choices():
-    """geometry signature -> engine chosen by the autotuner so far (for reports)."""
-    return dict(_ENGINE_CHOICE)
-
-
 def conv_wgrad(x_view, dy_view, g, dwpacked, n_pad, kc, split_k=1):
     if 'wgrad' in _SKIP:
         return
@@ -506,13 +501,6 @@ def sample_z_bwd(mu, lss, eps, dz, dmu, dlss, total, kl_scale_dev):
 def pixel_loss(pred_addr, pred_cs, target_addr, target_cs, dpred_addr, dpred_cs, rows, c, mode, mean_count, grad_scale, out):
     check(lib().vp_pixel_loss(addr(pred_addr), pred_cs, addr(target_addr), target_cs, addr(dpred_addr or 0), dpred_cs,
                               C.c_longlong(rows), c, mode, C.c_longlong(mean_count), _f(grad_scale), ptr(out), stream_ptr()))
-
-
-def lsgan_loss(logits, label, n, grad_scale, dlogits, out):
-    check(lib().vp_lsgan_loss(ptr(logits), _f(label), n, _f(grad_scale), ptr(dlogits), ptr(out), stream_ptr()))
-
-
-GAN_KINDS = {'LSGAN': 0, 'GAN': 1, 'SNGAN': 2}
 
 
 def gan_loss(logits, label, n, grad_scale, kind, dlogits, out):
