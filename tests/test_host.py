@@ -197,3 +197,34 @@ def test_data_parallel_plumbing_gloo_world2():
     from video_prediction_b200 import dp
     with pytest.raises(ValueError):
         dp.shard_batch(10, 0, 4)
+
+
+def test_no_undefined_global_names_in_the_host_layer():
+    """A cheap static check (no GPU needed to hit a NameError on a rarely taken path): every name loaded in the package's
+    modules, the scripts and bench.py is a builtin, an import, an argument or assigned somewhere in the same file."""
+    import ast
+    import builtins
+    import glob
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    files = glob.glob(os.path.join(root, 'video_prediction_b200', '**', '*.py'), recursive=True) + \
+        glob.glob(os.path.join(root, 'scripts', '*.py')) + [os.path.join(root, 'bench.py'), os.path.join(root, '__graft_entry__.py')]
+    bad = []
+    for path in files:
+        tree = ast.parse(open(path).read())
+        defined = set(dir(builtins)) | {'__file__', '__name__', '__doc__'}
+        for n in ast.walk(tree):
+            if isinstance(n, (ast.FunctionDef, ast.ClassDef)):
+                defined.add(n.name)
+            elif isinstance(n, ast.Import):
+                defined.update((a.asname or a.name).split('.')[0] for a in n.names)
+            elif isinstance(n, ast.ImportFrom):
+                defined.update(a.asname or a.name for a in n.names)
+            elif isinstance(n, ast.Name) and isinstance(n.ctx, (ast.Store, ast.Del)):
+                defined.add(n.id)
+            elif isinstance(n, ast.arg):
+                defined.add(n.arg)
+            elif isinstance(n, ast.ExceptHandler) and n.name:
+                defined.add(n.name)
+        bad += ['%s:%d %s' % (os.path.relpath(path, root), n.lineno, n.id) for n in ast.walk(tree)
+                if isinstance(n, ast.Name) and isinstance(n.ctx, ast.Load) and n.id not in defined]
+    assert not bad, bad

@@ -503,6 +503,9 @@ def pixel_loss(pred_addr, pred_cs, target_addr, target_cs, dpred_addr, dpred_cs,
                               C.c_longlong(rows), c, mode, C.c_longlong(mean_count), _f(grad_scale), ptr(out), stream_ptr()))
 
 
+GAN_KINDS = {'LSGAN': 0, 'GAN': 1, 'SNGAN': 2}
+
+
 def gan_loss(logits, label, n, grad_scale, kind, dlogits, out):
     check(lib().vp_gan_loss(ptr(logits), _f(label), n, _f(grad_scale), GAN_KINDS[kind], ptr(dlogits), ptr(out), stream_ptr()))
 
