@@ -209,7 +209,7 @@ def ncu_traffic():
 
 def time_gate_kernels(model, iters=3):
     """CUDA-event timing of the five ConvLSTM gate convolutions (one launch per timestep buffer, cycling through all
-    T-1 timesteps so consecutive launches touch different HBM lines; working set > L2)."""
+    T-1 timesteps so consecutive launches touch different HBM lines; working set > L2), replayed from a CUDA graph."""
     import torch
     flops, ms = 0.0, 0.0
     per_layer = []
@@ -223,14 +223,21 @@ def time_gate_kernels(model, iters=3):
         for t in range(S):
             conv.fwd(rin[t], gpre[t])
         torch.cuda.synchronize()
+        # the S launches are replayed from a CUDA graph: a 16 us kernel launched eagerly through ctypes is host-bound
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            for t in range(S):
+                conv.fwd(rin[t], gpre[t])
+        g.replay()
+        torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(iters):
-            for t in range(S):
-                conv.fwd(rin[t], gpre[t])
+            g.replay()
         e1.record()
         torch.cuda.synchronize()
         t_ms = e0.elapsed_time(e1) / (iters * S)
+        del g
         M = model.NB * d['h'] * d['w']
         fl = 2.0 * M * (4 * d['oc']) * (25 * conv.ci_ref)        # algorithmic: reference channel count, no padding
         per_layer.append(dict(layer='lstm_h%d' % li, M=M, N=4 * d['oc'], K=25 * conv.ci_ref, ms=t_ms, tflops=fl / t_ms / 1e9))
