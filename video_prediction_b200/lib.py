@@ -71,7 +71,9 @@ def tensor_view(t, c=None, c_off=0):
     else:
         n, d, h, w, ct = t.shape
     c = ct - c_off if c is None else c
-    return VpTensor(t.data_ptr() + 4 * c_off, n, d, h, w, c, ct)
+    v = VpTensor(t.data_ptr() + 4 * c_off, n, d, h, w, c, ct)
+    v._owner = t          # keeps the storage alive and lets the autotuner snapshot / restore an output it accumulates into
+    return v
 
 
 def geom(k, s=(1, 1, 1), p=(0, 0, 0), transposed=False):
@@ -146,15 +148,19 @@ def _conv_key(x_view, g, n_pad, kc, out_view, act, extra):
             out_view.c == out_view.cstride, g.kd, g.kh, g.kw, g.sd, g.sh, g.sw, g.pd, g.ph, g.pw, g.transposed, n_pad, kc, act, extra)
 
 
-def _pick_engine(key, call, idempotent):
+def _pick_engine(key, call, idempotent, out_view=None):
     """Both engines compute the same convolution; which one is faster depends on the geometry (plane size, taps per halo
-    group, N).  The first call of a geometry times both (3 launches each, CUDA events) and the winner is cached for the
-    process.  VP_HALO=0/1 or VP_AUTOTUNE=0 pin the engine; calls that accumulate into their output are never timed."""
+    group, N).  The first call of a geometry times both (CUDA-graph replays) and the winner is cached for the process.
+    VP_HALO=0/1 or VP_AUTOTUNE=0 pin the engine.  A call that accumulates into its output is timed on a snapshot: the output
+    tensor is cloned before and restored after (possible when the view was made by tensor_view), otherwise it is not timed."""
     choice = _ENGINE_CHOICE.get(key)
     if choice is not None:
         return choice
-    if os.environ.get('VP_AUTOTUNE', '1') == '0' or 'VP_HALO' in os.environ or not idempotent or torch.cuda.is_current_stream_capturing():
+    owner = getattr(out_view, '_owner', None)
+    if os.environ.get('VP_AUTOTUNE', '1') == '0' or 'VP_HALO' in os.environ or torch.cuda.is_current_stream_capturing() or \
+            (not idempotent and owner is None):
         return -1
+    snapshot = owner.clone() if not idempotent else None
     times = []
     for eng in (0, 1):
         check(lib().vp_conv_set_engine(eng))
@@ -176,6 +182,8 @@ def _pick_engine(key, call, idempotent):
         times.append(e0.elapsed_time(e1) * 3.0 / 16.0)      # keeps the unit of the log: milliseconds per 3 launches
         del g
     check(lib().vp_conv_set_engine(-1))
+    if snapshot is not None:
+        owner.copy_(snapshot)
     choice = 0 if times[0] <= times[1] else 1
     _ENGINE_CHOICE[key] = choice
     if os.environ.get('VP_AUTOTUNE_LOG'):
@@ -193,7 +201,7 @@ def conv_igemm(x_view, g, wpacked, n_pad, kc, out_view, bias=None, act=ACT_NONE,
                                   act, C.c_float(alpha), split_k, int(accumulate), stream_ptr()))
     # an explicit split_k > 1 adds atomically into a caller-cleared output: repeating the call (timing) would change it
     key = _conv_key(x_view, g, n_pad, kc, out_view, act, ('fwd', split_k))
-    eng = _pick_engine(key, call, not accumulate and split_k <= 1)
+    eng = _pick_engine(key, call, not accumulate and split_k <= 1, out_view if split_k <= 1 else None)
     check(lib().vp_conv_set_engine(eng))
     _profiled('igemm', _conv_flops(x_view, g, out_view), call, (key, eng))
     if eng >= 0:
@@ -209,7 +217,7 @@ def conv_igemm_actgrad(x_view, g, wpacked, n_pad, kc, out_view, act_output_addr,
                                           C.c_void_p(act_output_addr), C.c_void_p(addend_addr or 0), act, C.c_float(alpha),
                                           int(accumulate), stream_ptr()))
     key = _conv_key(x_view, g, n_pad, kc, out_view, act, ('actgrad', bool(addend_addr)))
-    eng = _pick_engine(key, call, not accumulate)
+    eng = _pick_engine(key, call, not accumulate, out_view)
     check(lib().vp_conv_set_engine(eng))
     _profiled('igemm', _conv_flops(x_view, g, out_view), call, (key, eng))
     if eng >= 0:
