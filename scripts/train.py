@@ -4,12 +4,14 @@ SAVP path.  Same flags, same options.json / dataset_hparams.json / model_hparams
 (global step, image/sec, d_loss / g_loss and their terms, learning rate), same checkpoint cadence -- no TensorFlow:
 `sess.run(train_op)` becomes `model.train_step(batch)`.
 
-    python scripts/train.py --input_dir none --dataset synthetic --model savp \
+    python scripts/train.py --input_dir data/bair --dataset bair --model savp \
         --model_hparams_dict hparams/bair_action_free/ours_savp/model_hparams.json --output_dir logs/savp
+    python scripts/train.py --input_dir none --dataset synthetic --model savp ...        (no input files)
     torchrun --nproc-per-node 8 scripts/train.py ... --model_hparams batch_size=128      (data parallel, global batch split)
 
-Outside the hot path: TFRecord datasets (`--dataset synthetic` is the one built), TensorBoard summaries
-(the *_summary_freq flags are accepted and inert), the long-sequence validation model."""
+Datasets: `bair` / `softmotion` and `kth` read the reference's TFRecords on the host (video_prediction_b200/datasets), `synthetic`
+generates videos.  Outside the hot path: TensorBoard summaries (the *_summary_freq flags are accepted and
+inert), the long-sequence validation model."""
 from __future__ import absolute_import, division, print_function
 
 import argparse
@@ -139,8 +141,6 @@ def main(argv=None):
         'sequence_length': train_dataset.hparams.sequence_length,
         'repeat': train_dataset.hparams.time_shift,
     })
-    if args.dataset in ('synthetic', 'SyntheticVideoDataset'):
-        hparams_dict['repeat'] = 1           # no time-shift augmentation on generated videos
     import torch
     if world > 1:
         torch.cuda.set_device(int(os.environ.get('LOCAL_RANK', '0')))

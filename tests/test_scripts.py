@@ -52,7 +52,7 @@ def test_dataset_registry_and_synthetic_batches():
     with pytest.raises(ValueError, match='Invalid dataset'):
         datasets.get_dataset_class('bogus')
     with pytest.raises(NotImplementedError):
-        datasets.get_dataset_class('bair')
+        datasets.get_dataset_class('google_robot')
     DS = datasets.get_dataset_class('synthetic')
     ds = DS('ignored', mode='val', num_epochs=1, seed=3, hparams='sequence_length=6,action_dim=4,num_examples=8')
     assert ds.hparams.long_sequence_length == 6 and ds.hparams.context_frames == 2
@@ -132,3 +132,35 @@ def test_train_three_steps_checkpoint_resume_and_generate(tmp_path):
         lo, av, hi = (em['eval_%s/%s' % (name, k)].mean(dim=1) for k in ('min', 'avg', 'max'))
         assert bool((lo <= av + 1e-6).all()) and bool((av <= hi + 1e-6).all()) and bool((hi > lo).any())
     assert bool((em['eval_mse/min'] >= 0).all()) and float(em['eval_ssim/max'].max()) <= 1.0
+
+
+@pytest.mark.gpu
+def test_train_on_bair_format_tfrecords_with_actions(tmp_path):
+    """scripts/train.py --dataset bair: TFRecords in the BAIR layout (one Example per trajectory, raw 64x64x3 frames,
+    4-d actions, 3-d states) -> host pipeline (datasets/video_datasets.py) -> action-conditioned SAVP training steps."""
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip('no CUDA device')
+    import train
+    from video_prediction_b200.datasets import tfrecord as R
+    rng = np.random.default_rng(0)
+    d = tmp_path / 'bair' / 'train'
+    d.mkdir(parents=True)
+    recs = []
+    for k in range(4):
+        base = rng.integers(0, 255, (64, 64, 3), dtype=np.uint8)
+        f = {}
+        for t in range(30):
+            f['%d/image_aux1/encoded' % t] = np.roll(base, (t, 2 * t), axis=(0, 1)).tobytes()
+            f['%d/endeffector_pos' % t] = rng.standard_normal(3).astype(np.float32)
+            if t < 29:
+                f['%d/action' % t] = rng.standard_normal(4).astype(np.float32)
+        recs.append(R.make_example(f))
+    R.write_records(str(d / 'traj_0_to_3.tfrecords'), recs)
+    out = str(tmp_path / 'run')
+    model = train.main(['--input_dir', str(tmp_path / 'bair'), '--dataset', 'bair', '--dataset_hparams', 'use_state=True,sequence_length=6',
+                        '--model', 'savp', '--output_dir', out, '--progress_freq', '1', '--save_freq', '0', '--seed', '2',
+                        '--model_hparams', 'batch_size=2,max_steps=2,clip_length=4,l1_weight=100.0,kl_weight=1.0,video_sn_gan_weight=0.1'])
+    assert model.global_step == 2 and np.isfinite(model.g_loss) and np.isfinite(model.d_loss)
+    assert model.hparams.repeat == 2 and model.hparams.sequence_length == 6          # time_shift of the BAIR dataset (train.py:160)
+    assert model.A == 4                                                              # actions reached the model

@@ -1,7 +1,9 @@
 """Dataset registry with the reference's surface (video_prediction/datasets/__init__.py:11-25).
 
-The TFRecord input pipelines (BAIR / KTH / ...; base_dataset.py:129-453) are OUTSIDE the B200 hot path:
-their names are registered and raise NotImplementedError.  `synthetic` is the dataset the hot path is measured on:
+The TFRecord input pipelines sit either side of the B200 hot path.  The two formats the BASELINE configs
+train on are read on the host without TensorFlow (`video_datasets.py`, `tfrecord.py`): BAIR robot pushing (`softmotion` /
+`bair`) and KTH (`kth`); the other registered names (JPEG-encoded or unused by any shipped config) raise
+NotImplementedError.  `synthetic` is the dataset the hot path is measured on:
 seeded videos of the shape the reference datasets deliver (`images` [B,T,H,W,C] f32 in [0,1], optional `actions`
 [B,T-1,A]; base_dataset.py:189), generated on the host, so `scripts/train.py --dataset synthetic` and
 `scripts/generate.py --dataset synthetic` run end to end without any input files."""
@@ -11,11 +13,14 @@ import numpy as np
 
 from ..hparams import HParams
 
+from .video_datasets import BaseVideoDataset, KTHVideoDataset, SoftmotionVideoDataset, VarLenFeatureVideoDataset, VideoDataset  # noqa: F401
+
 _OUT_OF_SCOPE = {
-    'google_robot': 'GoogleRobotVideoDataset', 'sv2p': 'SV2PVideoDataset', 'softmotion': 'SoftmotionVideoDataset',
-    'bair': 'SoftmotionVideoDataset', 'kth': 'KTHVideoDataset', 'ucf101': 'UCF101VideoDataset',
+    'google_robot': 'GoogleRobotVideoDataset', 'sv2p': 'SV2PVideoDataset', 'ucf101': 'UCF101VideoDataset',
     'cartgripper': 'CartgripperVideoDataset',
 }
+_TFRECORD = {'softmotion': SoftmotionVideoDataset, 'bair': SoftmotionVideoDataset, 'kth': KTHVideoDataset,
+             'SoftmotionVideoDataset': SoftmotionVideoDataset, 'KTHVideoDataset': KTHVideoDataset}
 
 
 class SyntheticVideoDataset(object):
@@ -90,7 +95,9 @@ class SyntheticVideoDataset(object):
 def get_dataset_class(dataset):
     if dataset in ('synthetic', 'SyntheticVideoDataset'):
         return SyntheticVideoDataset
+    if dataset in _TFRECORD:
+        return _TFRECORD[dataset]
     if dataset in _OUT_OF_SCOPE or dataset in _OUT_OF_SCOPE.values():
-        raise NotImplementedError('%s reads TFRecords: the input pipeline is outside the B200 hot path (SURVEY.md 8f-3); '
-                                  'use --dataset synthetic' % dataset)
+        raise NotImplementedError('%s is not built (SURVEY.md 8f-3 covers the BAIR and KTH formats); use --dataset bair | kth | synthetic'
+                                  % dataset)
     raise ValueError('Invalid dataset %s' % dataset)                        # datasets/__init__.py:24

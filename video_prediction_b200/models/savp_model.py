@@ -216,8 +216,9 @@ class SAVPVideoPredictionModel(TrainMixin, VideoPredictionModel):
                           ('context_images_background', False), ('generate_scratch_image', True),
                           ('dependent_mask', True), ('use_e_rnn', False), ('learn_prior', False),
                           ('learn_initial_state', False), ('ablation_conv_rnn_norm', False), ('ablation_rnn', False),
-                          ('use_rnn_z', True), ('joint_gan_optimization', False), ('use_same_discriminator', False),
-                          ('repeat', 1)):
+                          ('use_rnn_z', True), ('joint_gan_optimization', False), ('use_same_discriminator', False)):
+            # (`repeat` is accepted with any value: train.py sets it to the dataset's time_shift (train.py:160) and no model
+            #  code of the reference reads it, base_model.py:90-95)
             if getattr(hp, key) != want:
                 unsupported.append('%s=%r' % (key, getattr(hp, key)))
         if hp.transformation not in ('cdna', 'flow'):
