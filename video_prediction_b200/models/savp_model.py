@@ -582,7 +582,7 @@ class SAVPVideoPredictionModel(TrainMixin, VideoPredictionModel):
                     for name, arr in slots[slot].items():
                         flat, like = (self.g_flat, gbuf) if name.startswith('generator/') else (self.d_flat, dbuf)
                         if not name.endswith('/u'):
-                            self._view_of(like, flat, name).copy_(torch.from_numpy(np.ascontiguousarray(arr)).to(self.device))
+                            self._view_of(like, flat, name).copy_(torch.from_numpy(np.array(arr, order="C")).to(self.device))
             if self.mode == 'train' and adam_t is not None:
                 self.g_adam_t, self.d_adam_t = adam_t
 
