@@ -401,7 +401,7 @@ struct alignas(64) HaloArgs {
   int32_t sub_lines, sub_x;        // epilogue: line / x offset of sub-tile 1
   int32_t hw;                      // halo line pitch (rows)
   uint32_t halo_bytes, halo_stride;
-  int32_t a_stages, b_stages;
+  int32_t a_stages, b_stages, tps;  // tps: filter taps (weight tiles) per weight-ring stage
   int32_t kc, n_pad, bn_tile, tmem_cols, dbuf, k_tail;
   int32_t num_phases, splits, stagger, dbg_skip;
   int32_t group_begin[9];
@@ -506,16 +506,22 @@ __global__ void __launch_bounds__(256, 1) igemm_halo_kernel(const __grid_constan
           const int t0 = a.groups[g].tap_begin, t1 = a.groups[g].tap_end;
           int t = t0 + static_cast<int>(rot % static_cast<uint32_t>(t1 - t0));
 #pragma unroll 1
-          for (int i = t0; i < t1; ++i) {
+          for (int i = t0; i < t1; i += a.tps) {
+            // a stage holds the weight tiles of `tps` consecutive taps: one barrier round trip per stage, not per tap
+            const int nt = min(a.tps, t1 - i);
             mbar_wait_addr(be0 + st * 8, ph ^ 1);
             if (DBG && (a.dbg_skip & 2)) {
               mbar_arrive_addr(bf0 + st * 8);     // timing experiment: no weight loads (wrong results)
+              for (int j = 0; j < nt; ++j) if (++t == t1) t = t0;
             } else {
-              mbar_expect_tx_addr(bf0 + st * 8, b_bytes);
-              tma_load_2d_addr(bring0 + st * b_bytes, &a.bmap, bf0 + st * 8, c * 32, a.tap_wslot[t] * a.n_pad + n0);
+              mbar_expect_tx_addr(bf0 + st * 8, static_cast<uint32_t>(nt) * b_bytes);
+              for (int j = 0; j < nt; ++j) {
+                tma_load_2d_addr(bring0 + (st * static_cast<uint32_t>(a.tps) + j) * b_bytes, &a.bmap, bf0 + st * 8, c * 32,
+                                 a.tap_wslot[t] * a.n_pad + n0);
+                if (++t == t1) t = t0;
+              }
             }
             if (++st == static_cast<uint32_t>(a.b_stages)) { st = 0; ph ^= 1; }
-            if (++t == t1) t = t0;
           }
           if (++c == a.kc) { c = 0; ++g; }
         }
@@ -534,7 +540,7 @@ __global__ void __launch_bounds__(256, 1) igemm_halo_kernel(const __grid_constan
       const uint64_t bd_base = make_smem_desc(bring0, 16, 1024, 0);
       const uint32_t af0 = opaque_u32(smem_u32(&a_full[0])), ae0 = opaque_u32(smem_u32(&a_empty[0]));
       const uint32_t bf0 = opaque_u32(smem_u32(&b_full[0])), be0 = opaque_u32(smem_u32(&b_empty[0]));
-      const uint32_t a_adv = a.halo_stride >> 4, b_adv = b_bytes >> 4;
+      const uint32_t a_adv = a.halo_stride >> 4, b_adv = b_bytes >> 4, b_stage_adv = b_adv * static_cast<uint32_t>(a.tps);
       const uint32_t sub_off = sub * static_cast<uint32_t>(a.sub_off);
       uint32_t ast = 0, aph = 0, bst = 0, bph = 0;
       int ti = 0;
@@ -562,21 +568,25 @@ __global__ void __launch_bounds__(256, 1) igemm_halo_kernel(const __grid_constan
           const int t0 = a.groups[g].tap_begin, t1 = a.groups[g].tap_end;
           int t = t0 + static_cast<int>(rot % static_cast<uint32_t>(t1 - t0));
 #pragma unroll 1
-          for (int i = t0; i < t1; ++i) {
+          for (int i = t0; i < t1; i += a.tps) {
+            const int nt = min(a.tps, t1 - i);
             if (DBG) c0 = clock64();
             mbar_wait_addr(bf0 + bst * 8, bph);
             if (DBG) w_b += clock64() - c0;
             tc_fence_after();
-            const uint64_t ad = ad_s + static_cast<uint32_t>(a.tap_aoff[t]) * 8u;    // rows * 128 B >> 4
-            const uint64_t bd = bd_base + bst * b_adv;
-            umma_tf32(d0, ad, bd, idesc, accum);
-            if (nk > 1) umma_tf32(d0, ad + 2, bd + 2, idesc, 1u);
-            if (nk > 2) umma_tf32(d0, ad + 4, bd + 4, idesc, 1u);
-            if (nk > 3) umma_tf32(d0, ad + 6, bd + 6, idesc, 1u);
+            uint64_t bd = bd_base + bst * b_stage_adv;
+#pragma unroll 1
+            for (int j = 0; j < nt; ++j, bd += b_adv) {
+              const uint64_t ad = ad_s + static_cast<uint32_t>(a.tap_aoff[t]) * 8u;    // rows * 128 B >> 4
+              umma_tf32(d0, ad, bd, idesc, accum);
+              if (nk > 1) umma_tf32(d0, ad + 2, bd + 2, idesc, 1u);
+              if (nk > 2) umma_tf32(d0, ad + 4, bd + 4, idesc, 1u);
+              if (nk > 3) umma_tf32(d0, ad + 6, bd + 6, idesc, 1u);
+              accum = 1u;
+              if (++t == t1) t = t0;
+            }
             umma_commit_addr(be0 + bst * 8);
-            accum = 1u;
             if (++bst == static_cast<uint32_t>(a.b_stages)) { bst = 0; bph ^= 1; }
-            if (++t == t1) t = t0;
           }
           umma_commit_addr(ae0 + ast * 8);
           if (++ast == static_cast<uint32_t>(a.a_stages)) { ast = 0; aph ^= 1; }
@@ -1237,6 +1247,10 @@ static int conv_halo_try(const vp_tensor* in, const vp_conv_geom* g, const float
   if (const char* e = getenv("VP_HALO_SKIP")) A.dbg_skip = atoi(e);
   if (A.b_stages < 3 && !getenv("VP_HALO_BSTAGES")) return 1;
   if (b_budget - A.b_stages * static_cast<long long>(b_bytes) >= static_cast<long long>(A.halo_stride) && A.b_stages >= 6) A.a_stages = 3;
+  // two taps per weight stage when at least three such stages fit: halves the barrier round trips of the issuing threads
+  A.tps = A.b_stages >= 6 ? 2 : 1;
+  if (const char* e = getenv("VP_HALO_TPS")) { const int v = atoi(e); if (v == 1 || (v == 2 && A.b_stages >= 4)) A.tps = v; }
+  A.b_stages /= A.tps;
   // split the (group, chunk) items over CTAs when the grid would leave SMs idle
   const int m_tiles = A.tiles_w * A.tiles_h * A.tiles_d * A.tiles_n;
   const int n_tiles = n_pad / A.bn_tile;
@@ -1283,7 +1297,7 @@ static int conv_halo_try(const vp_tensor* in, const vp_conv_geom* g, const float
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return set_error("cuTensorMapEncodeTiled(weights) failed with %d", static_cast<int>(r));
   }
-  const size_t smem = static_cast<size_t>(A.a_stages) * A.halo_stride + static_cast<size_t>(A.b_stages) * b_bytes + 1024;
+  const size_t smem = static_cast<size_t>(A.a_stages) * A.halo_stride + static_cast<size_t>(A.b_stages) * A.tps * b_bytes + 1024;
   static bool attr_set = false;
   if (!attr_set) {
     if (cudaFuncSetAttribute(igemm_halo_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_max)) != cudaSuccess ||
