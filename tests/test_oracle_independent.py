@@ -177,3 +177,55 @@ def test_two_unrolled_steps_match_the_oracle():
         merr = np.abs(masks - ref['masks'][t].numpy()[..., 0, :]).max()
         assert merr < 1e-9, 'step %d masks: %g' % (t, merr)
     assert not bool(gt[1][0])                                                # the second step consumed the first step's output
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# video discriminator (networks.video_sn_discriminator, networks.py:72-108): zero pad 1 on T, H, W, VALID conv3d, leaky relu
+# 0.1, spectrally normalised kernels (one power iteration from the stored u, ops.py:1020-1049), dense logit; LSGAN loss.
+def conv3d_valid(x, w, strides):
+    kd, kh, kw, _, co = w.shape
+    sd, sh, sw = strides
+    B, D, H, W, _ = x.shape
+    Do, Ho, Wo = (D - kd) // sd + 1, (H - kh) // sh + 1, (W - kw) // sw + 1
+    out = np.zeros((B, Do, Ho, Wo, co))
+    for a in range(kd):
+        for i in range(kh):
+            for j in range(kw):
+                out += x[:, a:a + (Do - 1) * sd + 1:sd, i:i + (Ho - 1) * sh + 1:sh, j:j + (Wo - 1) * sw + 1:sw, :] @ w[a, i, j]
+    return out
+
+
+def sn_weight(W, u):
+    Wr = W.reshape(-1, W.shape[-1])
+    v = u @ Wr.T
+    v = v / (np.linalg.norm(v) + 1e-12)
+    u1 = v @ Wr
+    u1 = u1 / (np.linalg.norm(u1) + 1e-12)
+    return W / (v @ Wr @ u1.T).item(), u1
+
+
+def test_video_discriminator_and_lsgan_loss_match_the_oracle():
+    ndf, scope = 4, 'discriminator/video/encoder'
+    T, B, H, W, C = 5, 2, 16, 16, 3
+    clips = torch.rand(T, B, H, W, C, dtype=torch.float64, generator=torch.Generator().manual_seed(11))
+    V = O.Vars(rng=np.random.RandomState(7), dtype=torch.float64)          # variables created by the oracle call (reference initialisers)
+    u_out = {}
+    with torch.no_grad():
+        O.video_sn_discriminator(V, scope, clips, ndf)                      # creates the variables
+        for k in V.params:                                                  # non-trivial biases
+            if k.endswith('/bias'):
+                V.params[k] = V.params[k] + 0.1 * torch.randn(V.params[k].shape, dtype=torch.float64, generator=torch.Generator().manual_seed(len(k)))
+        feats, logits = O.video_sn_discriminator(V, scope, clips, ndf, u_out=u_out)
+    P = {k: v.detach().numpy() for k, v in V.params.items()}
+    x = clips.numpy().transpose(1, 0, 2, 3, 4)
+    for li, (name, mult, k, strides) in enumerate(O.VIDEO_D_LAYERS):
+        Wb, u1 = sn_weight(P['%s/%s/conv3d/kernel' % (scope, name)], P['%s/%s/conv3d/u' % (scope, name)])
+        assert np.abs(u1 - u_out['%s/%s/conv3d/u' % (scope, name)].numpy()).max() < 1e-12
+        y = conv3d_valid(np.pad(x, ((0, 0), (1, 1), (1, 1), (1, 1), (0, 0))), Wb, strides) + P['%s/%s/conv3d/bias' % (scope, name)]
+        x = np.maximum(0.1 * y, y)
+        assert x.shape == tuple(feats[li].shape) and np.abs(x - feats[li].numpy()).max() < 1e-9, name
+    Wb, _ = sn_weight(P['%s/sn_fc4/dense/kernel' % scope], P['%s/sn_fc4/dense/u' % scope])
+    lg = x.reshape(B, -1) @ Wb + P['%s/sn_fc4/dense/bias' % scope]
+    assert np.abs(lg - logits.numpy()).max() < 1e-9
+    # losses.gan_loss LSGAN (losses.py:29-54): mean (logit - label)^2
+    assert abs(float(O.gan_loss(logits, 1.0, 'LSGAN')) - float(((lg - 1.0) ** 2).mean())) < 1e-12
