@@ -326,3 +326,42 @@ def test_full_length_generator_matches_oracle(Model, name, hk, B, shape, A):
             e = (model.outputs[k].cpu() - refs[None][k].permute(1, 0, 2, 3, 4)).abs().max().item()
             print('%s %s [exact]: max-abs vs fp32 oracle %.2e' % (name, k, e))
             assert e <= 1e-4, (name, k, e)
+
+
+# ---------------------------------------------------------------------------------------------- graph replay vs eager
+def test_captured_step_reproduces_the_eager_step(Model, tmp_path):
+    """The step bench.py times is ONE captured CUDA graph with parallel branches (discriminator towers, spectral norm + packing
+    under the generator forward).  From the same checkpoint and batch: the eager step, a captured replay and a second replay
+    must produce the same losses and gradients up to what summation-order noise becomes in TF32 arithmetic (atomics in split-K
+    and the weight gradients reorder fp32 sums; downstream truncations to TF32 flip, profiles/r02_parity_noise_floor.md):
+    measured 7e-4 / 1e-3 between two replays and 9e-3 / 3e-3 between the graph and the eager step (G / D gradients).  A step
+    that is not executed at capture time (the bug this test found), a stale buffer or a race between branches shows as O(1)."""
+    import make_golden_b16 as G
+    hp, params, inputs, noise = G.case()
+    binp = {'images': inputs['images'].permute(1, 0, 2, 3, 4)}
+    grads = {}
+    for how in ('eager', 'graph'):
+        model = Model(mode='train', hparams_dict=G.HK)
+        model.set_params(params)
+        model.build_graph(binp)
+        model.use_cuda_graph = how == 'graph'
+        model.train_step(binp)                                   # step 0 (always eager; the graph is captured afterwards)
+        ck = model.save(str(tmp_path / how))
+        runs = []
+        for rep in range(2 if how == 'graph' else 1):
+            model.restore(None, ck)
+            assert model.global_step == 1
+            model.train_step(binp)
+            torch.cuda.synchronize()
+            assert (model._graph is not None) == (how == 'graph')
+            runs.append((model.g_grad.clone(), model.d_grad.clone(), model.loss_vals.clone()))
+        grads[how] = runs
+
+    def rel(a, b):
+        return ((a - b).double().norm() / b.double().norm()).item()
+    (g0, d0, l0), (g1, d1, l1) = grads['graph']
+    ge, de, le = grads['eager'][0]
+    errs = dict(replay_vs_replay=(rel(g0, g1), rel(d0, d1), rel(l0, l1)), graph_vs_eager=(rel(g0, ge), rel(d0, de), rel(l0, le)))
+    print('captured-step reproducibility (relative L2 of the flat G / D gradients, loss vector):', errs)
+    assert max(errs['replay_vs_replay'][:2]) < 5e-3 and errs['replay_vs_replay'][2] < 1e-3, errs
+    assert max(errs['graph_vs_eager'][:2]) < 3e-2 and errs['graph_vs_eager'][2] < 1e-3, errs

@@ -628,6 +628,7 @@ class TrainMixin(object):
                     with torch.cuda.graph(g):
                         self._step_device(allreduce)
                     self._graph = g
+                    g.replay()               # capturing only records: this step still has to run
                 except Exception as ex:      # noqa: BLE001  (e.g. a collective that cannot be captured): stay eager
                     import sys
                     sys.stderr.write('CUDA graph capture failed (%s); continuing with eager launches\n' % ex)
