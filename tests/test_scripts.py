@@ -164,3 +164,56 @@ def test_train_on_bair_format_tfrecords_with_actions(tmp_path):
     assert model.global_step == 2 and np.isfinite(model.g_loss) and np.isfinite(model.d_loss)
     assert model.hparams.repeat == 2 and model.hparams.sequence_length == 6          # time_shift of the BAIR dataset (train.py:160)
     assert model.A == 4                                                              # actions reached the model
+
+
+REFERENCE_EVALUATE_FLAGS = ['--input_dir', '--results_dir', '--output_dir', '--checkpoint', '--mode', '--dataset', '--dataset_hparams',
+                            '--model', '--model_hparams', '--batch_size', '--num_samples', '--num_epochs', '--eval_substasks',
+                            '--only_metrics', '--num_stochastic_samples', '--gt_inputs_dir', '--gt_outputs_dir',
+                            '--eval_parallel_iterations', '--gpu_mem_frac', '--seed']
+
+
+def test_evaluate_accepts_the_reference_argument_set_and_writes_its_csv_layout(tmp_path):
+    import evaluate
+    flags = {a.option_strings[0]: a for a in evaluate.build_parser()._actions if a.option_strings}
+    assert set(REFERENCE_EVALUATE_FLAGS) <= set(flags)                       # /root/reference/scripts/evaluate.py:143-175
+    assert flags['--num_stochastic_samples'].default == 100 and flags['--eval_substasks'].default == ['max', 'avg', 'min']
+    assert flags['--mode'].choices == ['val', 'test'] and flags['--seed'].default == 7
+    with pytest.raises(ValueError):
+        evaluate.resolve_options(evaluate.build_parser().parse_args(['--input_dir', 'x', '--model', 'savp']))
+    a = evaluate.build_parser().parse_args(['--input_dir', 'x', '--model', 'savp', '--dataset', 'synthetic', '--results_dir', str(tmp_path)])
+    evaluate.resolve_options(a)
+    assert a.output_dir == os.path.join(str(tmp_path), 'model.savp')
+    # metrics files: header + appended batches, read back without index / mean columns (evaluate.py:44-66)
+    m0, m1 = np.arange(6, dtype=np.float32).reshape(2, 3), np.arange(6, 12, dtype=np.float32).reshape(2, 3)
+    fname = str(tmp_path / 'task' / 'metrics' / 'psnr')
+    evaluate.save_metrics(fname, m0, 0)
+    evaluate.save_metrics(fname, m1, 2)
+    rows = open(fname + '.csv').read().splitlines()
+    assert rows[0].split('\t') == ['sample_ind', '0', '1', '2', 'mean'] and rows[3].split('\t')[0] == '2' and len(rows) == 5
+    assert np.array_equal(evaluate.load_metrics(fname), np.concatenate([m0, m1]))
+
+
+@pytest.mark.gpu
+def test_evaluate_best_of_n_on_a_trained_checkpoint(tmp_path):
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip('no CUDA device')
+    import train
+    import evaluate
+    out = str(tmp_path / 'run')
+    train.main(['--input_dir', 'none', '--dataset', 'synthetic', '--dataset_hparams', 'sequence_length=6,num_examples=8', '--model', 'savp',
+                '--output_dir', out, '--progress_freq', '0', '--save_freq', '2', '--seed', '1',
+                '--model_hparams', 'batch_size=2,max_steps=2,clip_length=4,l1_weight=100.0,kl_weight=1.0,video_sn_gan_weight=0.1'])
+    res = str(tmp_path / 'results')
+    summary = evaluate.main(['--input_dir', 'none', '--checkpoint', out, '--mode', 'test', '--results_dir', res, '--batch_size', '2',
+                             '--num_samples', '4', '--num_stochastic_samples', '3'])
+    assert set(summary) == {'psnr', 'ssim', 'mse'} and all(np.isfinite(v) for v in summary.values())
+    base = os.path.join(res, 'run')
+    for metric in ('psnr', 'ssim', 'mse'):
+        best = evaluate.load_metrics(os.path.join(base, 'prediction_eval_%s_max' % metric, 'metrics', metric))
+        avg = evaluate.load_metrics(os.path.join(base, 'prediction_eval_%s_avg' % metric, 'metrics', metric))
+        worst = evaluate.load_metrics(os.path.join(base, 'prediction_eval_%s_min' % metric, 'metrics', metric))
+        assert best.shape == (4, 4)                                          # 4 videos x 4 future frames
+        assert (best.mean(1) >= avg.mean(1) - 1e-6).all() and (avg.mean(1) >= worst.mean(1) - 1e-6).all()
+    pngs = os.listdir(os.path.join(base, 'prediction_eval_psnr_max', 'outputs'))
+    assert len(pngs) == 4 * 4 and len(os.listdir(os.path.join(base, 'prediction_eval_psnr_max', 'inputs'))) == 4 * 2
