@@ -2,8 +2,9 @@
 """Sampling driver with the reference's command line (scripts/generate.py:19-49) on the B200 SAVP path: restores a
 checkpoint written by scripts/train.py, runs the generator in test mode (prior unroll, no discriminators) for
 `--num_stochastic_samples` noise draws per batch, and writes the predicted future frames as PNGs
-(`gen_image_%05d_%02d_%02d.png`, generate.py:183-190).  GIF output needs ffmpeg (absent here): the frames of every sample
-are written to `<output_gif_dir>/gen_image_%05d_%02d.npy` instead, [context + future, H, W, C] uint8."""
+(`gen_image_%05d_%02d_%02d.png`, generate.py:183-190) and, per sample, the context + future frames as an animated GIF
+`<output_gif_dir>/gen_image_%05d_%02d.gif` at `--fps` (generate.py:176-181; written with PIL instead of the reference's
+moviepy / ffmpeg) next to the same frames as `gen_image_%05d_%02d.npy`, [context + future, H, W, C] uint8."""
 from __future__ import absolute_import, division, print_function
 
 import argparse
@@ -85,6 +86,17 @@ def resolve_options(args):
     return dataset_hparams_dict, model_hparams_dict
 
 
+def save_gif(path, frames, fps):
+    """Animated GIF of uint8 frames [H,W,C] (C = 1 or 3); utils/ffmpeg_gif.py:save_gif in the reference."""
+    try:
+        from PIL import Image
+    except ImportError:                               # the frame stack (.npy) is still written
+        return False
+    imgs = [Image.fromarray(f[..., 0] if f.shape[-1] == 1 else f) for f in frames]
+    imgs[0].save(path, save_all=True, append_images=imgs[1:], duration=int(round(1000.0 / max(fps, 1))), loop=0)
+    return True
+
+
 def main(argv=None):
     args = build_parser().parse_args(argv)
     if args.seed is not None:
@@ -152,8 +164,9 @@ def main(argv=None):
                 context_and_gen_images = list(context_images_[:context_frames]) + list(gen_images_)
                 if args.gif_length:
                     context_and_gen_images = context_and_gen_images[:args.gif_length]
-                np.save(os.path.join(args.output_gif_dir, 'gen_image_%05d_%02d.npy' % (sample_ind + i, stochastic_sample_ind)),
-                        np.stack(context_and_gen_images))
+                stem = os.path.join(args.output_gif_dir, 'gen_image_%05d_%02d' % (sample_ind + i, stochastic_sample_ind))
+                np.save(stem + '.npy', np.stack(context_and_gen_images))
+                save_gif(stem + '.gif', context_and_gen_images, args.fps)
                 pattern = 'gen_image_%%05d_%%02d_%%0%dd.png' % max(2, len(str(len(gen_images_) - 1)))
                 for t, gen_image in enumerate(gen_images_):
                     if gen_image.shape[-1] == 1:

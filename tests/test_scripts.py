@@ -96,6 +96,9 @@ def test_train_three_steps_checkpoint_resume_and_generate(tmp_path):
     png_dir = str(tmp_path / 'results' / 'run')
     pngs = [p for p in os.listdir(png_dir) if p.endswith('.png')]
     assert len(pngs) == 2 * 2 * 4                                           # samples x stochastic samples x future frames
+    from PIL import Image
+    gif = Image.open(os.path.join(png_dir, 'gen_image_00000_00.gif'))
+    assert gif.n_frames == 6 and gif.size == (64, 64)                       # context + future frames, --fps 4
     a = np.load(os.path.join(png_dir, 'gen_image_00000_00.npy'))
     b = np.load(os.path.join(png_dir, 'gen_image_00000_01.npy'))
     assert a.shape == (6, 64, 64, 3) and a.dtype == np.uint8
