@@ -17,6 +17,7 @@
 
 #include <cstdlib>
 #include <map>
+#include <mutex>
 #include <tuple>
 
 #include "common.h"
@@ -578,6 +579,8 @@ struct SlabPlan { int cs, ppc, lanes, iters; };
 
 static int max_active_clusters(const void* kernel, int cs, int threads, size_t smem) {
   static std::map<std::tuple<const void*, int, int, size_t>, int> cache;
+  static std::mutex cache_mutex;                       // ctypes releases the GIL: the C ABI may be entered from several host threads
+  std::lock_guard<std::mutex> lock(cache_mutex);
   const auto key = std::make_tuple(kernel, cs, threads, smem);
   auto it = cache.find(key);
   if (it != cache.end()) return it->second;
