@@ -12,7 +12,12 @@
 // s_d*s_h*s_w "parity" sub-lattices of the input (one tensor map each); transposed convolutions
 // (upsample_conv2d forward, dgrad of strided convs) are split into output phases.
 //
-// Warp roles (224 threads; wgrad 192): warp 0 (+ warp 6 in the forward kernel: weights) = TMA producer, warp 1 = TMEM allocator + single-thread MMA
+// Two forward / dgrad kernels compute the same convolution (the host layer times both per geometry): BOX mode above, and HALO
+// mode (igemm_halo_kernel): M = 256 per CTA as two 128-row sub-tiles, one halo tile per (tap group, 32-channel chunk) on which
+// every tap is a shifted K-major descriptor, weight tiles shared by both sub-tiles (two taps per ring stage), one MMA-issuing
+// thread per sub-tile.  Weight gradients: row mode (one x halo tile per kernel row) and tap-group mode (merged-tap wide-N MMAs).
+//
+// Warp roles (224 threads; wgrad 192; halo 256): warp 0 (+ warp 6 in the forward kernel: weights) = TMA producer, warp 1 = TMEM allocator + single-thread MMA
 // issuer, warps 2..5 = epilogue (TMEM -> registers -> bias/activation -> global).
 #include <cstdio>
 #include <cstdlib>
